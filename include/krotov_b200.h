@@ -1,0 +1,161 @@
+/* krotov_b200.h -- C ABI of libkrotov_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the Krotov sweep hot path of qucontrol/krotov.  The
+ * reference has no FFI: its boundary is the keyword plugin API of
+ * krotov.optimize_pulses (src/krotov/optimize.py:33-55), whose per-time-step
+ * Python work this library replaces:
+ *
+ *   kq_propagate_forward     <- _forward_propagation        optimize.py:806-846
+ *   kq_sweep_backward        <- _backward_propagation       optimize.py:849-886
+ *   kq_sweep_forward_update  <- update + fw-step loop       optimize.py:449-500
+ *                               (mu: mu.py:74-140, overlap: second_order.py:69-83,
+ *                                propagators.expm: propagators.py:79-122,
+ *                                plug_in_pulse_values: conversions.py:288-330)
+ *   kq_chi_boundary          <- chi_constructor + norm      optimize.py:404-410,
+ *                               functionals.py:177-197,225-253,293-317,389-437
+ *   kq_overlaps              <- tau_vals                    optimize.py:316-322,503-508
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (torch tensors on
+ *    the Python side); the library never allocates or frees user data.  The
+ *    only exception is kq_comm setup, which takes host arrays of device
+ *    pointers.
+ *  - complex128 = two consecutive doubles (re, im) ("kq_c128").
+ *  - Every function is asynchronous with respect to `stream` (a cudaStream_t
+ *    passed as void*), returns 0 on success and a negative kq_status on
+ *    error; kq_last_error() returns a thread-local message.  No exception
+ *    crosses the ABI.  No hidden global state besides that message and
+ *    per-device constant tables.
+ *  - States are vectors of length N: kets, or column-stacked density
+ *    matrices when `is_super` is set.
+ *
+ * Layouts (row = slowest index first)
+ *   ops, ops_adj : [K][M][N*N], matrix element (r,c) at c*N + r (column-major)
+ *                  term 0..M-1 of objective k's generator; ops_adj holds the
+ *                  element-wise adjoint (backward generator).
+ *   mu           : [K][L][N*N] column-major, dH/d eps_l (already times i for
+ *                  super-operators, mu.py:130-132); zero matrix if pulse l does
+ *                  not drive objective k.
+ *   term2pulse   : [K][M] int32: -1 = drift (coefficient 1), l>=0 = pulse l,
+ *                  -2 = padding (coefficient 0).
+ *   op_norm      : [K][M] upper bound of the 1-norm of each term (used to pick
+ *                  the Taylor degree / scaling of exp(A dt) v).
+ *   dt           : [NT]  tlist[n+1]-tlist[n]
+ *   shape        : [L][NT] update shape S_l on the intervals, in [0,1]
+ *   lambda_a     : [L]
+ *   pulses       : [L][NT] float64
+ *   state stores : [NT+1][K][N] complex128 (time-major)
+ */
+#ifndef KROTOV_B200_H
+#define KROTOV_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } kq_c128;
+
+typedef enum {
+  KQ_OK = 0,
+  KQ_ERR_ARG = -1,        /* invalid argument / unsupported size */
+  KQ_ERR_CUDA = -2,       /* CUDA runtime error (message has details) */
+  KQ_ERR_UNSUPPORTED = -3,/* configuration outside the built kernels */
+  KQ_ERR_EXCHANGE = -4    /* cross-CTA / cross-GPU exchange timed out */
+} kq_status;
+
+typedef struct {
+  int32_t K;          /* objectives held by this rank */
+  int32_t N;          /* state length */
+  int32_t NT;         /* number of time intervals (nt - 1) */
+  int32_t L;          /* number of pulses */
+  int32_t M;          /* generator terms per objective (padded) */
+  int32_t is_super;   /* 0: d/dt psi = -i H psi ; 1: d/dt rho = L rho */
+  const kq_c128* ops;
+  const kq_c128* ops_adj;
+  const kq_c128* mu;
+  const int32_t* term2pulse;
+  const double*  op_norm;
+  const double*  dt;
+  const double*  shape;
+  const double*  lambda_a;
+} kq_problem;
+
+/* Cross-GPU exchange descriptor for the per-time-step reduction of the pulse
+ * update (optimize.py:454-470 sums over ALL objectives).  NULL = single GPU.
+ * slots[r] is rank r's exchange buffer (kq_comm_slot_bytes() bytes, zeroed
+ * once) mapped into this process (CUDA IPC / symmetric memory); every rank
+ * writes its partial sums into every peer's buffer and reads only its own. */
+typedef struct {
+  int32_t rank;
+  int32_t world;
+  void* const* slots;   /* DEVICE array of `world` device pointers */
+} kq_comm;
+
+/* chi_constructor kinds lowered to the device (functionals.py). */
+enum { KQ_CHI_RE = 0, KQ_CHI_SS = 1, KQ_CHI_SM = 2, KQ_CHI_HS = 3 };
+
+int kq_version(void);
+const char* kq_last_error(void);
+
+/* Bytes of zero-initialised device workspace kq_sweep_forward_update needs
+ * (status word + cross-CTA exchange slots). */
+size_t kq_workspace_bytes(const kq_problem* p);
+size_t kq_comm_slot_bytes(const kq_problem* p);
+
+/* Forward propagation over the whole grid under `pulses`:
+ * store[0] = state0, store[n+1] = exp(f A_n dt_n) store[n]; stateT = final.
+ * `store` and `stateT` may be NULL (not both). */
+int kq_propagate_forward(const kq_problem* p, const double* pulses,
+                         const kq_c128* state0, kq_c128* stateT,
+                         kq_c128* store, void* stream);
+
+/* Backward propagation of chiT (already normalised) under the adjoint
+ * generator: X[NT] = chiT, X[n] = exp(conj(f) A^dag_n dt_n) X[n+1]. */
+int kq_sweep_backward(const kq_problem* p, const double* guess_pulses,
+                      const kq_c128* chiT, kq_c128* X, void* stream);
+
+/* Fused sequential sweep: for n = 0..NT-1
+ *   d_l   = Im sum_k [ chi_norms[k] <X[n][k]| mu_lk |phi_k>
+ *                      + 0.5 sigma[n] <dphi_k| mu_lk |phi_k> ]
+ *   opt_l[n] = guess_l[n] + (S_l[n]/lambda_l) d_l ;  g_a[l] += (S/lambda) d_l^2 dt
+ *   phi_k <- exp(f A_k(opt[:,n]) dt_n) phi_k ; dphi_k = phi_k - Phi0[n+1][k]
+ * sigma/Phi0/Phi1 NULL = first order.  Phi1 (if given) receives all forward
+ * states.  g_a is overwritten.  `workspace` = kq_workspace_bytes() zeroed
+ * bytes, `epoch` must increase by one with every call sharing a workspace. */
+int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses,
+                            double* opt_pulses, const kq_c128* X,
+                            const double* chi_norms, const kq_c128* phi0,
+                            kq_c128* phiT, const double* sigma,
+                            const kq_c128* Phi0, kq_c128* Phi1, double* g_a,
+                            const kq_comm* comm, void* workspace,
+                            uint32_t epoch, void* stream);
+
+/* Boundary condition chi_k(T) for the built-in functionals, followed by the
+ * normalisation of optimize.py:407-410 (L2 / Frobenius norm):
+ * chi_out[k] = chi_k/||chi_k||, chi_norms[k] = ||chi_k||.
+ * weights may be NULL (all 1).  K_total = number of objectives over all
+ * ranks (the 1/N prefactors of functionals.py use the global count);
+ * tau_sum = sum_j w_j tau_j over ALL objectives for KQ_CHI_SM (device pointer
+ * to one complex value), ignored otherwise. */
+int kq_chi_boundary(const kq_problem* p, int kind, int32_t K_total,
+                    const kq_c128* phiT, const kq_c128* targets,
+                    const kq_c128* tau, const double* weights,
+                    const kq_c128* tau_sum, kq_c128* chi_out,
+                    double* chi_norms, void* stream);
+
+/* out[k] = <a_k | b_k> for K vectors of length N (tau_vals). */
+int kq_overlaps(int32_t K, int32_t N, const kq_c128* a, const kq_c128* b,
+                kq_c128* out, void* stream);
+
+/* Introspection for tests / bench: kernel family chosen for a problem
+ * (0 = thread-per-objective, 1 = lane-per-row) and its launch geometry. */
+int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid,
+            int32_t* block, int32_t* smem_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KROTOV_B200_H */

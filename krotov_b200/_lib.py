@@ -1,0 +1,137 @@
+"""ctypes binding of ``libkrotov_b200.so`` (C ABI in ``include/krotov_b200.h``).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (plain
+``nvcc -shared`` for sm_100a, no torch headers).  There is NO fallback: if the
+library is missing or a CUDA device is unavailable the engine raises
+:class:`EngineUnavailable` -- the sweeps never run on the CPU.
+"""
+import ctypes
+import os
+import subprocess
+
+__all__ = ['load', 'EngineUnavailable', 'KqError', 'KqProblem', 'KqComm',
+           'LIB_PATH', 'build_library', 'check']
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB_PATH = os.path.join(CSRC, 'libkrotov_b200.so')
+INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+    '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
+]
+
+
+class EngineUnavailable(RuntimeError):
+    """The CUDA library or device required by the sweep engine is missing."""
+
+
+class KqError(RuntimeError):
+    """An ABI call returned a negative status."""
+
+
+class KqProblem(ctypes.Structure):
+    """Mirror of ``kq_problem`` (include/krotov_b200.h)."""
+    _fields_ = [
+        ('K', ctypes.c_int32), ('N', ctypes.c_int32), ('NT', ctypes.c_int32),
+        ('L', ctypes.c_int32), ('M', ctypes.c_int32),
+        ('is_super', ctypes.c_int32),
+        ('ops', ctypes.c_void_p), ('ops_adj', ctypes.c_void_p),
+        ('mu', ctypes.c_void_p), ('term2pulse', ctypes.c_void_p),
+        ('op_norm', ctypes.c_void_p), ('dt', ctypes.c_void_p),
+        ('shape', ctypes.c_void_p), ('lambda_a', ctypes.c_void_p),
+    ]
+
+
+class KqComm(ctypes.Structure):
+    """Mirror of ``kq_comm``."""
+    _fields_ = [('rank', ctypes.c_int32), ('world', ctypes.c_int32),
+                ('slots', ctypes.c_void_p)]
+
+
+_SIGNATURES = {
+    'kq_version': (ctypes.c_int, []),
+    'kq_last_error': (ctypes.c_char_p, []),
+    'kq_workspace_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
+    'kq_comm_slot_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
+    'kq_propagate_forward': (ctypes.c_int, [
+        ctypes.POINTER(KqProblem), ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'kq_sweep_backward': (ctypes.c_int, [
+        ctypes.POINTER(KqProblem), ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p]),
+    'kq_sweep_forward_update': (ctypes.c_int, [
+        ctypes.POINTER(KqProblem), ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.POINTER(KqComm), ctypes.c_void_p, ctypes.c_uint32,
+        ctypes.c_void_p]),
+    'kq_chi_boundary': (ctypes.c_int, [
+        ctypes.POINTER(KqProblem), ctypes.c_int, ctypes.c_int32,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'kq_overlaps': (ctypes.c_int, [
+        ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p]),
+    'kq_plan': (ctypes.c_int, [
+        ctypes.POINTER(KqProblem), ctypes.POINTER(ctypes.c_int32),
+        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+        ctypes.POINTER(ctypes.c_int32)]),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def build_library(verbose=False):
+    """Compile ``csrc/kq_abi.cu`` into ``csrc/libkrotov_b200.so`` for
+    sm_100a.  nvcc cross-compiles without a GPU."""
+    src = os.path.join(CSRC, 'kq_abi.cu')
+    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                    if f.endswith('.cuh')]
+    deps.append(os.path.join(INCLUDE, 'krotov_b200.h'))
+    if os.path.exists(LIB_PATH) and all(
+            os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH, src]
+    if verbose:
+        print(' '.join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+def load():
+    """Load the library (once) and declare every entry point's signature.
+
+    Raises:
+        EngineUnavailable: the shared library has not been built.
+    """
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineUnavailable(
+            "%s not found: build it with `python -c 'import __graft_entry__ "
+            "as g; g.build()'` (needs nvcc). krotov_b200 has no CPU fallback."
+            % LIB_PATH)
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as exc:
+        raise EngineUnavailable("cannot load %s: %s" % (LIB_PATH, exc))
+    for name, (restype, argtypes) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status):
+    """Raise :class:`KqError` with the library's message if `status` < 0."""
+    if status != 0:
+        msg = load().kq_last_error()
+        raise KqError("libkrotov_b200 error %d: %s"
+                      % (status, msg.decode() if msg else '?'))

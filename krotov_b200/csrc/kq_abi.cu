@@ -1,0 +1,482 @@
+// C ABI of libkrotov_b200.so: argument checking, launch planning and kernel
+// dispatch for the Krotov sweep hot path (see include/krotov_b200.h for the
+// reference call sites each entry point replaces).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/krotov_b200.h"
+#include "kq_common.cuh"
+#include "kq_small.cuh"
+#include "kq_warp.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define KQ_CUDA(call)                                                              \
+  do {                                                                             \
+    cudaError_t e_ = (call);                                                       \
+    if (e_ != cudaSuccess)                                                         \
+      return fail(KQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                             \
+  } while (0)
+
+constexpr int kMaxDevices = 64;
+constexpr int kMaxBlocks = 4096;   // exchange slots are sized for this many CTAs
+constexpr int kMaxWorld = 16;
+constexpr size_t kStatusBytes = 256;
+constexpr size_t kSmemBudget = 200 * 1024;
+
+struct DeviceInfo {
+  bool ready = false;
+  int sms = 0;
+  int max_smem_optin = 0;
+  int coop = 0;
+};
+DeviceInfo g_dev[kMaxDevices];
+std::mutex g_mu;
+
+// Taylor degree per binade: smallest m with  b^(m+1)/(m+1)! <= 2^-56,
+// b = min(1, 2^-bin) the largest scaled norm in the bin.
+void build_tables(KqTables& T) {
+  const double tol = std::ldexp(1.0, -56);
+  for (int bin = 0; bin < KQ_TAYLOR_BINS; ++bin) {
+    const double b = std::ldexp(1.0, -bin);
+    double term = b;  // b^1/1!
+    int m = 0;        // term = b^(m+1)/(m+1)!
+    while (term > tol && m < KQ_TAYLOR_MAXM) {
+      ++m;
+      term *= b / (double)(m + 1);
+    }
+    T.m_of_bin[bin] = m < 1 ? 1 : m;
+  }
+  T.inv[0] = 0.0;
+  for (int j = 1; j <= KQ_TAYLOR_MAXM; ++j) T.inv[j] = 1.0 / (double)j;
+}
+
+int device_init(int* dev_out) {
+  int dev = 0;
+  KQ_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(KQ_ERR_ARG, "device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (!d.ready) {
+    KqTables T;
+    build_tables(T);
+    KQ_CUDA(cudaMemcpyToSymbol(c_kq_tables, &T, sizeof T));
+    KQ_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    KQ_CUDA(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    KQ_CUDA(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, dev));
+    d.ready = true;
+  }
+  *dev_out = dev;
+  return KQ_OK;
+}
+
+int check_problem(const kq_problem* p) {
+  if (!p) return fail(KQ_ERR_ARG, "problem is NULL");
+  if (p->K < 1 || p->N < 1 || p->NT < 1 || p->L < 0 || p->M < 1)
+    return fail(KQ_ERR_ARG, "invalid sizes K=%d N=%d NT=%d L=%d M=%d", p->K, p->N, p->NT, p->L, p->M);
+  if (p->L > KQ_LMAX) return fail(KQ_ERR_UNSUPPORTED, "L=%d pulses > %d", p->L, KQ_LMAX);
+  if (p->N > 64)
+    return fail(KQ_ERR_UNSUPPORTED, "state length N=%d > 64 is not built yet", p->N);
+  if (!p->ops || !p->ops_adj || !p->term2pulse || !p->op_norm || !p->dt)
+    return fail(KQ_ERR_ARG, "problem has NULL operator/time arrays");
+  return KQ_OK;
+}
+
+struct Plan {
+  int family;  // 0 thread-per-objective, 1 lane-per-row
+  int grid, block;
+  size_t smem;
+  KqWarpGeom geom;
+  int rpl;
+};
+
+int round_up(int v, int q) { return (v + q - 1) / q * q; }
+
+// update = fused sweep (objectives should share a CTA); otherwise spread
+// independent objectives over the SMs.
+int make_plan(const kq_problem* p, bool update, int sms, Plan& pl) {
+  const int K = p->K, N = p->N, M = p->M, L = p->L, NN = N * N;
+  std::memset(&pl, 0, sizeof pl);
+  if (N <= 4 && M <= KQ_MMAX_SMALL) {
+    pl.family = 0;
+    const size_t per_thread = (size_t)(M + (update ? L : 0)) * NN * sizeof(cplx);
+    const size_t fixed = (2 * KQ_LMAX * 32 + 2 * KQ_LMAX) * sizeof(double);
+    int cap = (int)((kSmemBudget - fixed) / per_thread) / 32 * 32;
+    const int maxbt = update ? KQ_SMALL_MAXBT(N) : 256;
+    if (cap > maxbt) cap = maxbt;
+    if (cap < 32) return fail(KQ_ERR_UNSUPPORTED, "generator terms do not fit shared memory");
+    int bt;
+    if (update) {
+      bt = std::min(cap, round_up(K, 32));
+    } else {
+      bt = std::min(cap, std::max(32, round_up((K + sms - 1) / sms, 32)));
+    }
+    pl.block = bt;
+    pl.grid = (K + bt - 1) / bt;
+    pl.smem = per_thread * bt + fixed;
+    return KQ_OK;
+  }
+  pl.family = 1;
+  int R = 2;
+  while (R < N && R < 32) R <<= 1;
+  pl.rpl = (N + 31) / 32;
+  if (pl.rpl < 1) pl.rpl = 1;
+  KqWarpGeom& g = pl.geom;
+  g.R = R;
+  g.G = 32 / R;
+  const size_t fixed = (2 * KQ_LMAX * 32 + 2 * KQ_LMAX) * sizeof(double);
+  const size_t base = (size_t)NN + 2 * N + (M + 1) / 2;
+  const size_t with_mu = base + (update ? (size_t)L * NN : 0);
+  const size_t with_all = with_mu + (size_t)M * NN;
+  size_t stride;
+  if (fixed + with_all * sizeof(cplx) * g.G <= kSmemBudget) {
+    g.terms_in_smem = 1;
+    g.mu_in_smem = update ? 1 : 0;
+    stride = with_all;
+  } else if (fixed + with_mu * sizeof(cplx) * g.G <= kSmemBudget) {
+    g.terms_in_smem = 0;
+    g.mu_in_smem = update ? 1 : 0;
+    stride = with_mu;
+  } else if (fixed + base * sizeof(cplx) * g.G <= kSmemBudget) {
+    g.terms_in_smem = 0;
+    g.mu_in_smem = 0;
+    stride = base;
+  } else {
+    return fail(KQ_ERR_UNSUPPORTED, "N=%d does not fit shared memory", N);
+  }
+  g.obj_stride = (int)stride;
+  const size_t per_warp = stride * sizeof(cplx) * g.G;
+  int max_warps = (int)((kSmemBudget - fixed) / per_warp);
+  if (max_warps > 16) max_warps = 16;  // kernel is built for <= 512 threads
+  if (max_warps < 1) max_warps = 1;
+  const int warps_needed = (K + g.G - 1) / g.G;
+  int wpb;
+  if (update) {
+    wpb = std::min(max_warps, warps_needed);
+  } else {
+    wpb = std::min(max_warps, std::max(1, (warps_needed + sms - 1) / sms));
+  }
+  pl.block = wpb * 32;
+  pl.grid = (warps_needed + wpb - 1) / wpb;
+  pl.smem = fixed + per_warp * wpb;
+  return KQ_OK;
+}
+
+KqSweepArgs base_args(const kq_problem* p) {
+  KqSweepArgs a;
+  std::memset(&a, 0, sizeof a);
+  a.K = p->K;
+  a.N = p->N;
+  a.NT = p->NT;
+  a.L = p->L;
+  a.M = p->M;
+  a.is_super = p->is_super;
+  a.mu = reinterpret_cast<const cplx*>(p->mu);
+  a.term2pulse = p->term2pulse;
+  a.op_norm = p->op_norm;
+  a.dt = p->dt;
+  a.shape = p->shape;
+  a.lambda_a = p->lambda_a;
+  a.world = 1;
+  return a;
+}
+
+template <typename Kern>
+int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** params) {
+  KQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  if (cooperative) {
+    int per_sm = 0;
+    KQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl.block, pl.smem));
+    int dev = 0, sms = 0;
+    KQ_CUDA(cudaGetDevice(&dev));
+    KQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if ((long long)per_sm * sms < pl.grid)
+      return fail(KQ_ERR_UNSUPPORTED,
+                  "fused sweep needs %d co-resident CTAs but only %d fit (K too large)", pl.grid,
+                  per_sm * sms);
+    KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params,
+                                        pl.smem, st));
+  } else {
+    KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params, pl.smem, st));
+  }
+  return KQ_OK;
+}
+
+template <int N>
+int launch_prop_small(const KqSweepArgs& a, const Plan& pl, int fsel, cudaStream_t st) {
+  void* params[] = {(void*)&a};
+  switch (fsel) {
+    case 0: return launch(k_prop_small<N, 0>, pl, false, st, params);
+    case 1: return launch(k_prop_small<N, 1>, pl, false, st, params);
+    default: return launch(k_prop_small<N, 2>, pl, false, st, params);
+  }
+}
+
+template <int N>
+int launch_fwupd_small(const KqSweepArgs& a, const Plan& pl, int fsel, bool second,
+                       cudaStream_t st) {
+  void* params[] = {(void*)&a};
+  const bool coop = pl.grid > 1;
+  if (N <= 2 && pl.block > 256) {
+    constexpr int BT = (N <= 2) ? 1024 : 256;
+    if (fsel == 0) {
+      return second ? launch(k_fwupd_small<N, 0, true, BT>, pl, coop, st, params)
+                    : launch(k_fwupd_small<N, 0, false, BT>, pl, coop, st, params);
+    }
+    return second ? launch(k_fwupd_small<N, 2, true, BT>, pl, coop, st, params)
+                  : launch(k_fwupd_small<N, 2, false, BT>, pl, coop, st, params);
+  }
+  if (fsel == 0) {
+    return second ? launch(k_fwupd_small<N, 0, true, 256>, pl, coop, st, params)
+                  : launch(k_fwupd_small<N, 0, false, 256>, pl, coop, st, params);
+  }
+  return second ? launch(k_fwupd_small<N, 2, true, 256>, pl, coop, st, params)
+                : launch(k_fwupd_small<N, 2, false, 256>, pl, coop, st, params);
+}
+
+template <int RPL>
+int launch_warp(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, bool update,
+                cudaStream_t st) {
+  void* params[] = {(void*)&a, (void*)&pl.geom};
+  const bool coop = update && pl.grid > 1;
+  if (!update) {
+    switch (fsel) {
+      case 0: return launch(k_sweep_warp<RPL, 0, false, false>, pl, false, st, params);
+      case 1: return launch(k_sweep_warp<RPL, 1, false, false>, pl, false, st, params);
+      default: return launch(k_sweep_warp<RPL, 2, false, false>, pl, false, st, params);
+    }
+  }
+  if (fsel == 0) {
+    return second ? launch(k_sweep_warp<RPL, 0, true, true>, pl, coop, st, params)
+                  : launch(k_sweep_warp<RPL, 0, false, true>, pl, coop, st, params);
+  }
+  return second ? launch(k_sweep_warp<RPL, 2, true, true>, pl, coop, st, params)
+                : launch(k_sweep_warp<RPL, 2, false, true>, pl, coop, st, params);
+}
+
+int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_c128* state0,
+             kq_c128* stateT, kq_c128* store, void* stream) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (!pulses && p->L > 0) return fail(KQ_ERR_ARG, "pulses is NULL");
+  if (!state0) return fail(KQ_ERR_ARG, "initial state is NULL");
+  if (!stateT && !store) return fail(KQ_ERR_ARG, "both outputs are NULL");
+  int dev;
+  rc = device_init(&dev);
+  if (rc) return rc;
+  Plan pl;
+  rc = make_plan(p, false, g_dev[dev].sms, pl);
+  if (rc) return rc;
+  KqSweepArgs a = base_args(p);
+  a.ops = reinterpret_cast<const cplx*>(backward ? p->ops_adj : p->ops);
+  a.pulses = pulses;
+  a.state0 = reinterpret_cast<const cplx*>(state0);
+  a.stateT = reinterpret_cast<cplx*>(stateT);
+  a.store = reinterpret_cast<cplx*>(store);
+  a.backward = backward ? 1 : 0;
+  const int fsel = p->is_super ? 2 : (backward ? 1 : 0);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl.family == 0) {
+    switch (p->N) {
+      case 1: return launch_prop_small<1>(a, pl, fsel, st);
+      case 2: return launch_prop_small<2>(a, pl, fsel, st);
+      case 3: return launch_prop_small<3>(a, pl, fsel, st);
+      default: return launch_prop_small<4>(a, pl, fsel, st);
+    }
+  }
+  return pl.rpl == 1 ? launch_warp<1>(a, pl, fsel, false, false, st)
+                     : launch_warp<2>(a, pl, fsel, false, false, st);
+}
+
+// ---- boundary condition / overlaps --------------------------------------
+__global__ void k_overlaps(int K, int N, const cplx* __restrict__ a, const cplx* __restrict__ b,
+                           cplx* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  cplx acc = c_zero();
+  for (int i = 0; i < N; ++i) acc = c_fma_conj(a[(size_t)k * N + i], b[(size_t)k * N + i], acc);
+  out[k] = acc;
+}
+
+// chi_k(T) of functionals.py:177-197 (ss), 225-253 (sm), 293-317 (re),
+// 389-437 (hs), then chi/||chi|| and ||chi|| (optimize.py:407-410).
+__global__ void k_chi_boundary(int K, int N, int kind, int K_total, const cplx* __restrict__ phiT,
+                               const cplx* __restrict__ targets, const cplx* __restrict__ tau,
+                               const double* __restrict__ weights,
+                               const cplx* __restrict__ tau_sum, cplx* __restrict__ chi,
+                               double* __restrict__ norms) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const double w = weights ? weights[k] : 1.0;
+  cplx c;  // chi_k = c * target_k   (hs: c * (target_k - phi_k))
+  if (kind == KQ_CHI_RE || kind == KQ_CHI_HS) {
+    c = c_make(w * (1.0 / (2.0 * (double)K_total)), 0.0);
+  } else if (kind == KQ_CHI_SS) {
+    const cplx t = tau[k];
+    c = c_make(t.x / (double)K_total * w, t.y / (double)K_total * w);
+  } else {
+    const double f = (1.0 / ((double)K_total * (double)K_total)) * w;
+    const cplx s = tau_sum[0];
+    c = c_make(f * s.x, f * s.y);
+  }
+  double nrm2 = 0.0;
+  for (int i = 0; i < N; ++i) {
+    cplx t = targets[(size_t)k * N + i];
+    if (kind == KQ_CHI_HS) t = c_sub(t, phiT[(size_t)k * N + i]);
+    const cplx v = c_make(c.x * t.x - c.y * t.y, c.x * t.y + c.y * t.x);
+    chi[(size_t)k * N + i] = v;
+    nrm2 = fma(v.x, v.x, nrm2);
+    nrm2 = fma(v.y, v.y, nrm2);
+  }
+  const double nrm = sqrt(nrm2);
+  norms[k] = nrm;
+  for (int i = 0; i < N; ++i) {
+    cplx v = chi[(size_t)k * N + i];
+    chi[(size_t)k * N + i] = c_make(v.x / nrm, v.y / nrm);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int kq_version(void) { return 100; }
+
+const char* kq_last_error(void) { return g_err.c_str(); }
+
+size_t kq_comm_slot_bytes(const kq_problem*) {
+  return (size_t)2 * (kMaxBlocks + kMaxWorld) * KQ_LMAX * sizeof(KqSlot);
+}
+
+size_t kq_workspace_bytes(const kq_problem* p) { return kStatusBytes + kq_comm_slot_bytes(p); }
+
+int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
+            int32_t* smem_bytes) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  Plan pl;
+  rc = make_plan(p, true, 148, pl);
+  if (rc) return rc;
+  if (family) *family = pl.family;
+  if (grid) *grid = pl.grid;
+  if (block) *block = pl.block;
+  if (smem_bytes) *smem_bytes = (int32_t)pl.smem;
+  return KQ_OK;
+}
+
+int kq_propagate_forward(const kq_problem* p, const double* pulses, const kq_c128* state0,
+                         kq_c128* stateT, kq_c128* store, void* stream) {
+  return run_prop(p, false, pulses, state0, stateT, store, stream);
+}
+
+int kq_sweep_backward(const kq_problem* p, const double* guess_pulses, const kq_c128* chiT,
+                      kq_c128* X, void* stream) {
+  if (!X) return fail(KQ_ERR_ARG, "X is NULL");
+  return run_prop(p, true, guess_pulses, chiT, nullptr, X, stream);
+}
+
+int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, double* opt_pulses,
+                            const kq_c128* X, const double* chi_norms, const kq_c128* phi0,
+                            kq_c128* phiT, const double* sigma, const kq_c128* Phi0,
+                            kq_c128* Phi1, double* g_a, const kq_comm* comm, void* workspace,
+                            uint32_t epoch, void* stream) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (!guess_pulses || !opt_pulses || !X || !chi_norms || !phi0 || !g_a || !workspace)
+    return fail(KQ_ERR_ARG, "NULL argument to kq_sweep_forward_update");
+  if (!p->mu || !p->shape || !p->lambda_a) return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
+  if (p->L < 1) return fail(KQ_ERR_ARG, "no pulses to update");
+  const bool second = sigma != nullptr;
+  if (second && !Phi0) return fail(KQ_ERR_ARG, "second order needs Phi0");
+  int dev;
+  rc = device_init(&dev);
+  if (rc) return rc;
+  Plan pl;
+  rc = make_plan(p, true, g_dev[dev].sms, pl);
+  if (rc) return rc;
+  if (pl.grid > kMaxBlocks) return fail(KQ_ERR_UNSUPPORTED, "too many CTAs (%d)", pl.grid);
+  KqSweepArgs a = base_args(p);
+  a.ops = reinterpret_cast<const cplx*>(p->ops);
+  a.pulses = guess_pulses;
+  a.opt_pulses = opt_pulses;
+  a.state0 = reinterpret_cast<const cplx*>(phi0);
+  a.stateT = reinterpret_cast<cplx*>(phiT);
+  a.store = second ? reinterpret_cast<cplx*>(Phi1) : nullptr;
+  a.X = reinterpret_cast<const cplx*>(X);
+  a.chi_norms = chi_norms;
+  a.sigma = sigma;
+  a.Phi0 = reinterpret_cast<const cplx*>(Phi0);
+  a.g_a = g_a;
+  a.status = reinterpret_cast<int*>(workspace);
+  a.slots = reinterpret_cast<KqSlot*>(static_cast<char*>(workspace) + kStatusBytes);
+  a.tag_base = epoch * (uint32_t)(p->NT + 1);
+  if (comm && comm->world > 1) {
+    if (comm->world > kMaxWorld || !comm->slots)
+      return fail(KQ_ERR_ARG, "invalid kq_comm (world=%d)", comm->world);
+    a.rank = comm->rank;
+    a.world = comm->world;
+    a.peer_slots = reinterpret_cast<KqSlot* const*>(comm->slots);
+  }
+  const int fsel = p->is_super ? 2 : 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl.family == 0) {
+    switch (p->N) {
+      case 1: return launch_fwupd_small<1>(a, pl, fsel, second, st);
+      case 2: return launch_fwupd_small<2>(a, pl, fsel, second, st);
+      case 3: return launch_fwupd_small<3>(a, pl, fsel, second, st);
+      default: return launch_fwupd_small<4>(a, pl, fsel, second, st);
+    }
+  }
+  return pl.rpl == 1 ? launch_warp<1>(a, pl, fsel, second, true, st)
+                     : launch_warp<2>(a, pl, fsel, second, true, st);
+}
+
+int kq_chi_boundary(const kq_problem* p, int kind, int32_t K_total, const kq_c128* phiT,
+                    const kq_c128* targets, const kq_c128* tau, const double* weights,
+                    const kq_c128* tau_sum, kq_c128* chi_out, double* chi_norms, void* stream) {
+  if (!p || !targets || !chi_out || !chi_norms) return fail(KQ_ERR_ARG, "NULL argument");
+  if (kind < KQ_CHI_RE || kind > KQ_CHI_HS) return fail(KQ_ERR_ARG, "unknown chi kind %d", kind);
+  if (kind == KQ_CHI_SS && !tau) return fail(KQ_ERR_ARG, "chis_ss needs tau");
+  if (kind == KQ_CHI_SM && !tau_sum) return fail(KQ_ERR_ARG, "chis_sm needs tau_sum");
+  if (kind == KQ_CHI_HS && !phiT) return fail(KQ_ERR_ARG, "chis_hs needs phiT");
+  if (K_total < p->K) return fail(KQ_ERR_ARG, "K_total < K");
+  const int bt = 128;
+  k_chi_boundary<<<(p->K + bt - 1) / bt, bt, 0, static_cast<cudaStream_t>(stream)>>>(
+      p->K, p->N, kind, K_total, reinterpret_cast<const cplx*>(phiT),
+      reinterpret_cast<const cplx*>(targets), reinterpret_cast<const cplx*>(tau), weights,
+      reinterpret_cast<const cplx*>(tau_sum), reinterpret_cast<cplx*>(chi_out), chi_norms);
+  KQ_CUDA(cudaGetLastError());
+  return KQ_OK;
+}
+
+int kq_overlaps(int32_t K, int32_t N, const kq_c128* a, const kq_c128* b, kq_c128* out,
+                void* stream) {
+  if (K < 1 || N < 1 || !a || !b || !out) return fail(KQ_ERR_ARG, "invalid argument");
+  const int bt = 128;
+  k_overlaps<<<(K + bt - 1) / bt, bt, 0, static_cast<cudaStream_t>(stream)>>>(
+      K, N, reinterpret_cast<const cplx*>(a), reinterpret_cast<const cplx*>(b),
+      reinterpret_cast<cplx*>(out));
+  KQ_CUDA(cudaGetLastError());
+  return KQ_OK;
+}
+
+}  // extern "C"

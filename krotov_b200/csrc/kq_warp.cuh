@@ -1,0 +1,264 @@
+// Lane-per-row kernels for 5 <= N <= 64 (and small N with many terms).
+//
+// A group of R = 2^ceil(log2 N) lanes (R = 32 and RPL = 2 rows per lane for
+// 32 < N <= 64) owns one objective; a warp holds G = 32/R objectives.  The
+// assembled generator A, the generator terms and mu sit in shared memory in
+// column-major order so that consecutive lanes (= consecutive rows) read
+// consecutive 16-byte words: conflict-free LDS.128, coalesced global fills.
+// The state vector is exchanged through a double-buffered shared-memory
+// vector with one __syncwarp per Horner step; objectives never span warps.
+// One template covers the plain propagation sweeps (UPDATE = false:
+// optimize.py:806-886 of the reference) and the fused update + forward sweep
+// (UPDATE = true: optimize.py:449-500).
+#pragma once
+#include "kq_common.cuh"
+#include "kq_small.cuh"  // KqSweepArgs
+
+struct KqWarpGeom {
+  int R;              // lanes per objective
+  int G;              // objectives per warp
+  int terms_in_smem;  // generator terms resident in shared memory
+  int mu_in_smem;
+  int obj_stride;     // per-objective shared memory, in cplx units
+};
+
+template <int RPL, int FSEL, bool SECOND, bool UPDATE>
+__global__ void __launch_bounds__(512, 1)
+k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const KqTables& T = c_kq_tables;
+  const int K = a.K, N = a.N, NT = a.NT, M = a.M, L = a.L, NN = N * N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int R = g.R, G = g.G;
+  const int grp = lane / R, lig = lane - grp * R;
+  const int ob = (blockIdx.x * nwarps + warp) * G + grp;
+  const bool valid = ob < K;
+  const int kk = valid ? ob : K - 1;
+  const int nblk = gridDim.x;
+  const bool writer = UPDATE && (blockIdx.x == 0 && tid == 0);
+
+  // ---- shared memory carve-up ------------------------------------------
+  double* red = reinterpret_cast<double*>(smem_raw);  // [2][KQ_LMAX][32]
+  double* tot = red + 2 * KQ_LMAX * 32;               // [2][KQ_LMAX]
+  cplx* objbase = reinterpret_cast<cplx*>(tot + 2 * KQ_LMAX) +
+                  (size_t)(warp * G + grp) * g.obj_stride;
+  cplx* sA = objbase;                   // [N*N] column-major
+  cplx* xb = sA + NN;                   // [2][N]
+  double* scoef = reinterpret_cast<double*>(xb + 2 * N);  // [M] current coefficients
+  cplx* sterms = reinterpret_cast<cplx*>(scoef + ((M + 1) & ~1));
+  cplx* smu = sterms + (g.terms_in_smem ? (size_t)M * NN : 0);
+  const cplx* terms = a.ops + (size_t)kk * M * NN;
+  const cplx* mu = UPDATE ? a.mu + (size_t)kk * L * NN : nullptr;
+  if (g.terms_in_smem) {
+    for (int e = lig; e < M * NN; e += R) sterms[e] = terms[e];
+    terms = sterms;
+  }
+  if (UPDATE && g.mu_in_smem) {
+    for (int e = lig; e < L * NN; e += R) smu[e] = mu[e];
+    mu = smu;
+  }
+  const int* t2p = a.term2pulse + (size_t)kk * M;
+  const double* opn = a.op_norm + (size_t)kk * M;
+
+  // ---- per-lane rows -------------------------------------------------------
+  int row[RPL];
+  bool act[RPL];
+  cplx y[RPL], chi[RPL], dphi[RPL];
+#pragma unroll
+  for (int q = 0; q < RPL; ++q) {
+    row[q] = lig + R * q;
+    act[q] = row[q] < N;
+    y[q] = act[q] ? a.state0[(size_t)kk * N + row[q]] : c_zero();
+    chi[q] = c_zero();
+    dphi[q] = c_zero();
+    if (UPDATE && act[q]) chi[q] = a.X[((size_t)0 * K + kk) * N + row[q]];
+    if (act[q]) xb[row[q]] = y[q];
+  }
+  const double cnorm = (UPDATE && valid) ? a.chi_norms[kk] : 0.0;
+  const int n_first = (!UPDATE && a.backward) ? NT - 1 : 0;
+  const int n_step = (!UPDATE && a.backward) ? -1 : 1;
+  if (a.store && valid && (!UPDATE || SECOND)) {
+    const size_t r0 = (!UPDATE && a.backward) ? (size_t)NT : 0;
+#pragma unroll
+    for (int q = 0; q < RPL; ++q)
+      if (act[q]) a.store[(r0 * K + ob) * N + row[q]] = y[q];
+  }
+  double ga[KQ_LMAX];
+#pragma unroll
+  for (int l = 0; l < KQ_LMAX; ++l) ga[l] = 0.0;
+  bool failed = false;
+  int p = 0;  // xb[p] holds the current state
+  __syncwarp();
+
+  for (int it = 0, n = n_first; it < NT; ++it, n += n_step) {
+    const int par = it & 1;
+    const double dtn = a.dt[n];
+    cplx chi_next[RPL], p0_next[RPL];
+    if (UPDATE) {
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        chi_next[q] = c_zero();
+        p0_next[q] = c_zero();
+        if (act[q]) {
+          chi_next[q] = a.X[((size_t)(n + 1) * K + kk) * N + row[q]];
+          if (SECOND) p0_next[q] = a.Phi0[((size_t)(n + 1) * K + kk) * N + row[q]];
+        }
+      }
+      const double sig = SECOND ? a.sigma[n] : 0.0;
+      // ---- Im <chi| mu_l |phi>, summed over all objectives -----------------
+      const cplx* xcur = xb + p * N;
+      for (int l = 0; l < L; ++l) {
+        double val = 0.0, val2 = 0.0;
+        const cplx* Ml = mu + (size_t)l * NN;
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+          if (act[q]) {
+            cplx w0 = c_zero(), w1 = c_zero();
+            int c = 0;
+            for (; c + 1 < N; c += 2) {
+              w0 = c_fma(Ml[c * N + row[q]], xcur[c], w0);
+              w1 = c_fma(Ml[(c + 1) * N + row[q]], xcur[c + 1], w1);
+            }
+            if (c < N) w0 = c_fma(Ml[c * N + row[q]], xcur[c], w0);
+            const cplx w = c_add(w0, w1);
+            val += c_im_conj_mul(chi[q], w);
+            if (SECOND) val2 += c_im_conj_mul(dphi[q], w);
+          }
+        }
+        val *= cnorm;
+        if (SECOND) val = fma(0.5 * sig, valid ? val2 : 0.0, val);
+        val = warp_allreduce_sum(val);
+        if (lane == 0) red[(par * KQ_LMAX + l) * 32 + warp] = val;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
+        for (int l = 0; l < L; ++l) {
+          double acc = (lane < nwarps) ? red[(par * KQ_LMAX + l) * 32 + lane] : 0.0;
+          acc = warp_allreduce_sum(acc);
+          if (nblk > 1) {
+            if (lane == 0)
+              slot_store(&a.slots[((size_t)par * nblk + blockIdx.x) * L + l], acc, tag);
+            double g2 = 0.0;
+            for (int c = lane; c < nblk; c += 32)
+              g2 += slot_wait(&a.slots[((size_t)par * nblk + c) * L + l], tag, failed);
+            acc = warp_allreduce_sum(g2);
+          }
+          if (lane == 0) tot[par * KQ_LMAX + l] = acc;
+        }
+      }
+      if (a.world > 1) {
+        const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
+        __syncthreads();
+        KqSlot* mine = a.peer_slots[a.rank];
+        const size_t goff = (size_t)2 * nblk * KQ_LMAX;
+        if (blockIdx.x == 0 && tid < L * a.world) {
+          const int l = tid % L, r = tid / L;
+          slot_store(a.peer_slots[r] + goff + ((size_t)par * a.world + a.rank) * KQ_LMAX + l,
+                     tot[par * KQ_LMAX + l], tag);
+        }
+        __syncthreads();
+        if (tid == 0) {
+          for (int l = 0; l < L; ++l) {
+            double acc = 0.0;
+            for (int r = 0; r < a.world; ++r)
+              acc += slot_wait(mine + goff + ((size_t)par * a.world + r) * KQ_LMAX + l, tag, failed);
+            tot[par * KQ_LMAX + l] = acc;
+          }
+        }
+      }
+      __syncthreads();
+      if (writer) {
+        for (int l = 0; l < L; ++l) {
+          const double d1 = tot[par * KQ_LMAX + l];
+          const double sl = a.shape[(size_t)l * NT + n] / a.lambda_a[l];
+          a.opt_pulses[(size_t)l * NT + n] =
+              __dadd_rn(a.pulses[(size_t)l * NT + n], __dmul_rn(sl, d1));
+          ga[l] = __dadd_rn(ga[l], __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), dtn));
+        }
+      }
+    }
+    // ---- coefficients of this step's generator ----------------------------
+    for (int m = lig; m < M; m += R) {
+      const int l = t2p[m];
+      double c = (l == -1) ? 1.0 : 0.0;
+      if (l >= 0) {
+        c = a.pulses[(size_t)l * NT + n];
+        if (UPDATE) {
+          const double sl = a.shape[(size_t)l * NT + n] / a.lambda_a[l];
+          c = __dadd_rn(c, __dmul_rn(sl, tot[par * KQ_LMAX + l]));
+        }
+      }
+      scoef[m] = c;
+    }
+    __syncwarp();
+    double x = 0.0;
+    for (int m = 0; m < M; ++m) x = fma(fabs(scoef[m]), opn[m], x);
+    x *= dtn;
+    // assemble A = sum_m coef_m T_m (all lanes of the group, strided elements)
+    for (int e = lig; e < NN; e += R) {
+      cplx acc = c_zero();
+      for (int m = 0; m < M; ++m) acc = c_fma_real(scoef[m], terms[(size_t)m * NN + e], acc);
+      sA[e] = acc;
+    }
+    // warp-uniform Taylor plan from the largest bound in the warp
+    {
+      const int hi = __reduce_max_sync(0xffffffffu, __double2hiint(x));
+      x = __hiloint2double(hi, (int)0xffffffff);
+    }
+    int s, mdeg;
+    double xs;
+    taylor_plan(T, x, s, mdeg, xs);
+    const double h = (s == 1) ? dtn : dtn / (double)s;
+    __syncwarp();
+    for (int rep = 0; rep < s; ++rep) {
+      cplx v[RPL];
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) v[q] = y[q];
+      for (int j = mdeg; j >= 1; --j) {
+        const double cj = h * T.inv[j];
+        const cplx* xcur = xb + p * N;
+        cplx* xnext = xb + (p ^ 1) * N;
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+          if (act[q]) {
+            cplx w0 = c_zero(), w1 = c_zero();
+            int c = 0;
+            for (; c + 1 < N; c += 2) {
+              w0 = c_fma(sA[c * N + row[q]], xcur[c], w0);
+              w1 = c_fma(sA[(c + 1) * N + row[q]], xcur[c + 1], w1);
+            }
+            if (c < N) w0 = c_fma(sA[c * N + row[q]], xcur[c], w0);
+            y[q] = c_fma_real(cj, apply_f<FSEL>(c_add(w0, w1)), v[q]);
+            xnext[row[q]] = y[q];
+          }
+        }
+        __syncwarp();
+        p ^= 1;
+      }
+    }
+    if (UPDATE) {
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        chi[q] = chi_next[q];
+        if (SECOND) dphi[q] = c_sub(y[q], p0_next[q]);
+      }
+    }
+    if (a.store && valid && (!UPDATE || SECOND)) {
+      const size_t r1 = (!UPDATE && a.backward) ? (size_t)n : (size_t)n + 1;
+#pragma unroll
+      for (int q = 0; q < RPL; ++q)
+        if (act[q]) a.store[(r1 * K + ob) * N + row[q]] = y[q];
+    }
+  }
+  if (a.stateT && valid) {
+#pragma unroll
+    for (int q = 0; q < RPL; ++q)
+      if (act[q]) a.stateT[(size_t)ob * N + row[q]] = y[q];
+  }
+  if (writer) {
+    for (int l = 0; l < L; ++l) a.g_a[l] = ga[l];
+  }
+  if (UPDATE && failed) atomicExch(a.status, (int)-4);
+}

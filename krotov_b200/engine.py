@@ -1,0 +1,194 @@
+"""Device side of the sweep engine: owns the torch CUDA tensors of one
+compiled problem and issues the C-ABI calls (include/krotov_b200.h).
+
+PyTorch is used for device memory and streams only; every sweep is one launch
+of a hand-written sm_100a kernel from ``libkrotov_b200.so``.  All calls are
+asynchronous on the current torch stream.  There is no CPU fallback: without
+a CUDA device or without the built library construction raises
+:class:`krotov_b200._lib.EngineUnavailable`.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineUnavailable, KqComm, KqProblem, check
+
+__all__ = ['SweepEngine', 'CHI_KINDS']
+
+CHI_KINDS = {'re': 0, 'ss': 1, 'sm': 2, 'hs': 3}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+class SweepEngine:
+    """Device tensors + launches for one :class:`CompiledProblem`.
+
+    Attributes (torch tensors on the device):
+        X: backward states ``[NT+1, K, N]`` (time-major), filled by
+            :meth:`sweep_backward`.
+        chi, chi_norms: normalised boundary states ``[K, N]`` and their norms.
+    """
+
+    def __init__(self, cp, shape_arrays, lambda_vals, device=None):
+        import torch
+        self.torch = torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise EngineUnavailable(
+                "krotov_b200 needs a CUDA device (sm_100a); there is no CPU "
+                "fallback for the sweep kernels")
+        self.device = torch.device(
+            'cuda', torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.cp = cp
+        self.launches = 0
+        dev = self.device
+        c128, f64 = torch.complex128, torch.float64
+
+        def up(a, dtype):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype,
+                                   device=dev)
+
+        self.t_ops = up(cp.ops, c128)
+        self.t_ops_adj = up(cp.ops_adj, c128)
+        self.t_mu = up(cp.mu, c128)
+        self.t_t2p = up(cp.term2pulse, torch.int32)
+        self.t_opn = up(cp.op_norm, f64)
+        self.t_dt = up(cp.dt, f64)
+        self.t_shape = up(np.array(shape_arrays, dtype=np.float64).reshape(
+            cp.L, cp.NT), f64)
+        self.t_lambda = up(np.asarray(lambda_vals, dtype=np.float64), f64)
+        self.t_psi0 = up(cp.psi0, c128)
+        self.t_targets = None if cp.targets is None else up(cp.targets, c128)
+        self.t_weights = None if cp.weights is None else up(cp.weights, f64)
+        self.problem = KqProblem(
+            K=cp.K, N=cp.N, NT=cp.NT, L=cp.L, M=cp.M,
+            is_super=1 if cp.is_super else 0,
+            ops=self.t_ops.data_ptr(), ops_adj=self.t_ops_adj.data_ptr(),
+            mu=self.t_mu.data_ptr(), term2pulse=self.t_t2p.data_ptr(),
+            op_norm=self.t_opn.data_ptr(), dt=self.t_dt.data_ptr(),
+            shape=self.t_shape.data_ptr(), lambda_a=self.t_lambda.data_ptr())
+        self._p = ctypes.byref(self.problem)
+        nbytes = self.lib.kq_workspace_bytes(self._p)
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.epoch = 0
+        self.comm = None
+        K, N, NT = cp.K, cp.N, cp.NT
+        self.X = torch.empty((NT + 1, K, N), dtype=c128, device=dev)
+        self.chi = torch.empty((K, N), dtype=c128, device=dev)
+        self.chi_norms = torch.empty(K, dtype=f64, device=dev)
+        self.g_a = torch.zeros(max(cp.L, 1), dtype=f64, device=dev)
+
+    # -- helpers -----------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(
+            self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def new_state_store(self):
+        return self.torch.empty((self.cp.NT + 1, self.cp.K, self.cp.N),
+                                dtype=self.torch.complex128,
+                                device=self.device)
+
+    def new_states(self):
+        return self.torch.empty((self.cp.K, self.cp.N),
+                                dtype=self.torch.complex128,
+                                device=self.device)
+
+    def pulses_to_device(self, pulses):
+        arr = np.array(pulses, dtype=np.float64).reshape(self.cp.L,
+                                                         self.cp.NT)
+        return self.torch.as_tensor(arr, dtype=self.torch.float64,
+                                    device=self.device)
+
+    def set_lambda(self, lambda_vals):
+        """Refresh the device copy of lambda_a (hooks may change it between
+        iterations, optimize.py:552-555 / tests/test_infohooks.py:30-37)."""
+        self.t_lambda.copy_(self.torch.as_tensor(
+            np.asarray(lambda_vals, dtype=np.float64)))
+
+    def plan(self):
+        """(family, grid, block, smem) the fused sweep uses."""
+        vals = [ctypes.c_int32() for _ in range(4)]
+        check(self.lib.kq_plan(self._p, *[ctypes.byref(v) for v in vals]))
+        return tuple(v.value for v in vals)
+
+    # -- sweeps ------------------------------------------------------------
+    def propagate_forward(self, pulses_t, phiT=None, store=None,
+                          state0=None):
+        """Initial forward propagation (optimize.py:806-846)."""
+        if phiT is None:
+            phiT = self.new_states()
+        s0 = self.t_psi0 if state0 is None else state0
+        check(self.lib.kq_propagate_forward(
+            self._p, _ptr(pulses_t), _ptr(s0), _ptr(phiT), _ptr(store),
+            self._stream()))
+        self.launches += 1
+        return phiT
+
+    def sweep_backward(self, pulses_t):
+        """Backward propagation of :attr:`chi` into :attr:`X`
+        (optimize.py:849-886)."""
+        check(self.lib.kq_sweep_backward(
+            self._p, _ptr(pulses_t), _ptr(self.chi), _ptr(self.X),
+            self._stream()))
+        self.launches += 1
+        return self.X
+
+    def sweep_forward_update(self, guess_t, opt_t, phiT=None, sigma_t=None,
+                             Phi0=None, Phi1=None):
+        """Fused pulse update + forward propagation (optimize.py:449-500)."""
+        if phiT is None:
+            phiT = self.new_states()
+        self.epoch += 1
+        comm = ctypes.byref(self.comm) if self.comm is not None else None
+        check(self.lib.kq_sweep_forward_update(
+            self._p, _ptr(guess_t), _ptr(opt_t), _ptr(self.X),
+            _ptr(self.chi_norms), _ptr(self.t_psi0), _ptr(phiT),
+            _ptr(sigma_t), _ptr(Phi0), _ptr(Phi1), _ptr(self.g_a), comm,
+            _ptr(self.workspace), ctypes.c_uint32(self.epoch & 0xFFFFFFFF),
+            self._stream()))
+        self.launches += 1
+        return phiT
+
+    def overlaps(self, a, b, out=None):
+        """tau_k = <a_k|b_k> (optimize.py:316-322, 503-508)."""
+        if out is None:
+            out = self.torch.empty(self.cp.K, dtype=self.torch.complex128,
+                                   device=self.device)
+        check(self.lib.kq_overlaps(self.cp.K, self.cp.N, _ptr(a), _ptr(b),
+                                   _ptr(out), self._stream()))
+        self.launches += 1
+        return out
+
+    def chi_builtin(self, kind, phiT, tau_t, K_total=None):
+        """Device chi-constructor + normalisation (optimize.py:404-410)."""
+        tau_sum = None
+        if kind == 'sm':
+            w = tau_t if self.t_weights is None else tau_t * self.t_weights
+            tau_sum = w.sum().reshape(1)
+        check(self.lib.kq_chi_boundary(
+            self._p, CHI_KINDS[kind],
+            self.cp.K if K_total is None else K_total, _ptr(phiT),
+            _ptr(self.t_targets), _ptr(tau_t), _ptr(self.t_weights),
+            _ptr(tau_sum), _ptr(self.chi), _ptr(self.chi_norms),
+            self._stream()))
+        self.launches += 1
+
+    def chi_from_host(self, chi_vectors):
+        """Upload host chi states [K,N] (custom chi_constructor), normalise
+        with the L2/Frobenius norm."""
+        arr = np.asarray(chi_vectors, dtype=np.complex128).reshape(
+            self.cp.K, self.cp.N)
+        norms = np.sqrt((arr.real ** 2 + arr.imag ** 2).sum(axis=1))
+        with np.errstate(divide='ignore', invalid='ignore'):
+            arr = arr / norms[:, None]
+        self.chi.copy_(self.torch.as_tensor(arr))
+        self.chi_norms.copy_(self.torch.as_tensor(norms))
+        return norms
+
+    def status(self):
+        """Exchange status word (0 = ok); synchronises."""
+        return int(self.workspace[:4].view(self.torch.int32).item())

@@ -1,0 +1,497 @@
+"""``optimize_pulses``: Krotov's method with the time loops lowered to B200.
+
+Same keyword plugin surface, bookkeeping and :class:`Result` semantics as
+``krotov.optimize_pulses`` (/root/reference/src/krotov/optimize.py:33-590).
+What differs is *where* the work happens: the three per-time-step Python
+loops of the reference (initial forward propagation :806-846, backward
+propagation :849-886, sequential update + forward step :449-500) are one
+CUDA kernel launch each (``libkrotov_b200.so``), and the built-in
+chi-constructors and tau overlaps run on the device too, so that an iteration
+without hooks needs no host round trip at all.  Host callbacks
+(`chi_constructor`, `info_hook`, `modify_params_after_iter`,
+`check_convergence`, ``sigma.refresh``) keep their reference signatures and
+run once per iteration.
+"""
+import copy
+import logging
+import time
+
+import numpy as np
+
+from . import functionals as _functionals
+from .compiler import compile_problem, initialize_controls
+from .conversions import control_onto_interval, pulse_onto_tlist
+from .engine import SweepEngine
+from .info_hooks import chain
+from .mu import derivative_wrt_pulse
+from .propagators import DensityMatrixODEPropagator
+from .propagators import expm as _expm_marker
+from .result import Result
+from .second_order import _overlap
+
+__all__ = ['optimize_pulses']
+
+_BUILTIN_CHI = {
+    _functionals.chis_re: 're',
+    _functionals.chis_ss: 'ss',
+    _functionals.chis_sm: 'sm',
+    _functionals.chis_hs: 'hs',
+}
+
+
+class _LazyStates:
+    """Per-objective view ``store[k][n]`` of a device state store
+    ``[nt, K, N]``; the tensor is downloaded once, on first access.  Valid
+    during the iteration in which it is handed to a hook (the device buffers
+    are re-used by the next iteration)."""
+
+    def __init__(self, tensor, cp):
+        self._tensor, self._cp, self._host = tensor, cp, None
+        self._expired = False
+
+    def _data(self):
+        if self._host is None:
+            if self._expired:
+                raise RuntimeError(
+                    "state storage is only valid during the iteration it "
+                    "was passed to a hook; copy what you need inside the hook")
+            self._host = self._tensor.cpu().numpy()
+        return self._host
+
+    def _expire(self):
+        self._expired = True
+        self._tensor = None
+
+    def __len__(self):
+        return self._cp.K
+
+    def __getitem__(self, k):
+        return _LazyObjectiveStates(self, k)
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+class _LazyObjectiveStates:
+    def __init__(self, parent, k):
+        self._p, self._k = parent, k
+
+    def __len__(self):
+        return self._p._cp.NT + 1
+
+    def __getitem__(self, n):
+        cp = self._p._cp
+        data = self._p._data()
+        if isinstance(n, slice):
+            return [self[i] for i in range(*n.indices(len(self)))]
+        return cp.unvec(data[n, self._k].copy(), cp.state_templates[self._k])
+
+    def __iter__(self):
+        return (self[n] for n in range(len(self)))
+
+
+def _check_lowerable(propagator, objectives):
+    props = propagator if isinstance(propagator, list) else [propagator]
+    if isinstance(propagator, list):
+        assert len(props) == len(objectives)
+    for p in props:
+        if p is _expm_marker or isinstance(p, DensityMatrixODEPropagator):
+            continue
+        raise NotImplementedError(
+            "krotov_b200 lowers the time loop to CUDA kernels and therefore "
+            "only accepts krotov_b200.propagators.expm or a "
+            "DensityMatrixODEPropagator instance as `propagator`; a custom "
+            "per-step Python propagator (%r) cannot be lowered and there is "
+            "no CPU fallback" % (p,))
+
+
+def _check_overlap(overlap, cp):
+    """A custom `overlap` is accepted only if it is the standard one
+    (verified on random states); it is then lowered like the default."""
+    if overlap is None or overlap is _overlap:
+        return
+    rng = np.random.default_rng(0)
+    for _ in range(2):
+        a = rng.normal(size=cp.N) + 1j * rng.normal(size=cp.N)
+        b = rng.normal(size=cp.N) + 1j * rng.normal(size=cp.N)
+        tmpl = cp.state_templates[0]
+        got = overlap(cp.unvec(a, tmpl), cp.unvec(b, tmpl))
+        if got is None or abs(complex(got) - np.vdot(a, b)) > 1e-10 * abs(
+                np.vdot(a, b)):
+            raise NotImplementedError(
+                "custom `overlap` differs from <a|b> / tr(a^dag b) and "
+                "cannot be lowered to the B200 sweep kernels")
+
+
+def _restore_from_previous_result(result, objectives, tlist, store_all_pulses):
+    """Guess controls/pulses from a previous Result, with the reference's
+    validation and messages (optimize.py:707-774)."""
+    if not isinstance(result, Result):
+        raise ValueError("Continuation is only possible from a Result object")
+    if len(objectives) != len(result.objectives):
+        raise ValueError(
+            "When continuing from a previous Result, the number of "
+            "objectives must be the same")
+    for a, b in zip(objectives, result.objectives):
+        if a != b:
+            raise ValueError(
+                "When continuing from a previous Result, the objectives must "
+                "remain unchanged")
+    if store_all_pulses and len(result.all_pulses) == 0:
+        raise ValueError(
+            "The store_all_pulses parameter cannot be changed when "
+            "continuing from a previous Result. Pass it as False.")
+    if not store_all_pulses and len(result.all_pulses) > 0:
+        raise ValueError(
+            "The store_all_pulses parameter cannot be changed when "
+            "continuing from a previous Result. Pass it as True.")
+    same_grid = len(tlist) == len(result.tlist) and np.max(
+        np.abs(np.array(tlist) - np.array(result.tlist))) <= 1e-5
+    if not same_grid:
+        raise ValueError(
+            "When continuing from a previous Result, the controls must be "
+            "defined on the same time grid")
+    nt = len(tlist)
+    guess_controls = []
+    for control in result.optimized_controls:
+        if len(control) == nt - 1:   # dumped before finalisation: pulses
+            guess_controls.append(pulse_onto_tlist(control))
+        elif len(control) == nt:
+            guess_controls.append(control)
+        else:
+            raise ValueError(
+                "Invalid Result: optimized_controls and tlist are incongruent")
+    return guess_controls, [control_onto_interval(c) for c in guess_controls]
+
+
+def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
+                    chi_constructor, mu=None, sigma=None, iter_start=0,
+                    iter_stop=5000, check_convergence=None, info_hook=None,
+                    modify_params_after_iter=None, storage='array',
+                    parallel_map=None, store_all_pulses=False,
+                    continue_from=None,
+                    skip_initial_forward_propagation=False, norm=None,
+                    overlap=None, limit_thread_pool=None, device=None):
+    """Use Krotov's method to optimize towards the given `objectives`.
+
+    Arguments have the meaning documented for the reference
+    (optimize.py:56-228), with these engine-specific notes:
+
+    * `propagator`: :func:`krotov_b200.propagators.expm` or a
+      :class:`~krotov_b200.propagators.DensityMatrixODEPropagator` (or a list
+      of those).  Both select exact piecewise-constant propagation on the
+      device.  Any other callable raises NotImplementedError.
+    * `chi_constructor`: ``krotov_b200.functionals.chis_re/ss/sm/hs`` run on
+      the device; any other callable is a host callback per iteration.
+    * `mu`: None (default derivative) or a custom callable that is linear in
+      the state and independent of time/pulse values (evaluated once).
+    * `norm`: ignored -- the engine normalises chi with the L2/Frobenius
+      norm; the update is invariant under this choice (optimize.py:410,467).
+    * `overlap`: None or a callable equal to the default overlap.
+    * `storage`, `parallel_map`, `limit_thread_pool`: accepted and ignored
+      (state stores live in HBM; objectives are batched on the GPU).
+    * `device`: CUDA device (default: current torch device).
+
+    Returns:
+        Result
+
+    Raises:
+        ValueError: as the reference, for invalid controls, shapes,
+            `pulse_options` or `continue_from`.
+        NotImplementedError: for plugins that cannot be lowered.
+        krotov_b200.EngineUnavailable: no CUDA device / library not built.
+    """
+    logger = logging.getLogger('krotov')
+    logger.info("Initializing optimization with Krotov's method")
+    second_order = sigma is not None
+    if modify_params_after_iter is not None:
+        info_hook = (modify_params_after_iter if info_hook is None
+                     else chain(modify_params_after_iter, info_hook))
+    _check_lowerable(propagator, objectives)
+
+    (controls, guess_controls, guess_pulses, pulses_mapping, lambda_vals,
+     shape_arrays) = initialize_controls(objectives, pulse_options, tlist)
+    if continue_from is not None:
+        guess_controls, guess_pulses = _restore_from_previous_result(
+            continue_from, objectives, tlist, store_all_pulses)
+    if skip_initial_forward_propagation and second_order:
+        raise ValueError(
+            "skip_initial_forward_propagation is incompatible with "
+            "second order Krotov (sigma is not None)")
+
+    cp = compile_problem(objectives, controls, pulses_mapping, tlist,
+                         mu=None if mu is derivative_wrt_pulse else mu,
+                         pulses_for_mu=guess_pulses)
+    _check_overlap(overlap, cp)
+    eng = SweepEngine(cp, shape_arrays, lambda_vals, device=device)
+    torch = eng.torch
+    chi_kind = _BUILTIN_CHI.get(chi_constructor)
+    if chi_kind is not None and cp.targets is None:
+        chi_kind = None  # built-ins need state targets; let the host raise
+    L, NT, K = cp.L, cp.NT, cp.K
+    has_targets = cp.targets is not None
+
+    def states_to_host(t):
+        arr = t.cpu().numpy()
+        return [cp.unvec(arr[k].copy(), cp.state_templates[k])
+                for k in range(K)]
+
+    def tau_to_host(tau_t):
+        if tau_t is None:
+            return np.array([None] * K)
+        return tau_t.cpu().numpy().copy()
+
+    def pulses_to_host(p_t):
+        arr = p_t.cpu().numpy()
+        return [arr[l].copy() for l in range(L)]
+
+    g_a_integrals = np.zeros(L)
+    if continue_from is None:
+        result = Result()
+        result.start_local_time = time.localtime()
+    else:
+        result = copy.deepcopy(continue_from)
+
+    # ---- initial forward propagation (optimize.py:295-322) ----------------
+    guess_t = eng.pulses_to_device(guess_pulses)
+    opt_t = guess_t.clone()
+    Phi0 = Phi1 = None
+    tic = time.time()
+    if skip_initial_forward_propagation:
+        if continue_from is not None:
+            fw_states_T = list(continue_from.states)
+            phiT = torch.as_tensor(
+                np.array([cp.vec(s) for s in fw_states_T]),
+                dtype=torch.complex128, device=eng.device)
+        else:
+            logger.warning(
+                "You should not use `skip_initial_forward_propagation` "
+                "unless you are also passing `continue_from`")
+            fw_states_T = [None] * K
+            phiT = None
+    else:
+        if second_order:
+            Phi0 = eng.new_state_store()
+            Phi1 = eng.new_state_store()
+        phiT = eng.propagate_forward(guess_t, store=Phi0)
+        fw_states_T = None  # materialised on demand
+    tau_t = None
+    if has_targets and phiT is not None:
+        tau_t = eng.overlaps(eng.t_targets, phiT)
+    torch.cuda.synchronize(eng.device)
+    toc = time.time()
+
+    host_loop = (info_hook is not None or check_convergence is not None
+                 or chi_kind is None or second_order)
+    tau_vals = tau_to_host(tau_t)
+    if fw_states_T is None and (host_loop or iter_stop <= iter_start):
+        fw_states_T = states_to_host(phiT)
+
+    forward_states = forward_states0 = None
+    if second_order:
+        forward_states0 = forward_states = _LazyStates(Phi0, cp)
+
+    info = None
+    optimized_pulses = copy.deepcopy(guess_pulses)
+    adjoint_objectives = ([obj.adjoint() for obj in objectives]
+                          if info_hook is not None else None)
+    static = dict(
+        objectives=objectives, adjoint_objectives=adjoint_objectives,
+        lambda_vals=lambda_vals, shape_arrays=shape_arrays, tlist=tlist,
+        propagator=propagator, chi_constructor=chi_constructor,
+        mu=derivative_wrt_pulse if mu is None else mu, sigma=sigma,
+        iter_start=iter_start, iter_stop=iter_stop,
+    )
+    if info_hook is not None:
+        info = info_hook(
+            backward_states=None, forward_states=forward_states,
+            forward_states0=forward_states0, guess_pulses=guess_pulses,
+            optimized_pulses=optimized_pulses, g_a_integrals=g_a_integrals,
+            fw_states_T=fw_states_T, tau_vals=tau_vals, start_time=tic,
+            stop_time=toc, iteration=0, info_vals=[], shared_data={},
+            **static)
+
+    result.tlist = tlist
+    result.objectives = objectives
+    result.guess_controls = guess_controls
+    result.optimized_controls = optimized_pulses
+    result.controls_mapping = pulses_mapping
+    if continue_from is None:
+        if info is not None:
+            result.info_vals.append(info)
+        result.iters.append(0)
+        result.iter_seconds.append(int(toc - tic))
+        result.iter_seconds_device.append(toc - tic)
+        if not np.all(tau_vals == None):  # noqa: E711
+            result.tau_vals.append(tau_vals)
+        if store_all_pulses:
+            result.all_pulses.append(guess_pulses)
+    else:
+        iter_start = continue_from.iters[-1]
+        logger.info("Continuing from previous result, with iteration %d",
+                    iter_start + 1)
+    result.states = fw_states_T
+
+    lam_snapshot = np.array(lambda_vals, dtype=np.float64)
+    deferred = []   # (iteration, tau_t, pulses_t or None, ev0, ev1) fast path
+    finished_by_break = False
+
+    # ---- main loop (optimize.py:393-577) ----------------------------------
+    for krotov_iteration in range(iter_start + 1, iter_stop + 1):
+        logger.info("Started Krotov iteration %d", krotov_iteration)
+        tic = time.time()
+        ev0 = ev1 = None
+        if not host_loop:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(eng.device))
+
+        # boundary condition chi(T), normalised (optimize.py:404-410)
+        chi_states = chi_norms = None
+        if chi_kind is not None:
+            eng.chi_builtin(chi_kind, phiT, tau_t)
+        else:
+            if fw_states_T is None:
+                fw_states_T = states_to_host(phiT)
+            chis = chi_constructor(fw_states_T=fw_states_T,
+                                   objectives=objectives, tau_vals=tau_vals)
+            chi_norms = list(eng.chi_from_host([cp.vec(c) for c in chis]))
+
+        # backward propagation under the guess pulses (optimize.py:413-425)
+        eng.sweep_backward(guess_t)
+
+        # forward propagation and pulse update (optimize.py:427-500)
+        sigma_t = None
+        if second_order:
+            sig = np.array([
+                float(sigma(tlist[n] + 0.5 * (tlist[n + 1] - tlist[n])))
+                for n in range(NT)])
+            sigma_t = torch.as_tensor(sig, dtype=torch.float64,
+                                      device=eng.device)
+        phiT = eng.sweep_forward_update(
+            guess_t, opt_t, phiT=phiT, sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
+        tau_t = eng.overlaps(eng.t_targets, phiT) if has_targets else None
+
+        if not host_loop:
+            ev1.record(torch.cuda.current_stream(eng.device))
+            deferred.append((krotov_iteration, tau_t,
+                             opt_t.clone() if store_all_pulses else None,
+                             ev0, ev1))
+            # prepare next iteration (optimize.py:564): guess <- optimized
+            guess_t, opt_t = opt_t, guess_t
+            continue
+
+        # ---- host bookkeeping (hooks present) -----------------------------
+        torch.cuda.synchronize(eng.device)
+        st = eng.status()
+        if st != 0:
+            raise RuntimeError("sweep kernel reported exchange failure %d"
+                               % st)
+        guess_pulses_host = pulses_to_host(guess_t)
+        optimized_pulses = pulses_to_host(opt_t)
+        g_a_integrals[:] = eng.g_a.cpu().numpy()[:L]
+        fw_states_T = states_to_host(phiT)
+        tau_vals = tau_to_host(tau_t)
+        backward_states = _LazyStates(eng.X, cp)
+        if second_order:
+            forward_states = _LazyStates(Phi1, cp)
+            forward_states0 = _LazyStates(Phi0, cp)
+        toc = time.time()
+
+        if info_hook is not None:
+            info = info_hook(
+                backward_states=backward_states,
+                forward_states=forward_states,
+                forward_states0=forward_states0, fw_states_T=fw_states_T,
+                guess_pulses=guess_pulses_host,
+                optimized_pulses=optimized_pulses,
+                g_a_integrals=g_a_integrals, tau_vals=tau_vals,
+                start_time=tic, stop_time=toc, info_vals=result.info_vals,
+                shared_data={}, iteration=krotov_iteration, **static)
+            # hooks may have modified lambda_vals / optimized_pulses
+            if not np.array_equal(lam_snapshot, np.asarray(lambda_vals)):
+                eng.set_lambda(lambda_vals)
+                lam_snapshot = np.array(lambda_vals, dtype=np.float64)
+            new_opt = eng.pulses_to_device(optimized_pulses)
+            if not torch.equal(new_opt, opt_t):
+                opt_t.copy_(new_opt)
+        result.iters.append(krotov_iteration)
+        result.iter_seconds.append(int(toc - tic))
+        result.iter_seconds_device.append(toc - tic)
+        if info is not None:
+            result.info_vals.append(info)
+        if not np.all(tau_vals == None):  # noqa: E711
+            result.tau_vals.append(tau_vals)
+        result.optimized_controls = optimized_pulses
+        if store_all_pulses:
+            result.all_pulses.append(copy.deepcopy(optimized_pulses))
+        result.states = fw_states_T
+        logger.info("Finished Krotov iteration %d", krotov_iteration)
+
+        msg = None
+        if check_convergence is not None:
+            msg = check_convergence(result)
+        if krotov_iteration >= static['iter_stop']:
+            iter_stop = static['iter_stop']
+            result.message = "Reached %d iterations" % iter_stop
+            finished_by_break = True
+        elif bool(msg) is True:
+            result.message = "Reached convergence"
+            if isinstance(msg, str):
+                result.message += ": " + msg
+            finished_by_break = True
+        if finished_by_break:
+            backward_states._expire()
+            break
+        # prepare next iteration
+        guess_t, opt_t = opt_t, guess_t
+        if second_order:
+            if chi_states is None:
+                chi_arr = eng.chi.cpu().numpy()
+                chi_states = [cp.unvec(chi_arr[k].copy(),
+                                       cp.state_templates[k])
+                              for k in range(K)]
+                if chi_norms is None:
+                    chi_norms = list(eng.chi_norms.cpu().numpy())
+            sigma.refresh(
+                forward_states=forward_states,
+                forward_states0=forward_states0, chi_states=chi_states,
+                chi_norms=chi_norms, optimized_pulses=optimized_pulses,
+                guess_pulses=optimized_pulses, objectives=objectives,
+                result=result)
+            forward_states._expire()
+            forward_states0._expire()
+            Phi0, Phi1 = Phi1, Phi0
+        backward_states._expire()
+
+    if not finished_by_break:
+        result.message = "Reached %d iterations" % max(iter_start, iter_stop)
+
+    # ---- fast path epilogue: one synchronisation for all iterations --------
+    if deferred:
+        torch.cuda.synchronize(eng.device)
+        st = eng.status()
+        if st != 0:
+            raise RuntimeError("sweep kernel reported exchange failure %d"
+                               % st)
+        for (it, tau_i, pulses_i, e0, e1) in deferred:
+            secs = e0.elapsed_time(e1) * 1e-3
+            result.iters.append(it)
+            result.iter_seconds.append(int(secs))
+            result.iter_seconds_device.append(secs)
+            if tau_i is not None:
+                result.tau_vals.append(tau_to_host(tau_i))
+            if pulses_i is not None:
+                result.all_pulses.append(pulses_to_host(pulses_i))
+        # after the swap at the end of the loop the optimized pulses of the
+        # last iteration are in guess_t
+        optimized_pulses = pulses_to_host(guess_t)
+        result.optimized_controls = optimized_pulses
+        result.states = states_to_host(phiT)
+
+    # ---- finalize (optimize.py:583-590) -----------------------------------
+    result.end_local_time = time.localtime()
+    result.optimized_controls = [
+        pulse_onto_tlist(np.asarray(p)) for p in result.optimized_controls]
+    result.gpu_launches = eng.launches
+    return result

@@ -1,0 +1,354 @@
+"""GPU parity tests: the CUDA sweep path (through the C ABI, driven by
+krotov_b200.optimize_pulses) against (i) golden vectors produced by the
+unmodified reference and (ii) the numpy oracle run on the same inputs.
+
+Tolerance: BASELINE.json's north_star asks for updated pulse values within
+1e-10 relative of the reference's CPU path; the tests use PULSE_RTOL = 1e-10
+on max|eps_gpu - eps_ref| / max|eps_ref| after 1, 2 and 3 iterations.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PULSE_RTOL = 1e-10
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+@pytest.fixture(scope='module')
+def krotov():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import krotov_b200
+    krotov_b200._lib.load()
+    return krotov_b200
+
+
+def chi_of(krotov, wl):
+    if wl.chi == 'qubit_reset':
+        fixed = wl.meta['chi_fixed']
+        return lambda fw_states_T, objectives, tau_vals: [
+            fixed.copy() for _ in fw_states_T]
+    return getattr(krotov.functionals, 'chis_' + wl.chi)
+
+
+class Recorder:
+    def __init__(self, keep_states=False):
+        self.pulses, self.g_a, self.tau, self.fwT = [], [], [], []
+        self.bw = self.fw = None
+        self.keep_states = keep_states
+
+    def __call__(self, **kw):
+        self.pulses.append(np.array(kw['optimized_pulses']))
+        self.g_a.append(np.array(kw['g_a_integrals']).copy())
+        self.tau.append(np.array(kw['tau_vals']))
+        self.fwT.append(np.array(
+            [np.asarray(s).reshape(-1, order='F') for s in kw['fw_states_T']]))
+        if self.keep_states and kw['iteration'] == 1:
+            self.bw = np.array([[np.asarray(s).reshape(-1, order='F')
+                                 for s in states]
+                                for states in kw['backward_states']])
+            if kw['forward_states'] is not None:
+                self.fw = np.array([[np.asarray(s).reshape(-1, order='F')
+                                     for s in states]
+                                    for states in kw['forward_states']])
+
+
+def run_gpu(krotov, wl, iters, keep_states=False, **kw):
+    rec = Recorder(keep_states)
+    res = krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm, chi_constructor=chi_of(krotov, wl),
+        info_hook=rec, iter_stop=iters, **kw)
+    return res, rec
+
+
+def check_against_golden(rec, g, iters, tau_atol=1e-11):
+    assert np.array_equal(rec.pulses[0], g['guess_pulses'])
+    for it in range(1, iters + 1):
+        assert rel(rec.pulses[it], g['pulses'][it]) < PULSE_RTOL, it
+        assert np.allclose(rec.g_a[it], g['g_a'][it], rtol=1e-9, atol=1e-18)
+    for it in range(iters + 1):
+        assert np.allclose(rec.tau[it].astype(complex), g['tau'][it],
+                           rtol=0, atol=tau_atol)
+        assert np.allclose(rec.fwT[it], g['fw_states_T'][it], rtol=0,
+                           atol=tau_atol)
+
+
+def test_tls_fixture_golden(krotov, golden):
+    """tests/test_krotov.py fixture of the reference (oct.log rows)."""
+    g = golden('tls_fixture_qobj')
+    res, rec = run_gpu(krotov, krotov.workloads.tls_reference_fixture(), 3,
+                       keep_states=True)
+    check_against_golden(rec, g, 3)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+    J_T = [1 - np.mean(t).real for t in rec.tau]
+    for got, want in zip(J_T, [1.00, 0.765, 0.556, 0.389]):
+        assert abs(got - want) < 5e-3 * max(want, 0.1)
+    assert rel(res.optimized_controls, g['optimized_controls']) < PULSE_RTOL
+    assert res.message == 'Reached 3 iterations'
+
+
+def test_c1_chis_ss(krotov, golden):
+    _, rec = run_gpu(krotov, krotov.workloads.tls_state_to_state(), 3,
+                     keep_states=True)
+    g = golden('C1_qobj')
+    check_against_golden(rec, g, 3)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+
+
+def test_c2_transmon_n3(krotov, golden):
+    _, rec = run_gpu(krotov,
+                     krotov.workloads.transmon_xgate(nstates=1, nt=1000), 3)
+    check_against_golden(rec, golden('C2_qobj'), 3)
+
+
+def test_transmon_n5_lane_per_row(krotov, golden):
+    """N=5 uses the lane-per-row kernel family; KAT of
+    tests/test_parallelization.py:139-140 (|tau| after one iteration)."""
+    _, rec = run_gpu(krotov,
+                     krotov.workloads.transmon_xgate(nstates=2, nt=100), 2,
+                     keep_states=True)
+    g = golden('transmon_N5_nt100_qobj')
+    check_against_golden(rec, g, 2)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+    assert abs(abs(rec.tau[1][0]) - 0.9693) < 1e-3
+    assert abs(abs(rec.tau[1][1]) - 0.7743) < 1e-3
+
+
+def test_transmon_n17(krotov, golden):
+    _, rec = run_gpu(krotov,
+                     krotov.workloads.transmon_xgate(nstates=8, nt=200), 2)
+    check_against_golden(rec, golden('transmon_N17_nt200_qobj'), 2)
+
+
+def test_c3_first_order(krotov, golden):
+    _, rec = run_gpu(krotov, krotov.workloads.two_qubit_gate(nt=250), 3)
+    check_against_golden(rec, golden('C3_nt250_first_order_qobj'), 3)
+
+
+def test_c3_second_order(krotov, golden):
+    """Second-order update with sigma(t) = -max(0, 2A), A re-estimated by
+    numerical_estimate_A after every iteration (notebook 07 cell 30)."""
+    g = golden('C3_nt250_second_order_qobj')
+
+    class ConstSigma(krotov.second_order.Sigma):
+        def __init__(self, A):
+            self.A, self.A_hist = A, [A]
+
+        def __call__(self, t):
+            return -max(0.0, 2 * self.A)
+
+        def refresh(self, forward_states, forward_states0, chi_states,
+                    chi_norms, optimized_pulses, guess_pulses, objectives,
+                    result):
+            taus = result.tau_vals
+            J1 = 1 - abs(np.mean(taus[-1])) ** 2
+            J0 = 1 - abs(np.mean(taus[-2])) ** 2
+            self.A = krotov.second_order.numerical_estimate_A(
+                forward_states, forward_states0, chi_states, chi_norms,
+                J1 - J0)
+            self.A_hist.append(self.A)
+
+    sig = ConstSigma(0.5)
+    _, rec = run_gpu(krotov, krotov.workloads.two_qubit_gate(nt=250), 3,
+                     keep_states=True, sigma=sig)
+    check_against_golden(rec, g, 3)
+    assert np.allclose(sig.A_hist, g['sigma_A'], rtol=1e-7)
+    assert np.allclose(rec.fw, g['forward_states_it1'], rtol=0, atol=1e-12)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+
+
+def test_c4_small_golden(krotov, golden):
+    _, rec = run_gpu(krotov, krotov.workloads.tls_ensemble(K=8, nt=200), 3,
+                     keep_states=True)
+    g = golden('C4_K8_nt200_qobj')
+    check_against_golden(rec, g, 3)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+
+
+def test_c4_full_size_golden_and_fast_path(krotov, golden):
+    """North-star workload at full size (K=128, nt=1000) against pulses from
+    the unmodified reference; also the hook-free fast path must give the
+    same pulses as the per-iteration host loop."""
+    g = golden('C4_K128_nt1000_numpy')
+    wl = krotov.workloads.tls_ensemble(K=128, nt=1000)
+    _, rec = run_gpu(krotov, wl, 2)
+    for it in (1, 2):
+        assert rel(rec.pulses[it], g['pulses'][it]) < PULSE_RTOL
+    res = krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+        store_all_pulses=True)
+    assert len(res.all_pulses) == 3 and len(res.tau_vals) == 3
+    for it in (1, 2):
+        assert np.array_equal(np.array(res.all_pulses[it]), rec.pulses[it])
+    assert np.allclose(res.tau_vals[2], g['tau'][2], atol=1e-11)
+
+
+def test_c5_liouville(krotov, golden):
+    """Liouville space (super-operator 16x16, density matrices).  The engine
+    normalises chi with the Frobenius norm, the reference with the trace
+    norm; chi_norm * state is invariant."""
+    g = golden('C5_nt500_qobj')
+    wl = krotov.workloads.dissipative_qubit_reset(nt=500)
+    _, rec = run_gpu(krotov, wl, 3, keep_states=True)
+    check_against_golden(rec, g, 3)
+    ratio = np.sqrt(2.0) / 2.0   # Frobenius / trace norm of the fixed chi
+    assert np.allclose(rec.bw * ratio, g['backward_states_it1'], rtol=0,
+                       atol=1e-12)
+    # DensityMatrixODEPropagator instances select the same exact propagation
+    res = krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.DensityMatrixODEPropagator(
+            atol=1e-10, rtol=1e-8),
+        chi_constructor=chi_of(krotov, wl), iter_stop=1,
+        store_all_pulses=True)
+    assert rel(res.all_pulses[1], g['pulses'][1]) < PULSE_RTOL
+
+
+def test_infohook_kat_lambda_update(krotov, golden):
+    """tests/test_infohooks.py:53-67 of the reference: lambda_a halved by
+    modify_params_after_iter; info_vals[1] = 0.001978333994757067."""
+    g = golden('infohook_kat_qobj')
+    eps0 = lambda t, args: 0.5 * np.exp(  # noqa: E731
+        -40.0 * (t / 10.0 - 0.5) ** 2) * np.cos(
+            8 * np.pi * float(g['w01']) * t)
+    H = [g['H0'], [g['H1'], eps0]]
+    obj = krotov.Objective(initial_state=g['psi0'], target=g['psi1'], H=H)
+
+    def adjust(**args):
+        args['lambda_vals'][0] *= 0.5
+
+    def fid(**args):
+        return np.average(np.array(args['tau_vals']).real)
+
+    res = krotov.optimize_pulses(
+        [obj], {eps0: dict(lambda_a=1, update_shape=1)}, g['tlist'],
+        propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, info_hook=fid,
+        modify_params_after_iter=adjust, iter_stop=2)
+    assert len(res.info_vals) == 3
+    assert abs(res.info_vals[1] - 0.001978333994757067) < 1e-12
+    assert np.allclose(res.info_vals, g['info_vals'], rtol=0, atol=1e-13)
+
+
+def test_multi_cta_exchange_vs_oracle(krotov):
+    """More objectives than one CTA holds: the per-time-step sum crosses CTAs
+    through the flag-tagged exchange slots (cooperative launch)."""
+    from oracle import krotov_oracle as orc
+    wl = krotov.workloads.tls_ensemble(K=2100, nt=24)
+    res = krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+        store_all_pulses=True)
+    low = wl.lowered()
+    rec = orc.optimize(low['terms'], low['psi0'], low['targets'],
+                       low['pulses'], low['shapes'], low['lambdas'],
+                       low['tlist'], orc.chis_re, iter_stop=2)
+    for it in (1, 2):
+        assert rel(res.all_pulses[it], rec[it]['optimized_pulses']) < PULSE_RTOL
+
+
+def test_chi_constructors_on_device_vs_oracle(krotov):
+    """chis_ss / chis_sm / chis_hs with weights, device vs oracle."""
+    from oracle import krotov_oracle as orc
+    wl = krotov.workloads.tls_ensemble(K=6, nt=60)
+    wl.weights = [0.5, 1.5, 1.0, 0.7, 1.3, 1.0]
+    low = wl.lowered()
+    for name, chi in (('ss', orc.chis_ss), ('sm', orc.chis_sm),
+                      ('hs', orc.chis_hs), ('re', orc.chis_re)):
+        wl.chi = name
+        res = krotov.optimize_pulses(
+            wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+            propagator=krotov.propagators.expm,
+            chi_constructor=getattr(krotov.functionals, 'chis_' + name),
+            iter_stop=2, store_all_pulses=True)
+        rec = orc.optimize(low['terms'], low['psi0'], low['targets'],
+                           low['pulses'], low['shapes'], low['lambdas'],
+                           low['tlist'], chi, iter_stop=2,
+                           weights=wl.weights)
+        for it in (1, 2):
+            assert rel(res.all_pulses[it],
+                       rec[it]['optimized_pulses']) < PULSE_RTOL, name
+
+
+def test_large_norm_scaling_and_nonhermitian(krotov):
+    """Generators with ||A|| dt >> 1 (scaling s > 1) and non-Hermitian drift
+    (notebook 03's decay), N = 3 (thread-per-objective) and N = 6
+    (lane-per-row), against scipy.linalg.expm step by step."""
+    import scipy.linalg
+    rng = np.random.default_rng(20240603)
+    for N in (3, 6, 33):
+        H0 = rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))
+        H0 = (H0 + H0.conj().T) * (8.0 / N) - 0.3j * np.diag(
+            rng.uniform(size=N))
+        H1 = rng.normal(size=(N, N))
+        H1 = (H1 + H1.T) / 2
+        psi = rng.normal(size=(N, 1)) + 1j * rng.normal(size=(N, 1))
+        psi /= np.linalg.norm(psi)
+        tlist = np.linspace(0, 3.0, 13)
+        ctrl = lambda t, args: 0.7 * np.sin(t)  # noqa: E731
+        obj = krotov.Objective(initial_state=psi, target=psi,
+                               H=[H0, [H1, ctrl]])
+        got = {}
+
+        def grab(**kw):
+            if kw['iteration'] == 1:
+                got['bw'] = [np.asarray(s) for s in kw['backward_states'][0]]
+                got['guess'] = kw['guess_pulses'][0].copy()
+            got['fwT'] = np.asarray(kw['fw_states_T'][0])
+            got.setdefault('fwT0', got['fwT'])
+
+        krotov.optimize_pulses(
+            [obj], {ctrl: dict(lambda_a=1e9, update_shape=1)}, tlist,
+            propagator=krotov.propagators.expm,
+            chi_constructor=krotov.functionals.chis_re, info_hook=grab,
+            iter_stop=1)
+        eps = got['guess']
+        state = psi.copy()
+        for n in range(len(tlist) - 1):
+            dt = tlist[n + 1] - tlist[n]
+            state = scipy.linalg.expm(-1j * (H0 + eps[n] * H1) * dt) @ state
+        assert np.allclose(got['fwT0'], state, rtol=0,
+                           atol=1e-12 * np.linalg.norm(state)), N
+        chi = (0.5 * psi) / np.linalg.norm(0.5 * psi)
+        for n in range(len(tlist) - 2, -1, -1):
+            dt = tlist[n + 1] - tlist[n]
+            A = 1j * (H0.conj().T + eps[n] * H1.conj().T) * dt
+            chi = scipy.linalg.expm(A) @ chi
+            assert np.allclose(got['bw'][n], chi, rtol=0,
+                               atol=1e-12 * np.linalg.norm(chi)), (N, n)
+
+
+def test_property_overlap_conserved_full_size(krotov):
+    """Size-independent property at the full north-star size: under the same
+    pulses <chi_k(t_n)|phi_k(t_n)> is independent of n because the backward
+    sweep applies the exact adjoint of every forward step."""
+    import torch
+    from krotov_b200.compiler import compile_problem, initialize_controls
+    from krotov_b200.engine import SweepEngine
+    wl = krotov.workloads.tls_ensemble(K=128, nt=1000)
+    objs = wl.objectives(krotov.Objective)
+    (controls, _, pulses, mapping, lam, shp) = initialize_controls(
+        objs, wl.pulse_options, wl.tlist)
+    cp = compile_problem(objs, controls, mapping, wl.tlist)
+    eng = SweepEngine(cp, shp, lam)
+    p_t = eng.pulses_to_device(pulses)
+    Phi = eng.new_state_store()
+    phiT = eng.propagate_forward(p_t, store=Phi)
+    tau = eng.overlaps(eng.t_targets, phiT)
+    eng.chi_builtin('re', phiT, tau)
+    X = eng.sweep_backward(p_t)
+    ov = (X.conj() * Phi).sum(dim=2)          # [nt, K]
+    dev = (ov - ov[-1:]).abs().max().item()
+    assert dev < 1e-12
+    norms = (Phi.conj() * Phi).sum(dim=2).real
+    assert (norms - 1).abs().max().item() < 1e-12
+    torch.cuda.synchronize()

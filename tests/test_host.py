@@ -1,0 +1,252 @@
+"""CPU tests: host logic of the facade, the problem compiler, and the C-ABI
+library's exported symbols (no compute calls; no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import krotov_b200 as krotov
+from krotov_b200 import _lib
+from krotov_b200.compiler import compile_problem, initialize_controls
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """include/krotov_b200.h and the built .so agree."""
+    _lib.build_library()
+    header = open(os.path.join(ROOT, 'include', 'krotov_b200.h')).read()
+    declared = set(re.findall(r'\b(kq_[a-z_]+)\s*\(', header))
+    assert declared == set(_lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().kq_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    wl = krotov.workloads.tls_ensemble(K=2, nt=10)
+    with pytest.raises(krotov.EngineUnavailable):
+        krotov.optimize_pulses(
+            wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+            propagator=krotov.propagators.expm,
+            chi_constructor=krotov.functionals.chis_re, iter_stop=1)
+
+
+def test_custom_propagator_rejected():
+    wl = krotov.workloads.tls_ensemble(K=2, nt=10)
+
+    def my_prop(H, state, dt, c_ops=None, backwards=False, initialize=False):
+        return state
+
+    with pytest.raises(NotImplementedError):
+        krotov.optimize_pulses(
+            wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+            propagator=my_prop, chi_constructor=krotov.functionals.chis_re,
+            iter_stop=1)
+
+
+def test_discretisation_inverse_property():
+    """tests/test_structural_conversions.py:18-60 of the reference: pulse ->
+    control -> pulse is the identity; discretize() argument checking."""
+    from functools import partial
+    from krotov_b200.conversions import discretize
+    from krotov_b200.shapes import blackman, qutip_callback
+    tlist = np.linspace(0, 10, 20)
+    ctrl = qutip_callback(blackman, t_start=0, t_stop=10)
+    pulse_orig = krotov.conversions.control_onto_interval(
+        discretize(ctrl, tlist))
+    control = krotov.conversions.pulse_onto_tlist(pulse_orig)
+    pulse = krotov.conversions.control_onto_interval(control)
+    assert np.max(np.abs(pulse - pulse_orig)) < 1e-14
+    with pytest.raises(TypeError):
+        discretize(partial(blackman, t_start=0, t_stop=10), tlist)
+    with pytest.raises(TypeError):
+        discretize('sin(t)', tlist)
+    with pytest.raises(ValueError):
+        discretize(np.array([ctrl(t, None) for t in tlist[:-1]]), tlist)
+    arr = discretize(ctrl, tlist)
+    assert len(arr) == len(tlist)
+    assert abs(arr[0]) < 1e-15 and abs(arr[-1]) < 1e-15
+    assert np.max(np.abs(np.array([ctrl(t, None) for t in tlist]) - arr)) \
+        < 1e-15
+
+
+def test_controls_mapping_doc_example():
+    """conversions.py:186-236 of the reference."""
+    X, Y, Z = np.eye(2), np.eye(2) * 2, np.eye(2) * 3
+    u1, u2 = np.array([]), np.array([])
+    psi = np.zeros((2, 1))
+    krotov.Objective.type_checking = False
+    try:
+        c_ops = [[[X, u1]], [[Y, u2]]]
+        objs = [
+            krotov.Objective(initial_state=psi, target=psi,
+                             H=[X, [Y, u1], [Z, u1]], c_ops=c_ops),
+            krotov.Objective(initial_state=psi, target=psi,
+                             H=[X, [Y, u2]], c_ops=c_ops),
+        ]
+        controls = krotov.conversions.extract_controls(objs)
+        assert len(controls) == 2 and controls[0] is u1 and controls[1] is u2
+        m = krotov.conversions.extract_controls_mapping(objs, controls)
+        assert m == [[[[1, 2], []], [[0], []], [[], [0]]],
+                     [[[], [1]], [[0], []], [[], [0]]]]
+    finally:
+        krotov.Objective.type_checking = True
+    H = ['X', ['X', None], ['Y', None], ['Z', None]]
+    pulses = [np.array([0, 10, 0]), np.array([0, 20, 0])]
+    out = krotov.conversions.plug_in_pulse_values(H, pulses, [[1, 2], [3]], 1)
+    assert out == ['X', ['X', 10], ['Y', 10], ['Z', 20]]
+
+
+def test_pulse_options_validation():
+    """tests/test_pulse_options.py:9-70 of the reference."""
+    wl = krotov.workloads.tls_ensemble(K=1, nt=10)
+    objs = wl.objectives(krotov.Objective)
+    ctrl = list(wl.pulse_options)[0]
+    with pytest.raises(ValueError, match="lambda_a"):
+        initialize_controls(objs, {ctrl: dict(update_shape=1)}, wl.tlist)
+    with pytest.raises(ValueError, match="update_shape"):
+        initialize_controls(objs, {ctrl: dict(lambda_a=1)}, wl.tlist)
+    with pytest.raises(ValueError, match=r"range \[0, 1\]"):
+        initialize_controls(
+            objs, {ctrl: dict(lambda_a=1, update_shape=lambda t: 2.0)},
+            wl.tlist)
+    with pytest.raises(ValueError, match="pulse options"):
+        initialize_controls(objs, {}, wl.tlist)
+    with pytest.raises(ValueError, match="real-valued"):
+        initialize_controls(
+            objs, {ctrl: dict(lambda_a=1, update_shape=lambda t: 1j)},
+            wl.tlist)
+
+
+def test_compile_problem_tables():
+    """Term merging, mu table, adjoints, column-major layout."""
+    rng = np.random.default_rng(3)
+    N = 3
+    mats = [rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))
+            for _ in range(4)]
+    u1 = lambda t, a: 1.0  # noqa: E731
+    u2 = lambda t, a: 2.0  # noqa: E731
+    psi = np.ones((N, 1), dtype=complex)
+    objs = [
+        krotov.Objective(initial_state=psi, target=psi,
+                         H=[mats[0], [mats[1], u1], [mats[2], u1],
+                            [mats[3], u2]]),
+        krotov.Objective(initial_state=psi, target=psi,
+                         H=[mats[0], [mats[3], u2]]),
+    ]
+    tlist = np.linspace(0, 1, 5)
+    opts = {u1: dict(lambda_a=1, update_shape=1),
+            u2: dict(lambda_a=2, update_shape=1)}
+    controls, _, pulses, mapping, lam, shp = initialize_controls(
+        objs, opts, tlist)
+    cp = compile_problem(objs, controls, mapping, tlist)
+    assert (cp.K, cp.N, cp.L, cp.M, cp.NT) == (2, 3, 2, 3, 4)
+    assert cp.term2pulse.tolist() == [[-1, 0, 1], [-1, 1, -2]]
+    # column-major: stored[c, r] == op[r, c]
+    assert np.allclose(cp.ops[0, 1].T, mats[1] + mats[2])
+    assert np.allclose(cp.ops_adj[0, 1].T, (mats[1] + mats[2]).conj().T)
+    assert np.allclose(cp.mu[0, 0].T, mats[1] + mats[2])
+    assert np.allclose(cp.mu[1, 0], 0)
+    assert np.allclose(cp.mu[1, 1].T, mats[3])
+    assert np.allclose(cp.op_norm[0, 0], np.linalg.norm(mats[0], 1))
+    assert np.allclose(lam, [1, 2])
+    # custom mu given as callable is probed into the same table
+    def my_mu(objectives, i_objective, pulses, pulses_mapping, i_pulse,
+              time_index):
+        op = krotov.mu.derivative_wrt_pulse(
+            objectives, i_objective, pulses, pulses_mapping, i_pulse,
+            time_index)
+        if callable(op) and not isinstance(op, np.ndarray):
+            return op
+        return lambda state: op @ state
+    cp2 = compile_problem(objs, controls, mapping, tlist, mu=my_mu,
+                          pulses_for_mu=pulses)
+    assert np.allclose(cp2.mu, cp.mu)
+
+
+def test_liouvillian_matches_lindblad_rhs():
+    rng = np.random.default_rng(5)
+    d = 3
+    H = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    H = H + H.conj().T
+    C = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    rho = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    L = krotov.liouvillian(H, [C])
+    rhs = -1j * (H @ rho - rho @ H) + C @ rho @ C.conj().T - 0.5 * (
+        C.conj().T @ C @ rho + rho @ C.conj().T @ C)
+    got = (L @ rho.reshape(-1, order='F')).reshape(d, d, order='F')
+    assert np.allclose(got, rhs)
+    nested = krotov.liouvillian([H, [H, None]], [C])
+    assert np.allclose(nested[0], L) and nested[1][1] is None
+
+
+def test_gate_and_ensemble_objectives():
+    b = [np.eye(2)[:, [i]].astype(complex) for i in range(2)]
+    X = np.array([[0, 1], [1, 0]], dtype=complex)
+    H = [np.eye(2), [X, lambda t, a: 0.0]]
+    objs = krotov.gate_objectives(b, X, H)
+    assert len(objs) == 2
+    assert objs[0].target is b[1] and objs[1].target is b[0]
+    objs_w = krotov.gate_objectives(b, X, H, weights=[1, 3])
+    assert [o.weight for o in objs_w] == [0.5, 1.5]
+    with pytest.raises(ValueError):
+        krotov.gate_objectives(b, np.eye(3), H)
+    ens = krotov.ensemble_objectives(objs, [H, H])
+    assert len(ens) == 6 and ens[2].H is H
+    b4 = [np.eye(4)[:, [i]].astype(complex) for i in range(4)]
+    pe = krotov.gate_objectives(b4, 'PE', [np.eye(4)])
+    assert len(pe) == 4 and pe[0].target == 'PE'
+    assert np.allclose(pe[1].initial_state,
+                       1j * (b4[1] + b4[2]) / np.sqrt(2))
+    rho = krotov.gate_objectives(b, X, H, liouville_states_set='3states')
+    assert len(rho) == 3 and rho[0].initial_state.shape == (2, 2)
+    adj = objs[0].adjoint()
+    assert np.allclose(adj.H[1][0], X.conj().T) and adj.H[1][1] is H[1][1]
+
+
+def test_qobj_duck_typing_through_compiler():
+    """Qobj-shaped inputs (the shim's dense Qobj) compile to the same tables
+    as numpy inputs."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'ref_shims'))
+    try:
+        import qutip
+    finally:
+        sys.path.pop(0)
+    wl = krotov.workloads.transmon_xgate(nstates=2, nt=20)
+    o_np = wl.objectives(krotov.Objective)
+    o_q = wl.objectives(krotov.Objective, wrap=lambda a: qutip.Qobj(a))
+    outs = []
+    for objs in (o_np, o_q):
+        controls, _, _, mapping, _, _ = initialize_controls(
+            objs, wl.pulse_options, wl.tlist)
+        outs.append(compile_problem(objs, controls, mapping, wl.tlist))
+    assert np.array_equal(outs[0].ops, outs[1].ops)
+    assert np.array_equal(outs[0].psi0, outs[1].psi0)
+    back = outs[1].unvec(outs[1].psi0[0], o_q[0].initial_state)
+    assert isinstance(back, qutip.Qobj) and back.type == 'ket'
+
+
+def test_result_dump_load_roundtrip(tmp_path):
+    r = krotov.Result()
+    wl = krotov.workloads.tls_ensemble(K=1, nt=10)
+    r.objectives = wl.objectives(krotov.Objective)
+    r.tlist = wl.tlist
+    r.optimized_controls = [np.arange(9.0)]
+    r.guess_controls = [np.arange(10.0)]
+    r.iters = [0, 1]
+    r.message = 'x'
+    fn = str(tmp_path / 'r.dump')
+    r.dump(fn)
+    r2 = krotov.Result.load(fn, finalize=True)
+    assert len(r2.optimized_controls[0]) == 10
+    assert r2.objectives[0].H[1][1] is None   # lambda control dropped
+    r3 = krotov.Result.load(fn, objectives=r.objectives)
+    assert r3.objectives is r.objectives
