@@ -332,7 +332,14 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     iter_start + 1)
     result.states = fw_states_T
 
+    # hooks may already have modified lambda_vals / guess_pulses at iteration 0
+    # (tests/test_infohooks.py:30-37 halves lambda_a in every call)
     lam_snapshot = np.array(lambda_vals, dtype=np.float64)
+    if info_hook is not None:
+        eng.set_lambda(lambda_vals)
+        new_guess = eng.pulses_to_device(guess_pulses)
+        if not torch.equal(new_guess, guess_t):
+            guess_t.copy_(new_guess)
     deferred = []   # (iteration, tau_t, pulses_t or None, ev0, ev1) fast path
     finished_by_break = False
 
