@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the Krotov sweep hot path.
+
+Metric (BASELINE.json): Krotov iterations/sec on the 128-objective, nt=1000
+two-level ensemble (configs[3], "C4").  One *step* = one Krotov iteration =
+chi boundary -> backward sweep -> fused update/forward sweep -> tau
+(/root/reference/src/krotov/optimize.py:393-508).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Our arm prints ONE JSON line with
+  value      iterations/s with all inputs resident in HBM, timed with CUDA
+             events on the launching stream (max over ranks),
+  e2e        the same metric through the public krotov_b200.optimize_pulses
+             call with HOST (numpy) objectives and a per-iteration host hook:
+             every iteration copies its results device->host and the pulses
+             host->device inside the timed region,
+  roofline   algorithmic HBM bytes of the dominant kernel / its measured
+             duration against MEASURED_PEAKS.json,
+  cpu_baseline  the numpy oracle port of the reference loop timed on this
+             box's host cores on a bounded sample.
+The reference arm (--impl reference) times the oracle port (the reference is
+pure Python + QuTiP and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "krotov_iterations_per_sec"
+UNIT = "it/s"
+WORKLOAD = dict(workload="C4_tls_ensemble", K=128, N=2, nt=1000, L=1,
+                chi="chis_re", propagator="expm")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,"
+             "clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index),
+                 '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload():
+    import krotov_b200 as krotov
+    return krotov.workloads.tls_ensemble(K=WORKLOAD['K'], nt=WORKLOAD['nt'])
+
+
+# --------------------------------------------------------------------------
+# CPU side: the oracle port of the reference loop
+
+def time_oracle(wl, iters, k_sample=None):
+    """Seconds per Krotov iteration of the numpy oracle (serial, 1 core) on
+    the first `k_sample` objectives of `wl`, scaled to the full K (the
+    reference loop is linear in the number of objectives)."""
+    from oracle import krotov_oracle as orc
+    try:
+        import threadpoolctl
+        limiter = threadpoolctl.threadpool_limits(limits=1)
+    except Exception:
+        limiter = None
+    low = wl.lowered()
+    K = len(low['terms'])
+    ks = K if k_sample is None else max(1, min(K, k_sample))
+    terms, psi0, targets = low['terms'][:ks], low['psi0'][:ks], \
+        low['targets'][:ks]
+    pulses = [p.copy() for p in low['pulses']]
+    fw_T = [orc.forward_propagation(terms[k], pulses, low['tlist'], psi0[k],
+                                    False, store_all=False)
+            for k in range(ks)]
+    tau = np.array([np.vdot(targets[k], fw_T[k]) for k in range(ks)])
+    times = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        rec = orc.krotov_iteration(
+            terms, psi0, targets, pulses, low['shapes'], low['lambdas'],
+            low['tlist'], fw_T, tau, orc.chis_re, False)
+        times.append(time.perf_counter() - t0)
+        pulses = rec['optimized_pulses']
+        fw_T, tau = rec['fw_states_T'], rec['tau_vals']
+    if limiter is not None:
+        limiter.restore_original_limits()
+    per_iter = float(np.mean(times)) * (K / ks)
+    return per_iter, ks
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wl = build_workload()
+    total = args.steps + args.warmup
+    # bounded sample: aim at <= ~150 s for the whole run
+    per_obj_iter = 0.05   # ~s per (objective, iteration), refined below
+    budget = 150.0 / max(total, 1)
+    ks = int(max(1, min(WORKLOAD['K'], budget / per_obj_iter)))
+    per_iter_w, ks = time_oracle(wl, max(args.warmup, 1), ks)
+    per_iter, ks = time_oracle(wl, args.steps, ks)
+    value = 1.0 / per_iter
+    sample = ("%d Krotov iterations of the first %d of %d objectives, "
+              "nt=%d, time scaled by %d/%d (loop is linear in K)"
+              % (args.steps, ks, WORKLOAD['K'], WORKLOAD['nt'],
+                 WORKLOAD['K'], ks))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_iter * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+        "data": "synthetic", "config": dict(WORKLOAD),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1,
+                         "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# GPU side
+
+def run_ours(args):
+    import torch
+    import krotov_b200 as krotov
+    from krotov_b200.compiler import compile_problem, initialize_controls
+    from krotov_b200.engine import SweepEngine
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(
+            'cuda', local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    wl = build_workload()
+    objectives = wl.objectives(krotov.Objective)
+    (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(
+        objectives, wl.pulse_options, wl.tlist)
+    cp = compile_problem(objectives, controls, mapping, wl.tlist)
+    eng = SweepEngine(cp, shp, lam)
+    if world > 1:
+        from krotov_b200 import multigpu
+        multigpu.attach(eng, dist)
+    K, N, NT, L = cp.K, cp.N, cp.NT, cp.L
+    stream = torch.cuda.current_stream()
+
+    # ---- device-resident steps ---------------------------------------------
+    guess_t = eng.pulses_to_device(guess_pulses)
+    opt_t = guess_t.clone()
+    phiT = eng.propagate_forward(guess_t)
+    tau_t = eng.overlaps(eng.t_targets, phiT)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32,
+                        device=eng.device)   # 256 MB > 126 MB L2
+
+    def one_iteration(ev=None):
+        nonlocal guess_t, opt_t, phiT, tau_t
+        eng.chi_builtin('re', phiT, tau_t)
+        if ev:
+            ev[0].record(stream)
+        eng.sweep_backward(guess_t)
+        if ev:
+            ev[1].record(stream)
+        phiT = eng.sweep_forward_update(guess_t, opt_t, phiT=phiT)
+        if ev:
+            ev[2].record(stream)
+        tau_t = eng.overlaps(eng.t_targets, phiT)
+        guess_t, opt_t = opt_t, guess_t
+
+    for _ in range(args.warmup):
+        one_iteration()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    t_iter, t_bw, t_fw = [], [], []
+    barrier()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()          # evict L2 between timed iterations (untimed)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        e[3].record(stream)
+        one_iteration(e)
+        e[4].record(stream)
+        e[4].synchronize()
+        t_iter.append(e[3].elapsed_time(e[4]))
+        t_bw.append(e[0].elapsed_time(e[1]))
+        t_fw.append(e[1].elapsed_time(e[2]))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = eng.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if eng.status() != 0:
+        raise RuntimeError("exchange failure in sweep kernel")
+    total_ms = float(np.sum(t_iter))
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+
+    # ---- end to end through the public API, host buffers ------------------
+    stamps = []
+
+    def hook(**kw):
+        stamps.append(time.perf_counter())
+        return 1 - np.mean(kw['tau_vals']).real
+
+    n_e2e = args.warmup + args.steps
+    t0 = time.perf_counter()
+    res = krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, info_hook=hook,
+        iter_stop=n_e2e)
+    t_call = time.perf_counter() - t0
+    steady = (stamps[-1] - stamps[args.warmup]) / args.steps
+    e2e_value = 1.0 / steady
+    d2h_step = (2 * L * NT * 8) + 8 * max(L, 1) + K * N * 16 + K * 16 + 4
+    h2d_step = L * NT * 8
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": h2d_step, "d2h_bytes_per_step": d2h_step,
+           "whole_call_value": n_e2e / t_call,
+           "whole_call_seconds": t_call,
+           "api": "krotov_b200.optimize_pulses(numpy objectives, info_hook)",
+           "measured_total_h2d_bytes": res.h2d_bytes,
+           "measured_total_d2h_bytes": res.d2h_bytes}
+    if dist is not None:
+        t = torch.tensor([steady], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["value"] = 1.0 / float(t.item())
+
+    # ---- roofline of the dominant kernel -----------------------------------
+    peaks, which = load_peaks()
+    fw_ms, bw_ms = float(np.mean(t_fw)), float(np.mean(t_bw))
+    dominant = "k_fwupd_small (fused update+forward sweep)" \
+        if fw_ms >= bw_ms else "k_prop_small (backward sweep)"
+    alg_bytes = 16.0 * K * (NT + 1) * N    # X read (fw) or written (bw)
+    dom_ms = max(fw_ms, bw_ms)
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+        "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+        "traffic": None, "peak_source": which + " (burst copy)",
+        "kernel": dominant, "kernel_ms": dom_ms,
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "fw_sweep_ms": fw_ms, "bw_sweep_ms": bw_ms,
+        "ns_per_time_step_fw": fw_ms * 1e6 / NT,
+        "ns_per_time_step_bw": bw_ms * 1e6 / NT,
+        "note": "sequential chain of nt-1 dependent steps; working set "
+                "(%.1f MB) is L2-resident, see DESIGN.md" % (
+                    2 * alg_bytes / 1e6),
+    }
+    traffic_file = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                roofline["traffic"] = json.load(fh).get(
+                    "fw" if fw_ms >= bw_ms else "bw")
+        except Exception:
+            pass
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        per_iter, ks = time_oracle(wl, 2, k_sample=48)
+        cpu = {"value": 1.0 / per_iter, "unit": UNIT, "cores": 1,
+               "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": "2 Krotov iterations of the first %d of %d "
+                         "objectives at nt=%d, time scaled by %d/%d"
+                         % (ks, K, NT + 1, K, ks)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+            "data": "synthetic",
+            "config": dict(WORKLOAD, l2="flushed between timed iterations "
+                           "(256 MB write)", parallelism=(
+                               "1 GPU" if world == 1 else
+                               "objectives sharded over %d GPUs" % world)),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "wall_seconds_timed_region": wall,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true',
+                    help='skip the CPU baseline leg')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -13,6 +13,7 @@
 #include "../../include/krotov_b200.h"
 #include "kq_common.cuh"
 #include "kq_small.cuh"
+#include "kq_spec.cuh"
 #include "kq_warp.cuh"
 
 namespace {
@@ -102,6 +103,7 @@ int check_problem(const kq_problem* p) {
 }
 
 struct Plan {
+  int spec;    // specialised M=2 (L=1) straight-line kernels (kq_spec.cuh)
   int family;  // 0 thread-per-objective, 1 lane-per-row
   int grid, block;
   size_t smem;
@@ -118,9 +120,14 @@ int make_plan(const kq_problem* p, bool update, int sms, Plan& pl) {
   std::memset(&pl, 0, sizeof pl);
   if (N <= 4 && M <= KQ_MMAX_SMALL) {
     pl.family = 0;
-    const size_t per_thread = (size_t)(M + (update ? L : 0)) * NN * sizeof(cplx);
-    const size_t fixed = (2 * KQ_LMAX * 32 + 2 * KQ_LMAX) * sizeof(double);
-    int cap = (int)((kSmemBudget - fixed) / per_thread) / 32 * 32;
+    pl.spec = (N >= 2 && M == 2 && (!update || L == 1)) ? 1 : 0;
+    size_t per_thread = (size_t)(M + (update ? L : 0)) * NN * sizeof(cplx);
+    size_t fixed = (2 * KQ_LMAX * 32 + 2 * KQ_LMAX) * sizeof(double);
+    if (pl.spec) {
+      per_thread = (N == 4) ? (size_t)2 * NN * sizeof(cplx) : 0;
+      fixed = 66 * sizeof(double);
+    }
+    int cap = per_thread ? (int)((kSmemBudget - fixed) / per_thread) / 32 * 32 : 1024;
     const int maxbt = update ? KQ_SMALL_MAXBT(N) : 256;
     if (cap > maxbt) cap = maxbt;
     if (cap < 32) return fail(KQ_ERR_UNSUPPORTED, "generator terms do not fit shared memory");
@@ -224,6 +231,14 @@ int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** 
 template <int N>
 int launch_prop_small(const KqSweepArgs& a, const Plan& pl, int fsel, cudaStream_t st) {
   void* params[] = {(void*)&a};
+  if (pl.spec) {
+    constexpr int NS = (N >= 2) ? N : 2;
+    switch (fsel) {
+      case 0: return launch(k_prop_spec<NS, 0>, pl, false, st, params);
+      case 1: return launch(k_prop_spec<NS, 1>, pl, false, st, params);
+      default: return launch(k_prop_spec<NS, 2>, pl, false, st, params);
+    }
+  }
   switch (fsel) {
     case 0: return launch(k_prop_small<N, 0>, pl, false, st, params);
     case 1: return launch(k_prop_small<N, 1>, pl, false, st, params);
@@ -236,6 +251,24 @@ int launch_fwupd_small(const KqSweepArgs& a, const Plan& pl, int fsel, bool seco
                        cudaStream_t st) {
   void* params[] = {(void*)&a};
   const bool coop = pl.grid > 1;
+  if (pl.spec) {
+    constexpr int NS = (N >= 2) ? N : 2;
+    constexpr int BIG = (NS <= 2) ? 1024 : 256;
+    if (NS <= 2 && pl.block > 256) {
+      if (fsel == 0) {
+        return second ? launch(k_fwupd_spec<NS, 0, true, BIG>, pl, coop, st, params)
+                      : launch(k_fwupd_spec<NS, 0, false, BIG>, pl, coop, st, params);
+      }
+      return second ? launch(k_fwupd_spec<NS, 2, true, BIG>, pl, coop, st, params)
+                    : launch(k_fwupd_spec<NS, 2, false, BIG>, pl, coop, st, params);
+    }
+    if (fsel == 0) {
+      return second ? launch(k_fwupd_spec<NS, 0, true, 256>, pl, coop, st, params)
+                    : launch(k_fwupd_spec<NS, 0, false, 256>, pl, coop, st, params);
+    }
+    return second ? launch(k_fwupd_spec<NS, 2, true, 256>, pl, coop, st, params)
+                  : launch(k_fwupd_spec<NS, 2, false, 256>, pl, coop, st, params);
+  }
   if (N <= 2 && pl.block > 256) {
     constexpr int BT = (N <= 2) ? 1024 : 256;
     if (fsel == 0) {

@@ -44,13 +44,17 @@ class SweepEngine:
             'cuda', torch.cuda.current_device()) if device is None \
             else torch.device(device)
         self.cp = cp
-        self.launches = 0
+        self.launches = 0       # kernels launched through the C ABI
+        self.h2d_bytes = 0      # host->device traffic issued by the engine
+        self.d2h_bytes = 0
         dev = self.device
         c128, f64 = torch.complex128, torch.float64
 
         def up(a, dtype):
-            return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype,
-                                   device=dev)
+            t = torch.as_tensor(np.ascontiguousarray(a), dtype=dtype,
+                                device=dev)
+            self.h2d_bytes += t.numel() * t.element_size()
+            return t
 
         self.t_ops = up(cp.ops, c128)
         self.t_ops_adj = up(cp.ops_adj, c128)
@@ -97,17 +101,27 @@ class SweepEngine:
                                 dtype=self.torch.complex128,
                                 device=self.device)
 
+    def upload(self, array, dtype):
+        t = self.torch.as_tensor(np.ascontiguousarray(array), dtype=dtype,
+                                 device=self.device)
+        self.h2d_bytes += t.numel() * t.element_size()
+        return t
+
+    def download(self, tensor):
+        self.d2h_bytes += tensor.numel() * tensor.element_size()
+        return tensor.cpu().numpy()
+
     def pulses_to_device(self, pulses):
         arr = np.array(pulses, dtype=np.float64).reshape(self.cp.L,
                                                          self.cp.NT)
-        return self.torch.as_tensor(arr, dtype=self.torch.float64,
-                                    device=self.device)
+        return self.upload(arr, self.torch.float64)
 
     def set_lambda(self, lambda_vals):
         """Refresh the device copy of lambda_a (hooks may change it between
         iterations, optimize.py:552-555 / tests/test_infohooks.py:30-37)."""
         self.t_lambda.copy_(self.torch.as_tensor(
             np.asarray(lambda_vals, dtype=np.float64)))
+        self.h2d_bytes += 8 * self.cp.L
 
     def plan(self):
         """(family, grid, block, smem) the fused sweep uses."""
@@ -187,8 +201,10 @@ class SweepEngine:
             arr = arr / norms[:, None]
         self.chi.copy_(self.torch.as_tensor(arr))
         self.chi_norms.copy_(self.torch.as_tensor(norms))
+        self.h2d_bytes += arr.nbytes + norms.nbytes
         return norms
 
     def status(self):
         """Exchange status word (0 = ok); synchronises."""
+        self.d2h_bytes += 4
         return int(self.workspace[:4].view(self.torch.int32).item())

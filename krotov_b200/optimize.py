@@ -45,8 +45,9 @@ class _LazyStates:
     during the iteration in which it is handed to a hook (the device buffers
     are re-used by the next iteration)."""
 
-    def __init__(self, tensor, cp):
+    def __init__(self, tensor, cp, eng=None):
         self._tensor, self._cp, self._host = tensor, cp, None
+        self._eng = eng
         self._expired = False
 
     def _data(self):
@@ -55,7 +56,8 @@ class _LazyStates:
                 raise RuntimeError(
                     "state storage is only valid during the iteration it "
                     "was passed to a hook; copy what you need inside the hook")
-            self._host = self._tensor.cpu().numpy()
+            self._host = (self._eng.download(self._tensor) if self._eng
+                          else self._tensor.cpu().numpy())
         return self._host
 
     def _expire(self):
@@ -232,17 +234,17 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     has_targets = cp.targets is not None
 
     def states_to_host(t):
-        arr = t.cpu().numpy()
+        arr = eng.download(t)
         return [cp.unvec(arr[k].copy(), cp.state_templates[k])
                 for k in range(K)]
 
     def tau_to_host(tau_t):
         if tau_t is None:
             return np.array([None] * K)
-        return tau_t.cpu().numpy().copy()
+        return eng.download(tau_t).copy()
 
     def pulses_to_host(p_t):
-        arr = p_t.cpu().numpy()
+        arr = eng.download(p_t)
         return [arr[l].copy() for l in range(L)]
 
     g_a_integrals = np.zeros(L)
@@ -260,9 +262,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     if skip_initial_forward_propagation:
         if continue_from is not None:
             fw_states_T = list(continue_from.states)
-            phiT = torch.as_tensor(
-                np.array([cp.vec(s) for s in fw_states_T]),
-                dtype=torch.complex128, device=eng.device)
+            phiT = eng.upload(np.array([cp.vec(s) for s in fw_states_T]),
+                              torch.complex128)
         else:
             logger.warning(
                 "You should not use `skip_initial_forward_propagation` "
@@ -289,7 +290,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
 
     forward_states = forward_states0 = None
     if second_order:
-        forward_states0 = forward_states = _LazyStates(Phi0, cp)
+        forward_states0 = forward_states = _LazyStates(Phi0, cp, eng)
 
     info = None
     optimized_pulses = copy.deepcopy(guess_pulses)
@@ -373,8 +374,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             sig = np.array([
                 float(sigma(tlist[n] + 0.5 * (tlist[n + 1] - tlist[n])))
                 for n in range(NT)])
-            sigma_t = torch.as_tensor(sig, dtype=torch.float64,
-                                      device=eng.device)
+            sigma_t = eng.upload(sig, torch.float64)
         phiT = eng.sweep_forward_update(
             guess_t, opt_t, phiT=phiT, sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
         tau_t = eng.overlaps(eng.t_targets, phiT) if has_targets else None
@@ -396,13 +396,13 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                                % st)
         guess_pulses_host = pulses_to_host(guess_t)
         optimized_pulses = pulses_to_host(opt_t)
-        g_a_integrals[:] = eng.g_a.cpu().numpy()[:L]
+        g_a_integrals[:] = eng.download(eng.g_a)[:L]
         fw_states_T = states_to_host(phiT)
         tau_vals = tau_to_host(tau_t)
-        backward_states = _LazyStates(eng.X, cp)
+        backward_states = _LazyStates(eng.X, cp, eng)
         if second_order:
-            forward_states = _LazyStates(Phi1, cp)
-            forward_states0 = _LazyStates(Phi0, cp)
+            forward_states = _LazyStates(Phi1, cp, eng)
+            forward_states0 = _LazyStates(Phi0, cp, eng)
         toc = time.time()
 
         if info_hook is not None:
@@ -454,12 +454,12 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         guess_t, opt_t = opt_t, guess_t
         if second_order:
             if chi_states is None:
-                chi_arr = eng.chi.cpu().numpy()
+                chi_arr = eng.download(eng.chi)
                 chi_states = [cp.unvec(chi_arr[k].copy(),
                                        cp.state_templates[k])
                               for k in range(K)]
                 if chi_norms is None:
-                    chi_norms = list(eng.chi_norms.cpu().numpy())
+                    chi_norms = list(eng.download(eng.chi_norms))
             sigma.refresh(
                 forward_states=forward_states,
                 forward_states0=forward_states0, chi_states=chi_states,
@@ -501,4 +501,5 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     result.optimized_controls = [
         pulse_onto_tlist(np.asarray(p)) for p in result.optimized_controls]
     result.gpu_launches = eng.launches
+    result.h2d_bytes, result.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
     return result
