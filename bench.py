@@ -106,7 +106,23 @@ class ClockSampler:
 
 def build_workload():
     import krotov_b200 as krotov
-    return krotov.workloads.tls_ensemble(K=WORKLOAD['K'], nt=WORKLOAD['nt'])
+    name = WORKLOAD['workload']
+    if name == 'C4_tls_ensemble':
+        return krotov.workloads.tls_ensemble(K=WORKLOAD['K'],
+                                             nt=WORKLOAD['nt'])
+    wl = krotov.workloads.by_name(name[:2])
+    low = wl.lowered()
+    WORKLOAD.update(K=wl.K, N=len(low['psi0'][0]), nt=wl.nt,
+                    chi='chis_' + wl.chi)
+    return wl
+
+
+def chi_of(krotov, wl):
+    if wl.chi == 'qubit_reset':
+        fixed = wl.meta['chi_fixed']
+        return lambda fw_states_T, objectives, tau_vals: [
+            fixed.copy() for _ in fw_states_T]
+    return getattr(krotov.functionals, 'chis_' + wl.chi)
 
 
 # --------------------------------------------------------------------------
@@ -223,9 +239,15 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32,
                         device=eng.device)   # 256 MB > 126 MB L2
 
+    fixed_chi = None
+    if wl.chi == 'qubit_reset':
+        fixed_chi = [cp.vec(wl.meta['chi_fixed']) for _ in range(K)]
+        eng.chi_from_host(fixed_chi)
+
     def one_iteration(ev=None):
         nonlocal guess_t, opt_t, phiT, tau_t
-        eng.chi_builtin('re', phiT, tau_t)
+        if fixed_chi is None:
+            eng.chi_builtin(wl.chi, phiT, tau_t)
         if ev:
             ev[0].record(stream)
         eng.sweep_backward(guess_t)
@@ -283,7 +305,7 @@ def run_ours(args):
     res = krotov.optimize_pulses(
         wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
         propagator=krotov.propagators.expm,
-        chi_constructor=krotov.functionals.chis_re, info_hook=hook,
+        chi_constructor=chi_of(krotov, wl), info_hook=hook,
         iter_stop=n_e2e)
     t_call = time.perf_counter() - t0
     steady = (stamps[-1] - stamps[args.warmup]) / args.steps
@@ -305,8 +327,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel -----------------------------------
     peaks, which = load_peaks()
     fw_ms, bw_ms = float(np.mean(t_fw)), float(np.mean(t_bw))
-    dominant = "k_fwupd_small (fused update+forward sweep)" \
-        if fw_ms >= bw_ms else "k_prop_small (backward sweep)"
+    dominant = "fused update+forward sweep kernel" \
+        if fw_ms >= bw_ms else "backward sweep kernel"
     alg_bytes = 16.0 * K * (NT + 1) * N    # X read (fw) or written (bw)
     dom_ms = max(fw_ms, bw_ms)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
@@ -370,7 +392,18 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true',
                     help='skip the CPU baseline leg')
+    ap.add_argument('--workload', default='C4',
+                    help='C4 (contract workload) or C1/C2/C3/C5/C4sat for '
+                         'additional measurements')
     args = ap.parse_args()
+    if args.workload == 'C4sat':
+        WORKLOAD.update(workload='C4_tls_ensemble', K=131072)
+        args.no_cpu = True
+    elif args.workload != 'C4':
+        names = {'C1': 'C1_tls_state_to_state', 'C2': 'C2_transmon_xgate',
+                 'C3': 'C3_two_qubit_gate', 'C5': 'C5_dissipative_qubit_reset'}
+        WORKLOAD.update(workload=names[args.workload])
+        args.no_cpu = True
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':

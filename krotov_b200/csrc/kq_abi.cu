@@ -115,7 +115,7 @@ int round_up(int v, int q) { return (v + q - 1) / q * q; }
 
 // update = fused sweep (objectives should share a CTA); otherwise spread
 // independent objectives over the SMs.
-int make_plan(const kq_problem* p, bool update, int sms, Plan& pl) {
+int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) {
   const int K = p->K, N = p->N, M = p->M, L = p->L, NN = N * N;
   std::memset(&pl, 0, sizeof pl);
   if (N <= 4 && M <= KQ_MMAX_SMALL) {
@@ -125,7 +125,13 @@ int make_plan(const kq_problem* p, bool update, int sms, Plan& pl) {
     size_t fixed = (2 * KQ_LMAX * 32 + 2 * KQ_LMAX) * sizeof(double);
     if (pl.spec) {
       per_thread = (N == 4) ? (size_t)2 * NN * sizeof(cplx) : 0;
-      fixed = 66 * sizeof(double);
+      if (update) {
+        per_thread += (size_t)KQ_RING * N * sizeof(cplx) * (second ? 2 : 1);
+        fixed = 72 * sizeof(double) + KQ_RING * sizeof(uint64_t) +
+                5 * KQ_NTC * sizeof(double) + KQ_NTC;
+      } else {
+        fixed = 2 * KQ_NTC * sizeof(double) + KQ_NTC + 32 * sizeof(double);
+      }
     }
     int cap = per_thread ? (int)((kSmemBudget - fixed) / per_thread) / 32 * 32 : 1024;
     const int maxbt = update ? KQ_SMALL_MAXBT(N) : 256;
@@ -317,7 +323,7 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   rc = device_init(&dev);
   if (rc) return rc;
   Plan pl;
-  rc = make_plan(p, false, g_dev[dev].sms, pl);
+  rc = make_plan(p, false, false, g_dev[dev].sms, pl);
   if (rc) return rc;
   KqSweepArgs a = base_args(p);
   a.ops = reinterpret_cast<const cplx*>(backward ? p->ops_adj : p->ops);
@@ -407,7 +413,7 @@ int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
   int rc = check_problem(p);
   if (rc) return rc;
   Plan pl;
-  rc = make_plan(p, true, 148, pl);
+  rc = make_plan(p, true, false, 148, pl);
   if (rc) return rc;
   if (family) *family = pl.family;
   if (grid) *grid = pl.grid;
@@ -444,7 +450,7 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   rc = device_init(&dev);
   if (rc) return rc;
   Plan pl;
-  rc = make_plan(p, true, g_dev[dev].sms, pl);
+  rc = make_plan(p, true, second, g_dev[dev].sms, pl);
   if (rc) return rc;
   if (pl.grid > kMaxBlocks) return fail(KQ_ERR_UNSUPPORTED, "too many CTAs (%d)", pl.grid);
   KqSweepArgs a = base_args(p);

@@ -2,31 +2,74 @@
 // one drift term + one control term (M = 2) driven by a single pulse (L = 1),
 // N <= 4 -- BASELINE configs C1..C4 all have this shape.
 //
-// Compared with the generic kernels in kq_small.cuh the per-time-step
-// instruction stream is straight-line:
-//  * generator terms (pre-multiplied by the equation-of-motion factor f) are
-//    kept in registers for N <= 3 (shared memory for N = 4);
+// The sweep is a chain of nt-1 dependent steps, so the design goal is the
+// shortest possible per-step instruction stream on the critical path:
+//  * generator terms (pre-multiplied by the equation-of-motion factor f) sit
+//    in registers for N <= 3 (shared memory for N = 4);
+//  * per-step scalars (dt, guess pulse, S/lambda, sigma) are staged in shared
+//    memory in chunks of KQ_NTC steps, so no global-load latency and no
+//    division sits on the chain;
+//  * the backward states chi(t_n) (and Phi0 for second order) are streamed
+//    HBM -> shared memory by TMA bulk copies (cp.async.bulk + mbarrier) into a
+//    ring KQ_RING steps deep: one contiguous K_cta*N*16-byte row per step
+//    thanks to the time-major [nt][K][N] layout;
 //  * the Horner/Taylor recurrence is entered through a fall-through switch on
-//    a warp-uniform degree, with 1/j as immediates;
-//  * the Taylor degree is planned from the *guess* pulse before the
-//    cross-objective reduction (off the sequential chain) and verified after
-//    the step; the rare violation replays the step with the exact degree;
-//  * <chi| mu |phi> is evaluated as <mu^dag chi | phi> with mu^dag chi (times
-//    ||chi||) prepared one step ahead from the prefetched backward state, so
-//    only an N-term dot product sits on the chain (first order).
+//    a warp-uniform degree with 1/j as immediates; the degree is planned from
+//    the *guess* pulse before the cross-objective reduction and verified after
+//    the step (a violation replays the step with the exact plan);
+//  * <chi| mu |phi> is evaluated as <mu^dag chi | phi>, with mu^dag chi (times
+//    ||chi||) prepared one step ahead, so only an N-term dot product sits on
+//    the chain (first order).
 #pragma once
 #include "kq_common.cuh"
 #include "kq_small.cuh"
 
-// y <- v + (1/J) * (At y)   for At = h f A (column-major, registers)
+#define KQ_NTC 512   // time steps of scalars staged per chunk
+#define KQ_RING 4    // depth of the TMA ring for state rows
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX) -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "KQ_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra KQ_DONE_%=;\n"
+      "bra KQ_WAIT_%=;\n"
+      "KQ_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// y <- v + invj * (At y)   for At = h f A (column-major, registers)
 template <int N>
 __device__ __forceinline__ void horner_step(const cplx (&At)[N * N], const cplx (&v)[N],
                                             cplx (&y)[N], double invj) {
   cplx w[N];
 #pragma unroll
   for (int r = 0; r < N; ++r) {
-    // two partial sums shorten the dependent chain
-    cplx a0 = c_zero(), a1 = c_zero();
+    cplx a0 = c_zero(), a1 = c_zero();  // two partial sums shorten the chain
 #pragma unroll
     for (int c = 0; c < N; ++c) {
       if (c & 1)
@@ -40,38 +83,56 @@ __device__ __forceinline__ void horner_step(const cplx (&At)[N * N], const cplx 
   for (int r = 0; r < N; ++r) y[r] = c_fma_real(invj, w[r], v[r]);
 }
 
-// y <- exp(At) y by an m-term Horner/Taylor recurrence (m warp-uniform).
-template <int N>
-__device__ __forceinline__ void expmv_spec(const cplx (&At)[N * N], cplx (&y)[N], int m) {
-  cplx v[N];
+// y <- exp(At) v with a compile-time Taylor degree M (fully unrolled, 1/j immediates).
+template <int N, int M>
+__device__ __forceinline__ void expmv_fixed(const cplx (&At)[N * N], const cplx (&v)[N],
+                                            cplx (&y)[N]) {
 #pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = y[i];
-  for (; m > 8; --m) horner_step<N>(At, v, y, c_kq_tables.inv[m]);
-  switch (m) {
-    case 8: horner_step<N>(At, v, y, 1.0 / 8.0);
-    case 7: horner_step<N>(At, v, y, 1.0 / 7.0);
-    case 6: horner_step<N>(At, v, y, 1.0 / 6.0);
-    case 5: horner_step<N>(At, v, y, 1.0 / 5.0);
-    case 4: horner_step<N>(At, v, y, 1.0 / 4.0);
-    case 3: horner_step<N>(At, v, y, 1.0 / 3.0);
-    case 2: horner_step<N>(At, v, y, 1.0 / 2.0);
-    default: horner_step<N>(At, v, y, 1.0);
+  for (int i = 0; i < N; ++i) y[i] = v[i];
+#pragma unroll
+  for (int j = M; j >= 1; --j) horner_step<N>(At, v, y, 1.0 / (double)j);
+}
+
+// y <- exp(At)^s v, run-time degree (generic path: s > 1 or m > KQ_MFIX)
+template <int N>
+__device__ __forceinline__ void expmv_generic(const cplx (&At)[N * N], const cplx (&v)[N],
+                                              cplx (&y)[N], int s, int m) {
+  cplx in[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) in[i] = v[i];
+  for (int rep = 0; rep < s; ++rep) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) y[i] = in[i];
+    for (int j = m; j >= 1; --j) horner_step<N>(At, in, y, c_kq_tables.inv[j]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) in[i] = y[i];
   }
 }
 
-// Warp-uniform (s, m, bound): plan for the largest norm bound in the warp.
-// `bound` is the largest x for which the plan is still valid.
-__device__ __forceinline__ void plan_uniform(double x, int& s, int& m, double& bound) {
-  const int hi = __reduce_max_sync(0xffffffffu, __double2hiint(x));
-  const double xu = __hiloint2double(hi, (int)0xffffffff);  // >= every x in the warp
+#define KQ_MFIX 8   // Taylor degrees 1..KQ_MFIX have fully unrolled step bodies
+
+// Plan for a norm bound x: (s, m) and the largest x for which it stays valid.
+__device__ __forceinline__ void plan_bound(double x, int& s, int& m, double& bound) {
   double xs;
-  taylor_plan(c_kq_tables, xu, s, m, xs);
-  // valid up to the top of the binade of xs (times s)
+  taylor_plan(c_kq_tables, x, s, m, xs);
   const int e = (__double2hiint(xs) >> 20) & 0x7ff;
-  double top = __hiloint2double((e + 1) << 20, 0);  // 2^(E+1)
+  double top = __hiloint2double((e + 1) << 20, 0);  // top of the binade of xs
   if (e >= 1022) top = 1.0;                         // xs <= 1 always
   if (e == 0) top = 0.0;
   bound = top * (double)s;
+}
+
+// CTA-wide maximum of a non-negative double (all threads call; uses `scratch[32]`).
+__device__ __forceinline__ double block_max(double v, double* scratch) {
+  v = warp_allreduce_max(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = scratch[0];
+  for (int w = 1; w < nw; ++w) r = fmax(r, scratch[w]);
+  __syncthreads();
+  return r;
 }
 
 // Terms of one objective, pre-rotated by f: T0f = f*T0, T1f = f*T1.
@@ -113,15 +174,56 @@ struct SpecTerms {
   }
 };
 
-template <int N>
-__device__ __forceinline__ void spec_step(const cplx (&At_full)[N * N], cplx (&y)[N], int s,
-                                          int m) {
-  // At_full = dt f A ; for s > 1 the caller has already divided by s
-  for (int rep = 0; rep < s; ++rep) expmv_spec<N>(At_full, y, m);
-}
-
 // ---------------------------------------------------------------------------
 // Propagation sweeps (optimize.py:806-886), M = 2.
+// shared: [sdt KQ_NTC][spulse KQ_NTC][splan KQ_NTC bytes][scratch 32][terms (N = 4)]
+template <int N, bool INREG>
+struct PropCtx {
+  SpecTerms<N, INREG> T;
+  cplx y[N];
+  const double* sdt;
+  const double* sp;
+  const unsigned char* splan;
+  const double* pulse;   // global pulse row when not staged
+  cplx* store;           // row pointer base for this objective, or null
+  size_t row_stride;     // K*N
+  bool driven, staged, valid;
+  double c1_fixed, opn0, opn1;
+  int base, dir;         // chunk base index, +1 forward / -1 backward
+};
+
+// Run consecutive steps j (moving by c.dir) while their planned degree is MT.
+template <int N, bool INREG, int MT>
+__device__ __forceinline__ int prop_run(PropCtx<N, INREG>& c, int j, int jend) {
+  constexpr int NN = N * N;
+  while (j != jend && c.splan[j] == MT) {
+    const int n = c.base + j;
+    const double dtn = c.sdt[j];
+    const double eps = c.driven ? (c.staged ? c.sp[j] : c.pulse[n]) : c.c1_fixed;
+    cplx At[NN], out[N];
+    if (MT > 0) {
+      c.T.assemble(dtn, dtn * eps, At);
+      expmv_fixed<N, (MT > 0 ? MT : 1)>(At, c.y, out);
+    } else {
+      int s, m;
+      double bound;
+      plan_bound(dtn * fma(fabs(eps), c.opn1, c.opn0), s, m, bound);
+      const double h = dtn / (double)s;
+      c.T.assemble(h, h * eps, At);
+      expmv_generic<N>(At, c.y, out, s, m);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) c.y[i] = out[i];
+    if (c.store && c.valid) {
+      const size_t row = (c.dir < 0) ? (size_t)n : (size_t)n + 1;
+#pragma unroll
+      for (int i = 0; i < N; ++i) c.store[row * c.row_stride + i] = out[i];
+    }
+    j += c.dir;
+  }
+  return j;
+}
+
 template <int N, int FSEL>
 __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -131,246 +233,383 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   const int K = a.K, NT = a.NT;
   int k = blockIdx.x * BT + tid;
   const bool valid = k < K;
-  if (!valid) k = K - 1;  // keep the warp converged for the uniform plan
-  SpecTerms<N, INREG> T;
-  T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
-                        reinterpret_cast<cplx*>(smem_raw), BT, tid);
-  const double opn0 = a.op_norm[k * 2 + 0], opn1 = a.op_norm[k * 2 + 1];
+  if (!valid) k = K - 1;  // shadow thread: keeps the CTA converged
+  double* sdt = reinterpret_cast<double*>(smem_raw);
+  double* sp = sdt + KQ_NTC;
+  unsigned char* splan = reinterpret_cast<unsigned char*>(sp + KQ_NTC);
+  double* scratch = reinterpret_cast<double*>(splan + KQ_NTC);
+  PropCtx<N, INREG> c;
+  c.T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
+                          reinterpret_cast<cplx*>(scratch + 32), BT, tid);
+  c.opn0 = a.op_norm[k * 2 + 0];
+  c.opn1 = a.op_norm[k * 2 + 1];
   const int l = a.term2pulse[k * 2 + 1];
-  const double* pulse = (l >= 0) ? a.pulses + (size_t)l * NT : nullptr;
-  const double c1_fixed = (l == -1) ? 1.0 : 0.0;
-
-  cplx y[N];
+  c.driven = l >= 0;
+  c.c1_fixed = (l == -1) ? 1.0 : 0.0;
+  c.staged = (a.L == 1);
+  c.pulse = c.driven ? a.pulses + (size_t)l * NT : nullptr;
+  c.valid = valid;
+  c.sdt = sdt;
+  c.sp = sp;
+  c.splan = splan;
+  c.store = a.store ? a.store + (size_t)k * N : nullptr;
+  c.row_stride = (size_t)K * N;
+  c.dir = a.backward ? -1 : 1;
+  // CTA-wide norm bounds for the per-step Taylor plan
+  const double O0 = block_max(c.opn0, scratch);
+  const double O1 = block_max(c.driven ? c.opn1 : 0.0, scratch);
+  const double Oc = block_max(c.driven ? 0.0 : c.c1_fixed * c.opn1, scratch);
 #pragma unroll
-  for (int i = 0; i < N; ++i) y[i] = a.state0[(size_t)k * N + i];
-  const int n_first = a.backward ? NT - 1 : 0, n_step = a.backward ? -1 : 1;
+  for (int i = 0; i < N; ++i) c.y[i] = a.state0[(size_t)k * N + i];
   if (a.store && valid) {
     const size_t row = a.backward ? (size_t)NT : 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) a.store[(row * K + k) * N + i] = y[i];
+    for (int i = 0; i < N; ++i) c.store[row * c.row_stride + i] = c.y[i];
   }
-  double eps = pulse ? pulse[n_first] : c1_fixed;
-  double dtn = a.dt[n_first];
-  for (int it = 0, n = n_first; it < NT; ++it, n += n_step) {
-    const int nn = (it + 1 < NT) ? n + n_step : n;
-    const double eps_next = pulse ? pulse[nn] : c1_fixed;
-    const double dt_next = a.dt[nn];
-    int s, m;
-    double bound;
-    plan_uniform(dtn * fma(fabs(eps), opn1, opn0), s, m, bound);
-    const double h = (s == 1) ? dtn : dtn / (double)s;
-    cplx At[NN];
-    T.assemble(h, h * eps, At);
-    spec_step<N>(At, y, s, m);
-    if (a.store && valid) {
-      const size_t row = a.backward ? (size_t)n : (size_t)n + 1;
-#pragma unroll
-      for (int i = 0; i < N; ++i) a.store[(row * K + k) * N + i] = y[i];
+  const int nchunks = (NT + KQ_NTC - 1) / KQ_NTC;
+  for (int cc = 0; cc < nchunks; ++cc) {
+    const int ch = a.backward ? nchunks - 1 - cc : cc;
+    const int base = ch * KQ_NTC;
+    const int len = min(KQ_NTC, NT - base);
+    __syncthreads();
+    for (int i = tid; i < len; i += BT) {
+      const double dti = a.dt[base + i];
+      sdt[i] = dti;
+      double xmax;
+      if (c.staged) {
+        const double e = a.pulses[base + i];
+        sp[i] = e;
+        xmax = dti * (fma(fabs(e), O1, O0) + Oc);
+      } else {
+        double emax = 0.0;
+        for (int ll = 0; ll < a.L; ++ll) emax = fmax(emax, fabs(a.pulses[(size_t)ll * NT + base + i]));
+        xmax = dti * (fma(emax, O1, O0) + Oc);
+      }
+      int s, m;
+      double bound;
+      plan_bound(xmax, s, m, bound);
+      splan[i] = (s == 1 && m <= KQ_MFIX) ? (unsigned char)m : (unsigned char)0;
     }
-    eps = eps_next;
-    dtn = dt_next;
+    __syncthreads();
+    c.base = base;
+    int j = a.backward ? len - 1 : 0;
+    const int jend = a.backward ? -1 : len;
+    while (j != jend) {
+      switch (splan[j]) {
+        case 1: j = prop_run<N, INREG, 1>(c, j, jend); break;
+        case 2: j = prop_run<N, INREG, 2>(c, j, jend); break;
+        case 3: j = prop_run<N, INREG, 3>(c, j, jend); break;
+        case 4: j = prop_run<N, INREG, 4>(c, j, jend); break;
+        case 5: j = prop_run<N, INREG, 5>(c, j, jend); break;
+        case 6: j = prop_run<N, INREG, 6>(c, j, jend); break;
+        case 7: j = prop_run<N, INREG, 7>(c, j, jend); break;
+        case 8: j = prop_run<N, INREG, 8>(c, j, jend); break;
+        default: j = prop_run<N, INREG, 0>(c, j, jend); break;
+      }
+    }
   }
   if (a.stateT && valid) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = y[i];
+    for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = c.y[i];
   }
 }
 
 // ---------------------------------------------------------------------------
 // Fused update + forward sweep (optimize.py:449-500), M = 2, L = 1.
-template <int N, int FSEL, bool SECOND, int BTMAX>
-__global__ void __launch_bounds__(BTMAX, 1) k_fwupd_spec(const KqSweepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int NN = N * N;
-  constexpr bool INREG = (N <= 3);
-  const int BT = blockDim.x, tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = (BT + 31) >> 5;
-  const int K = a.K, NT = a.NT;
-  int k = blockIdx.x * BT + tid;
-  const bool valid = k < K;
-  if (!valid) k = K - 1;
-  const int nblk = gridDim.x;
-  const bool multi = (nblk > 1) || (a.world > 1);
-  const bool writer = (blockIdx.x == 0 && tid == 0);
-  // shared: [red 2*32][tot 2][terms (N=4)][mu^dag (N=4 or SECOND)]
-  double* red = reinterpret_cast<double*>(smem_raw);
-  double* tot = red + 64;
-  cplx* sm_terms = reinterpret_cast<cplx*>(tot + 2);
+// shared: [red 2*32 | tot 2 | pad][mbar KQ_RING][sdt|sg|ssl|ssig|sbound KQ_NTC each]
+//         [splan KQ_NTC bytes][chi ring KQ_RING * BT*N][Phi0 ring (SECOND)][terms (N = 4)]
+template <int N, bool INREG, bool SECOND>
+struct FwCtx {
   SpecTerms<N, INREG> T;
-  T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
-                        sm_terms, BT, tid);
-  const double opn0 = a.op_norm[k * 2 + 0], opn1 = a.op_norm[k * 2 + 1];
-  const bool driven = a.term2pulse[k * 2 + 1] == 0;  // else: drift-like or padding
-  const double c1_fixed = (a.term2pulse[k * 2 + 1] == -1) ? 1.0 : 0.0;
-  const double lam = a.lambda_a[0];
-  // mu (column-major): w_r = sum_c mu[c*N+r] phi_c ; mu^dag chi: eta_c = sum_r conj(mu[c*N+r]) chi_r
-  cplx mu[NN];
-#pragma unroll
-  for (int e = 0; e < NN; ++e) mu[e] = a.mu[(size_t)k * NN + e];
+  cplx phi[N], chi[N], eta[N], dphi[N], mu[N * N];
+  double cnorm, opn0, opn1, c1_fixed, ga, O0, O1, Oc;
+  bool driven, valid, writer, multi, failed;
+  int lane, warp, nwarps, nblk, tl, last_row, base, K, k;
+  double *red, *tot;
+  const double *sdt, *sg, *ssl, *ssig, *sbound;
+  const unsigned char* splan;
+  uint64_t* mbar;
+  cplx *ring, *ring0;
+  size_t stage_cplx;
+  uint32_t row_bytes;
+  int k0;
+};
 
-  cplx phi[N], chi[N], eta[N], dphi[N];
-  const double cnorm = valid ? a.chi_norms[k] : 0.0;
+template <int N, bool INREG, bool SECOND>
+__device__ __forceinline__ void fw_make_eta(FwCtx<N, INREG, SECOND>& c) {
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    phi[i] = a.state0[(size_t)k * N + i];
-    chi[i] = a.X[((size_t)0 * K + k) * N + i];
-    dphi[i] = c_zero();
+  for (int cc = 0; cc < N; ++cc) {
+    cplx acc = c_zero();
+#pragma unroll
+    for (int r = 0; r < N; ++r) acc = c_fma_conj(c.mu[cc * N + r], c.chi[r], acc);
+    c.eta[cc] = make_double2(acc.x * c.cnorm, acc.y * c.cnorm);
   }
-  auto make_eta = [&](const cplx(&x)[N], cplx(&e)[N]) {
-#pragma unroll
-    for (int c = 0; c < N; ++c) {
-      cplx acc = c_zero();
-#pragma unroll
-      for (int r = 0; r < N; ++r) acc = c_fma_conj(mu[c * N + r], x[r], acc);
-      e[c] = make_double2(acc.x * cnorm, acc.y * cnorm);
-    }
-  };
-  make_eta(chi, eta);
-  if (SECOND && a.store && valid) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) a.store[((size_t)0 * K + k) * N + i] = phi[i];
-  }
-  double ga = 0.0;
-  bool failed = false;
-  double g_cur = a.pulses[0], s_cur = a.shape[0], dt_cur = a.dt[0];
-  double sig_cur = SECOND ? a.sigma[0] : 0.0;
+}
 
-  for (int n = 0; n < NT; ++n) {
+template <int N, bool INREG, bool SECOND>
+__device__ __forceinline__ void fw_issue_row(const KqSweepArgs& a, FwCtx<N, INREG, SECOND>& c,
+                                             int r) {
+  const int st = r % KQ_RING;
+  mbar_expect_tx(&c.mbar[st], SECOND ? 2 * c.row_bytes : c.row_bytes);
+  bulk_g2s(c.ring + st * c.stage_cplx, a.X + ((size_t)r * c.K + c.k0) * N, c.row_bytes,
+           &c.mbar[st]);
+  if (SECOND)
+    bulk_g2s(c.ring0 + st * c.stage_cplx, a.Phi0 + ((size_t)r * c.K + c.k0) * N, c.row_bytes,
+             &c.mbar[st]);
+}
+
+// Run consecutive steps while their planned Taylor degree is MT (0 = generic).
+template <int N, bool INREG, bool SECOND, int MT>
+__device__ __forceinline__ int fw_run(const KqSweepArgs& a, FwCtx<N, INREG, SECOND>& c, int j,
+                                      int len) {
+  constexpr int NN = N * N;
+  while (j < len && c.splan[j] == MT) {
+    const int n = c.base + j;
     const int par = n & 1;
-    const int nn = (n + 1 < NT) ? n + 1 : n;
-    // ---- prefetch for the next step (off the chain) ----------------------
-    cplx chi_next[N], p0_next[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      chi_next[i] = a.X[((size_t)(n + 1) * K + k) * N + i];
-      if (SECOND) p0_next[i] = a.Phi0[((size_t)(n + 1) * K + k) * N + i];
-    }
-    const double g_next = a.pulses[nn], s_next = a.shape[nn], dt_next = a.dt[nn];
-    const double sig_next = SECOND ? a.sigma[nn] : 0.0;
-    // plan from the guess pulse (verified after the update)
-    int s, m;
-    double bound;
-    const double eps_g = driven ? g_cur : c1_fixed;
-    plan_uniform(dt_cur * fma(fabs(eps_g), opn1, opn0), s, m, bound);
-    const double h = (s == 1) ? dt_cur : dt_cur / (double)s;
-    const double sl = s_cur / lam;  // S/lambda as in optimize.py:474
-
+    const double dt_cur = c.sdt[j], g_cur = c.sg[j], sl = c.ssl[j];
     // ---- Im <chi| mu |phi> ||chi|| (+ 0.5 sigma Im <dphi| mu |phi>) -------
-    double val = 0.0;
+    double val;
     if (SECOND) {
       double v1 = 0.0, v2 = 0.0;
 #pragma unroll
       for (int r = 0; r < N; ++r) {
         cplx w = c_zero();
 #pragma unroll
-        for (int c = 0; c < N; ++c) w = c_fma(mu[c * N + r], phi[c], w);
-        v1 += c_im_conj_mul(chi[r], w);
-        v2 += c_im_conj_mul(dphi[r], w);
+        for (int cc = 0; cc < N; ++cc) w = c_fma(c.mu[cc * N + r], c.phi[cc], w);
+        v1 += c_im_conj_mul(c.chi[r], w);
+        v2 += c_im_conj_mul(c.dphi[r], w);
       }
-      val = fma(0.5 * sig_cur, valid ? v2 : 0.0, v1 * cnorm);
+      val = fma(0.5 * c.ssig[j], c.valid ? v2 : 0.0, v1 * c.cnorm);
     } else {
       double e0 = 0.0, e1 = 0.0;
 #pragma unroll
-      for (int c = 0; c < N; ++c) {
-        if (c & 1)
-          e1 += c_im_conj_mul(eta[c], phi[c]);
+      for (int cc = 0; cc < N; ++cc) {
+        if (cc & 1)
+          e1 += c_im_conj_mul(c.eta[cc], c.phi[cc]);
         else
-          e0 += c_im_conj_mul(eta[c], phi[c]);
+          e0 += c_im_conj_mul(c.eta[cc], c.phi[cc]);
       }
       val = e0 + e1;
     }
     val = warp_allreduce_sum(val);
-    if (lane == 0) red[par * 32 + warp] = val;
+    if (c.lane == 0) c.red[par * 32 + c.warp] = val;
     __syncthreads();
+    if (threadIdx.x == 0 && n + KQ_RING <= c.last_row) fw_issue_row(a, c, n + KQ_RING);
     double d1;
-    if (!multi) {
-      const double* rp = red + par * 32;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int w = 0;
-      for (; w + 3 < nwarps; w += 4) {
-        s0 += rp[w];
-        s1 += rp[w + 1];
-        s2 += rp[w + 2];
-        s3 += rp[w + 3];
+    if (!c.multi) {
+      const double* rp = c.red + par * 32;
+      if (c.nwarps <= 4) {
+        const double2 p0 = *reinterpret_cast<const double2*>(rp);
+        const double2 p1 = *reinterpret_cast<const double2*>(rp + 2);
+        d1 = (p0.x + (c.nwarps > 1 ? p0.y : 0.0)) +
+             ((c.nwarps > 2 ? p1.x : 0.0) + (c.nwarps > 3 ? p1.y : 0.0));
+      } else {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int w = 0;
+        for (; w + 3 < c.nwarps; w += 4) {
+          s0 += rp[w];
+          s1 += rp[w + 1];
+          s2 += rp[w + 2];
+          s3 += rp[w + 3];
+        }
+        for (; w < c.nwarps; ++w) s0 += rp[w];
+        d1 = (s0 + s1) + (s2 + s3);
       }
-      for (; w < nwarps; ++w) s0 += rp[w];
-      d1 = (s0 + s1) + (s2 + s3);
     } else {
       const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
-      if (warp == 0) {
-        double acc = (lane < nwarps) ? red[par * 32 + lane] : 0.0;
+      if (c.warp == 0) {
+        double acc = (c.lane < c.nwarps) ? c.red[par * 32 + c.lane] : 0.0;
         acc = warp_allreduce_sum(acc);
-        if (nblk > 1) {
-          if (lane == 0) slot_store(&a.slots[(size_t)par * nblk + blockIdx.x], acc, tag);
+        if (c.nblk > 1) {
+          if (c.lane == 0) slot_store(&a.slots[(size_t)par * c.nblk + blockIdx.x], acc, tag);
           double g2 = 0.0;
-          for (int c = lane; c < nblk; c += 32)
-            g2 += slot_wait(&a.slots[(size_t)par * nblk + c], tag, failed);
+          for (int q = c.lane; q < c.nblk; q += 32)
+            g2 += slot_wait(&a.slots[(size_t)par * c.nblk + q], tag, c.failed);
           acc = warp_allreduce_sum(g2);
         }
         if (a.world > 1) {
           KqSlot* mine = a.peer_slots[a.rank];
-          const size_t goff = (size_t)2 * nblk * KQ_LMAX;
-          if (blockIdx.x == 0 && lane < a.world)
-            slot_store(a.peer_slots[lane] + goff + ((size_t)par * a.world + a.rank) * KQ_LMAX,
+          const size_t goff = (size_t)2 * c.nblk * KQ_LMAX;
+          if (blockIdx.x == 0 && c.lane < a.world)
+            slot_store(a.peer_slots[c.lane] + goff + ((size_t)par * a.world + a.rank) * KQ_LMAX,
                        acc, tag);
           double g3 = 0.0;
-          if (lane == 0) {
+          if (c.lane == 0) {
             for (int r = 0; r < a.world; ++r)
-              g3 += slot_wait(mine + goff + ((size_t)par * a.world + r) * KQ_LMAX, tag, failed);
+              g3 += slot_wait(mine + goff + ((size_t)par * a.world + r) * KQ_LMAX, tag, c.failed);
           }
           acc = __shfl_sync(0xffffffffu, g3, 0);
         }
-        if (lane == 0) tot[par] = acc;
+        if (c.lane == 0) c.tot[par] = acc;
       }
       __syncthreads();
-      d1 = tot[par];
+      d1 = c.tot[par];
     }
     // ---- pulse update (optimize.py:471-477) --------------------------------
     const double eps_new = __dadd_rn(g_cur, __dmul_rn(sl, d1));
-    const double eps = driven ? eps_new : c1_fixed;
-    if (writer) {
+    const double eps = c.driven ? eps_new : c.c1_fixed;
+    if (c.writer) {
       a.opt_pulses[n] = eps_new;
-      ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), dt_cur));
+      c.ga = __dadd_rn(c.ga, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), dt_cur));
     }
     // ---- forward step under the updated pulse -------------------------------
-    cplx At[NN];
-    T.assemble(h, h * eps, At);
-    cplx ysave[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) ysave[i] = phi[i];
-    spec_step<N>(At, phi, s, m);
-    // verify the plan made from the guess pulse; replay the step if the
-    // updated pulse pushed the norm bound out of its binade (rare)
-    const double x_new = dt_cur * fma(fabs(eps), opn1, opn0);
-    if (__any_sync(0xffffffffu, x_new > bound)) {
-      int s2, m2;
-      double b2;
-      plan_uniform(x_new, s2, m2, b2);
-      const double h2 = (s2 == 1) ? dt_cur : dt_cur / (double)s2;
-      T.assemble(h2, h2 * eps, At);
-#pragma unroll
-      for (int i = 0; i < N; ++i) phi[i] = ysave[i];
-      spec_step<N>(At, phi, s2, m2);
+    cplx At[NN], out[N];
+    // the plan was made from the guess pulse with CTA-wide norm bounds; the
+    // updated pulse (CTA-uniform) may push the bound out of its binade (rare)
+    const double x_new = dt_cur * (fma(fabs(eps_new), c.O1, c.O0) + c.Oc);
+    if (MT > 0 && x_new <= c.sbound[j]) {
+      c.T.assemble(dt_cur, dt_cur * eps, At);
+      expmv_fixed<N, (MT > 0 ? MT : 1)>(At, c.phi, out);
+    } else {
+      int s, m;
+      double bound;
+      plan_bound(x_new, s, m, bound);
+      const double h = dt_cur / (double)s;
+      c.T.assemble(h, h * eps, At);
+      expmv_generic<N>(At, c.phi, out, s, m);
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      chi[i] = chi_next[i];
-      if (SECOND) dphi[i] = c_sub(phi[i], p0_next[i]);
-    }
-    if (!SECOND) make_eta(chi, eta);
-    if (SECOND && a.store && valid) {
+    for (int i = 0; i < N; ++i) c.phi[i] = out[i];
+    // ---- next step's backward state (TMA ring) ------------------------------
+    if (n + 1 <= c.last_row) {
+      const int r = n + 1, st = r % KQ_RING;
+      mbar_wait(&c.mbar[st], (uint32_t)((r / KQ_RING) & 1));
 #pragma unroll
-      for (int i = 0; i < N; ++i) a.store[((size_t)(n + 1) * K + k) * N + i] = phi[i];
+      for (int i = 0; i < N; ++i) {
+        c.chi[i] = c.ring[st * c.stage_cplx + (size_t)c.tl * N + i];
+        if (SECOND)
+          c.dphi[i] = c_sub(c.phi[i], c.ring0[st * c.stage_cplx + (size_t)c.tl * N + i]);
+      }
+      if (!SECOND) fw_make_eta(c);
     }
-    g_cur = g_next;
-    s_cur = s_next;
-    dt_cur = dt_next;
-    sig_cur = sig_next;
+    if (SECOND && a.store && c.valid) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) a.store[((size_t)(n + 1) * c.K + c.k) * N + i] = c.phi[i];
+    }
+    ++j;
   }
-  if (a.stateT && valid) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = phi[i];
+  return j;
+}
+
+template <int N, int FSEL, bool SECOND, int BTMAX>
+__global__ void __launch_bounds__(BTMAX, 1) k_fwupd_spec(const KqSweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NN = N * N;
+  constexpr bool INREG = (N <= 3);
+  const int BT = blockDim.x, tid = threadIdx.x;
+  const int K = a.K, NT = a.NT;
+  FwCtx<N, INREG, SECOND> c;
+  c.K = K;
+  c.lane = tid & 31;
+  c.warp = tid >> 5;
+  c.nwarps = (BT + 31) >> 5;
+  c.k0 = blockIdx.x * BT;
+  int k = c.k0 + tid;
+  c.valid = k < K;
+  if (!c.valid) k = K - 1;
+  c.k = k;
+  const int kcta = min(BT, K - c.k0);   // objectives held by this CTA
+  c.tl = c.valid ? tid : kcta - 1;      // row slot read by this thread
+  c.nblk = gridDim.x;
+  c.multi = (c.nblk > 1) || (a.world > 1);
+  c.writer = (blockIdx.x == 0 && tid == 0);
+  c.failed = false;
+  c.ga = 0.0;
+
+  c.red = reinterpret_cast<double*>(smem_raw);             // [2][32]
+  c.tot = c.red + 64;                                      // [2] (+6 pad)
+  c.mbar = reinterpret_cast<uint64_t*>(c.red + 72);        // [KQ_RING]
+  double* sdt = reinterpret_cast<double*>(c.mbar + KQ_RING);
+  double* sg = sdt + KQ_NTC;
+  double* ssl = sg + KQ_NTC;
+  double* ssig = ssl + KQ_NTC;
+  double* sbound = ssig + KQ_NTC;
+  unsigned char* splan = reinterpret_cast<unsigned char*>(sbound + KQ_NTC);
+  c.sdt = sdt;
+  c.sg = sg;
+  c.ssl = ssl;
+  c.ssig = ssig;
+  c.sbound = sbound;
+  c.splan = splan;
+  c.ring = reinterpret_cast<cplx*>(splan + KQ_NTC);
+  c.stage_cplx = (size_t)BT * N;
+  c.ring0 = c.ring + (size_t)KQ_RING * c.stage_cplx;
+  cplx* sm_terms = c.ring0 + (SECOND ? (size_t)KQ_RING * c.stage_cplx : 0);
+  c.row_bytes = (uint32_t)kcta * N * sizeof(cplx);
+  c.last_row = NT - 1;   // chi(t_r) for steps r = 0..NT-1; Phi0 row r travels with it
+
+  if (tid == 0) {
+    for (int st = 0; st < KQ_RING; ++st) mbar_init(&c.mbar[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (writer) a.g_a[0] = ga;
-  if (failed) atomicExch(a.status, (int)-4);
+  __syncthreads();
+  if (tid == 0) {
+    for (int r = 0; r < KQ_RING && r <= c.last_row; ++r) fw_issue_row(a, c, r);
+  }
+  c.T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
+                          sm_terms, BT, tid);
+  c.opn0 = a.op_norm[k * 2 + 0];
+  c.opn1 = a.op_norm[k * 2 + 1];
+  c.driven = a.term2pulse[k * 2 + 1] == 0;  // else drift-like or padding
+  c.c1_fixed = (a.term2pulse[k * 2 + 1] == -1) ? 1.0 : 0.0;
+  const double lam = a.lambda_a[0];
+#pragma unroll
+  for (int e = 0; e < NN; ++e) c.mu[e] = a.mu[(size_t)k * NN + e];
+  c.cnorm = c.valid ? a.chi_norms[k] : 0.0;
+  c.O0 = block_max(c.opn0, c.red);
+  c.O1 = block_max(c.driven ? c.opn1 : 0.0, c.red);
+  c.Oc = block_max(c.driven ? 0.0 : c.c1_fixed * c.opn1, c.red);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    c.phi[i] = a.state0[(size_t)k * N + i];
+    c.dphi[i] = c_zero();
+  }
+  mbar_wait(&c.mbar[0], 0);   // row 0
+#pragma unroll
+  for (int i = 0; i < N; ++i) c.chi[i] = c.ring[(size_t)c.tl * N + i];
+  fw_make_eta(c);
+  if (SECOND && a.store && c.valid) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.store[((size_t)0 * K + k) * N + i] = c.phi[i];
+  }
+
+  for (int base = 0; base < NT; base += KQ_NTC) {
+    const int len = min(KQ_NTC, NT - base);
+    // stage the per-step scalars and the Taylor plan of this chunk
+    __syncthreads();
+    for (int i = tid; i < len; i += BT) {
+      const double dti = a.dt[base + i], gi = a.pulses[base + i];
+      sdt[i] = dti;
+      sg[i] = gi;
+      ssl[i] = a.shape[base + i] / lam;   // S/lambda as in optimize.py:474
+      if (SECOND) ssig[i] = a.sigma[base + i];
+      int s, m;
+      double bound;
+      plan_bound(dti * (fma(fabs(gi), c.O1, c.O0) + c.Oc), s, m, bound);
+      sbound[i] = bound;
+      splan[i] = (s == 1 && m <= KQ_MFIX) ? (unsigned char)m : (unsigned char)0;
+    }
+    __syncthreads();
+    c.base = base;
+    int j = 0;
+    while (j < len) {
+      switch (splan[j]) {
+        case 1: j = fw_run<N, INREG, SECOND, 1>(a, c, j, len); break;
+        case 2: j = fw_run<N, INREG, SECOND, 2>(a, c, j, len); break;
+        case 3: j = fw_run<N, INREG, SECOND, 3>(a, c, j, len); break;
+        case 4: j = fw_run<N, INREG, SECOND, 4>(a, c, j, len); break;
+        case 5: j = fw_run<N, INREG, SECOND, 5>(a, c, j, len); break;
+        case 6: j = fw_run<N, INREG, SECOND, 6>(a, c, j, len); break;
+        case 7: j = fw_run<N, INREG, SECOND, 7>(a, c, j, len); break;
+        case 8: j = fw_run<N, INREG, SECOND, 8>(a, c, j, len); break;
+        default: j = fw_run<N, INREG, SECOND, 0>(a, c, j, len); break;
+      }
+    }
+  }
+  if (a.stateT && c.valid) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = c.phi[i];
+  }
+  if (c.writer) a.g_a[0] = c.ga;
+  if (c.failed) atomicExch(a.status, (int)-4);
 }
