@@ -87,7 +87,8 @@ typedef struct {
  * update (optimize.py:454-470 sums over ALL objectives).  NULL = single GPU.
  * slots[r] is rank r's exchange buffer (kq_comm_slot_bytes() bytes, zeroed
  * once) mapped into this process (CUDA IPC / symmetric memory); every rank
- * writes its partial sums into every peer's buffer and reads only its own. */
+ * writes its partial sums into every peer's buffer and reads only its own.
+ * All ranks must call kq_sweep_forward_update with the same `epoch`. */
 typedef struct {
   int32_t rank;
   int32_t world;
@@ -99,6 +100,17 @@ enum { KQ_CHI_RE = 0, KQ_CHI_SS = 1, KQ_CHI_SM = 2, KQ_CHI_HS = 3 };
 
 int kq_version(void);
 const char* kq_last_error(void);
+
+/* Cross-GPU exchange buffers (one process per GPU).  kq_comm_alloc allocates
+ * `bytes` of zeroed device memory on the current device and returns a 64-byte
+ * CUDA IPC handle to pass to the peer processes (e.g. through
+ * torch.distributed.all_gather_object); kq_comm_open maps a peer's buffer.
+ * Every rank allocates kq_comm_slot_bytes() this way; kq_comm.slots[r] is
+ * rank r's buffer as mapped into the calling process. */
+int kq_comm_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int kq_comm_open(const unsigned char* handle64, void** ptr);
+int kq_comm_close(void* ptr);
+int kq_comm_free(void* ptr);
 
 /* Bytes of zero-initialised device workspace kq_sweep_forward_update needs
  * (status word + cross-CTA exchange slots). */

@@ -53,6 +53,13 @@ class KqComm(ctypes.Structure):
 _SIGNATURES = {
     'kq_version': (ctypes.c_int, []),
     'kq_last_error': (ctypes.c_char_p, []),
+    'kq_comm_alloc': (ctypes.c_int, [ctypes.c_size_t,
+                                     ctypes.POINTER(ctypes.c_void_p),
+                                     ctypes.c_char_p]),
+    'kq_comm_open': (ctypes.c_int, [ctypes.c_char_p,
+                                    ctypes.POINTER(ctypes.c_void_p)]),
+    'kq_comm_close': (ctypes.c_int, [ctypes.c_void_p]),
+    'kq_comm_free': (ctypes.c_int, [ctypes.c_void_p]),
     'kq_workspace_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
     'kq_comm_slot_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
     'kq_propagate_forward': (ctypes.c_int, [

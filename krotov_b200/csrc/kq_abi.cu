@@ -39,8 +39,8 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr int kMaxDevices = 64;
-constexpr int kMaxBlocks = 4096;   // exchange slots are sized for this many CTAs
-constexpr int kMaxWorld = 16;
+constexpr int kMaxBlocks = KQ_MAX_BLOCKS;
+constexpr int kMaxWorld = KQ_MAX_WORLD;
 constexpr size_t kStatusBytes = 256;
 constexpr size_t kSmemBudget = 200 * 1024;
 
@@ -398,15 +398,53 @@ __global__ void k_chi_boundary(int K, int N, int kind, int K_total, const cplx* 
 
 extern "C" {
 
-int kq_version(void) { return 100; }
+int kq_version(void) { return 101; }
+
+// ---- cross-GPU exchange buffers (CUDA IPC) --------------------------------
+int kq_comm_alloc(size_t bytes, void** ptr, unsigned char* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return fail(KQ_ERR_ARG, "invalid argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  KQ_CUDA(cudaMalloc(&p, bytes));
+  KQ_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(KQ_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+  }
+  std::memcpy(handle64, &h, 64);
+  *ptr = p;
+  return KQ_OK;
+}
+
+int kq_comm_open(const unsigned char* handle64, void** ptr) {
+  if (!ptr || !handle64) return fail(KQ_ERR_ARG, "invalid argument");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  KQ_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return KQ_OK;
+}
+
+int kq_comm_close(void* ptr) {
+  if (ptr) KQ_CUDA(cudaIpcCloseMemHandle(ptr));
+  return KQ_OK;
+}
+
+int kq_comm_free(void* ptr) {
+  if (ptr) KQ_CUDA(cudaFree(ptr));
+  return KQ_OK;
+}
 
 const char* kq_last_error(void) { return g_err.c_str(); }
 
 size_t kq_comm_slot_bytes(const kq_problem*) {
-  return (size_t)2 * (kMaxBlocks + kMaxWorld) * KQ_LMAX * sizeof(KqSlot);
+  return (size_t)2 * kMaxWorld * KQ_LMAX * sizeof(KqSlot);
 }
 
-size_t kq_workspace_bytes(const kq_problem* p) { return kStatusBytes + kq_comm_slot_bytes(p); }
+size_t kq_workspace_bytes(const kq_problem*) {
+  return kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
+}
 
 int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
             int32_t* smem_bytes) {

@@ -18,6 +18,11 @@ typedef double2 cplx;
 
 #define KQ_MMAX_SMALL 5   // terms kept in registers by thread-per-objective kernels
 #define KQ_LMAX 8         // pulses handled per sweep
+#define KQ_MAX_BLOCKS 4096  // cross-CTA exchange slots are sized for this many CTAs
+#define KQ_MAX_WORLD 16
+// the per-rank (cross-GPU) slots [2][world][KQ_LMAX] start at the beginning of
+// each rank's IPC exchange buffer (kq_comm.slots[r])
+#define KQ_RANK_SLOT_OFFSET ((size_t)0)
 #define KQ_TAYLOR_BINS 64
 #define KQ_TAYLOR_MAXM 32
 

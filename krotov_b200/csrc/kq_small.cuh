@@ -301,7 +301,7 @@ k_fwupd_small(const KqSweepArgs a) {
         // by CTA 0, gathered from the local buffer by every CTA (rank order).
         __syncthreads();
         KqSlot* mine = a.peer_slots[a.rank];
-        const size_t goff = (size_t)2 * nblk * KQ_LMAX;  // rank slots follow the CTA slots
+        const size_t goff = KQ_RANK_SLOT_OFFSET;
         if (blockIdx.x == 0 && tid < L * a.world) {
           const int l = tid % L, r = tid / L;
           KqSlot* dst = a.peer_slots[r] + goff + ((size_t)par * a.world + a.rank) * KQ_LMAX + l;

@@ -429,7 +429,7 @@ __device__ __forceinline__ int fw_run(const KqSweepArgs& a, FwCtx<N, INREG, SECO
         }
         if (a.world > 1) {
           KqSlot* mine = a.peer_slots[a.rank];
-          const size_t goff = (size_t)2 * c.nblk * KQ_LMAX;
+          const size_t goff = KQ_RANK_SLOT_OFFSET;
           if (blockIdx.x == 0 && c.lane < a.world)
             slot_store(a.peer_slots[c.lane] + goff + ((size_t)par * a.world + a.rank) * KQ_LMAX,
                        acc, tag);

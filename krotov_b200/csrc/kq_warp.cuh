@@ -152,7 +152,7 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
         const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
         __syncthreads();
         KqSlot* mine = a.peer_slots[a.rank];
-        const size_t goff = (size_t)2 * nblk * KQ_LMAX;
+        const size_t goff = KQ_RANK_SLOT_OFFSET;
         if (blockIdx.x == 0 && tid < L * a.world) {
           const int l = tid % L, r = tid / L;
           slot_store(a.peer_slots[r] + goff + ((size_t)par * a.world + a.rank) * KQ_LMAX + l,

@@ -177,12 +177,16 @@ class SweepEngine:
         self.launches += 1
         return out
 
-    def chi_builtin(self, kind, phiT, tau_t, K_total=None):
-        """Device chi-constructor + normalisation (optimize.py:404-410)."""
+    def chi_builtin(self, kind, phiT, tau_t, K_total=None, shard=None):
+        """Device chi-constructor + normalisation (optimize.py:404-410).
+        With `shard` (a ShardComm) the 1/N prefactors use the global number
+        of objectives and the chis_sm sum runs over all ranks."""
         tau_sum = None
         if kind == 'sm':
             w = tau_t if self.t_weights is None else tau_t * self.t_weights
             tau_sum = w.sum().reshape(1)
+            if shard is not None:
+                shard.all_reduce_sum(tau_sum)
         check(self.lib.kq_chi_boundary(
             self._p, CHI_KINDS[kind],
             self.cp.K if K_total is None else K_total, _ptr(phiT),

@@ -24,6 +24,7 @@ from .conversions import control_onto_interval, pulse_onto_tlist
 from .engine import SweepEngine
 from .info_hooks import chain
 from .mu import derivative_wrt_pulse
+from .parallelization import GPUShards, ShardComm, shard_bounds
 from .propagators import DensityMatrixODEPropagator
 from .propagators import expm as _expm_marker
 from .result import Result
@@ -190,8 +191,14 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     * `norm`: ignored -- the engine normalises chi with the L2/Frobenius
       norm; the update is invariant under this choice (optimize.py:410,467).
     * `overlap`: None or a callable equal to the default overlap.
-    * `storage`, `parallel_map`, `limit_thread_pool`: accepted and ignored
-      (state stores live in HBM; objectives are batched on the GPU).
+    * `parallel_map`: a :class:`krotov_b200.parallelization.GPUShards`
+      instance shards the objectives over the GPUs of a ``torchrun`` job
+      (every rank calls ``optimize_pulses`` with the full `objectives` list
+      and obtains identical pulses; hooks see gathered ``tau_vals`` and
+      ``fw_states_T`` but only the local part of the state stores).  The
+      reference's process-pool maps are accepted and ignored.
+    * `storage`, `limit_thread_pool`: accepted and ignored (state stores live
+      in HBM; objectives are batched on the GPU).
     * `device`: CUDA device (default: current torch device).
 
     Returns:
@@ -221,26 +228,46 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             "skip_initial_forward_propagation is incompatible with "
             "second order Krotov (sigma is not None)")
 
-    cp = compile_problem(objectives, controls, pulses_mapping, tlist,
-                         mu=None if mu is derivative_wrt_pulse else mu,
+    # ---- sharding over GPUs (parallel_map=GPUShards()) ---------------------
+    K_total = len(objectives)
+    shard = None
+    lo, hi = 0, K_total
+    if isinstance(parallel_map, GPUShards):
+        if second_order:
+            raise NotImplementedError(
+                "second-order Krotov is not available with GPUShards yet")
+        dist, group, rank, world = parallel_map.resolve()
+        if world > 1:
+            if K_total < world:
+                raise ValueError("fewer objectives than GPUs")
+            lo, hi = shard_bounds(K_total, world, rank)
+    local_objectives = objectives[lo:hi]
+    cp = compile_problem(local_objectives, controls, pulses_mapping[lo:hi],
+                         tlist, mu=None if mu is derivative_wrt_pulse else mu,
                          pulses_for_mu=guess_pulses)
     _check_overlap(overlap, cp)
     eng = SweepEngine(cp, shape_arrays, lambda_vals, device=device)
     torch = eng.torch
+    if (hi - lo) != K_total:
+        shard = ShardComm(dist, group, eng.device).attach(eng)
     chi_kind = _BUILTIN_CHI.get(chi_constructor)
     if chi_kind is not None and cp.targets is None:
         chi_kind = None  # built-ins need state targets; let the host raise
-    L, NT, K = cp.L, cp.NT, cp.K
+    L, NT, K = cp.L, cp.NT, K_total
     has_targets = cp.targets is not None
+    templates = [obj.initial_state for obj in objectives]
 
     def states_to_host(t):
+        if shard is not None:
+            t = shard.all_gather_rows(t, K_total)
         arr = eng.download(t)
-        return [cp.unvec(arr[k].copy(), cp.state_templates[k])
-                for k in range(K)]
+        return [cp.unvec(arr[k].copy(), templates[k]) for k in range(K)]
 
     def tau_to_host(tau_t):
         if tau_t is None:
             return np.array([None] * K)
+        if shard is not None:
+            tau_t = shard.all_gather_rows(tau_t, K_total)
         return eng.download(tau_t).copy()
 
     def pulses_to_host(p_t):
@@ -262,8 +289,9 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     if skip_initial_forward_propagation:
         if continue_from is not None:
             fw_states_T = list(continue_from.states)
-            phiT = eng.upload(np.array([cp.vec(s) for s in fw_states_T]),
-                              torch.complex128)
+            phiT = eng.upload(
+                np.array([cp.vec(s) for s in fw_states_T[lo:hi]]),
+                torch.complex128)
         else:
             logger.warning(
                 "You should not use `skip_initial_forward_propagation` "
@@ -357,13 +385,15 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         # boundary condition chi(T), normalised (optimize.py:404-410)
         chi_states = chi_norms = None
         if chi_kind is not None:
-            eng.chi_builtin(chi_kind, phiT, tau_t)
+            eng.chi_builtin(chi_kind, phiT, tau_t, K_total=K_total,
+                            shard=shard)
         else:
             if fw_states_T is None:
                 fw_states_T = states_to_host(phiT)
             chis = chi_constructor(fw_states_T=fw_states_T,
                                    objectives=objectives, tau_vals=tau_vals)
-            chi_norms = list(eng.chi_from_host([cp.vec(c) for c in chis]))
+            chi_norms = list(eng.chi_from_host(
+                [cp.vec(c) for c in chis[lo:hi]]))
 
         # backward propagation under the guess pulses (optimize.py:413-425)
         eng.sweep_backward(guess_t)
@@ -455,8 +485,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         if second_order:
             if chi_states is None:
                 chi_arr = eng.download(eng.chi)
-                chi_states = [cp.unvec(chi_arr[k].copy(),
-                                       cp.state_templates[k])
+                chi_states = [cp.unvec(chi_arr[k].copy(), templates[k])
                               for k in range(K)]
                 if chi_norms is None:
                     chi_norms = list(eng.download(eng.chi_norms))
@@ -502,4 +531,6 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         pulse_onto_tlist(np.asarray(p)) for p in result.optimized_controls]
     result.gpu_launches = eng.launches
     result.h2d_bytes, result.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
+    if shard is not None:
+        shard.close()
     return result

@@ -1,0 +1,148 @@
+"""Multi-GPU execution: objectives sharded over the ranks of a
+``torch.distributed`` process group (one process per GPU).
+
+The reference parallelises over objectives with process pools
+(/root/reference/src/krotov/parallelization.py:233-604): whole state histories
+are pickled back after the backward sweep and, in the sequential update sweep,
+one queue round trip per time step sends the new pulse values to K worker
+processes.  Here the same data-parallel split runs on the GPUs of one
+NVLink/NVSwitch box:
+
+* each rank owns a contiguous block of objectives (operators, chi store and
+  forward states never leave its HBM);
+* backward sweep and initial forward propagation need no communication;
+* the fused update/forward sweep needs the sum over ALL objectives at every
+  time step (optimize.py:454-470).  Each rank's kernel writes its partial sum
+  straight into every peer's exchange buffer (flag-tagged 16-byte stores over
+  NVLink, CUDA-IPC mapped memory) and polls its own buffer; ranks add the
+  partials in rank order, so every GPU computes bit-identical pulses.  No
+  host or NCCL call sits inside the time loop;
+* once per iteration NCCL all-gathers tau / final states for the host
+  callbacks and all-reduces the scalar needed by ``chis_sm``.
+
+Pass ``parallel_map=GPUShards()`` to :func:`krotov_b200.optimize_pulses` from
+every rank of a ``torchrun`` job.  The process-pool maps of the reference
+(``parallel_map``, ``parallel_map_fw_prop_step``) are accepted by
+``optimize_pulses`` for signature compatibility and ignored.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import KqComm, check
+
+__all__ = ['GPUShards', 'shard_bounds', 'ShardComm', 'USE_THREADPOOL_LIMITS']
+
+USE_THREADPOOL_LIMITS = True
+
+
+def shard_bounds(K, world, rank):
+    """Half-open range of the objectives owned by `rank`: contiguous blocks
+    whose sizes differ by at most one (the first ``K % world`` ranks hold one
+    more)."""
+    base, extra = divmod(K, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class GPUShards:
+    """Selector for sharded execution (value of `parallel_map`).
+
+    Args:
+        group: ``torch.distributed`` process group (default: WORLD).  The
+            group must already be initialised (backend ``nccl`` on GPUs).
+    """
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def resolve(self):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError(
+                "GPUShards needs an initialised torch.distributed process "
+                "group (launch with torchrun)")
+        return dist, self.group, dist.get_rank(self.group), \
+            dist.get_world_size(self.group)
+
+
+class ShardComm:
+    """Exchange buffers and collectives of one rank."""
+
+    def __init__(self, dist, group, device):
+        import torch
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = device
+        self._own = None
+        self._peers = []
+        self.slots_t = None
+
+    def attach(self, eng):
+        """Allocate this rank's IPC exchange buffer, map the peers' buffers
+        and hand the pointer table to the engine."""
+        lib = _lib.load()
+        nbytes = lib.kq_comm_slot_bytes(eng._p)
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        check(lib.kq_comm_alloc(nbytes, ctypes.byref(ptr), handle))
+        self._own = ptr
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle.raw, group=self.group)
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(ptr.value)
+            else:
+                peer = ctypes.c_void_p()
+                check(lib.kq_comm_open(handles[r], ctypes.byref(peer)))
+                self._peers.append(peer)
+                ptrs.append(peer.value)
+        self.slots_t = self.torch.tensor(ptrs, dtype=self.torch.int64,
+                                         device=self.device)
+        eng.comm = KqComm(rank=self.rank, world=self.world,
+                          slots=self.slots_t.data_ptr())
+        self.dist.barrier(group=self.group)
+        return self
+
+    def close(self):
+        lib = _lib.load()
+        self.torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)
+        for p in self._peers:
+            lib.kq_comm_close(p)
+        self._peers = []
+        if self._own is not None:
+            lib.kq_comm_free(self._own)
+            self._own = None
+
+    # -- once-per-iteration collectives (NCCL) ------------------------------
+    def all_gather_rows(self, local, K_total):
+        """Concatenate per-rank row blocks ``[K_r, ...]`` into ``[K, ...]``
+        (ranks own :func:`shard_bounds` blocks)."""
+        torch = self.torch
+        kmax = -(-K_total // self.world)
+        pad = torch.zeros((kmax,) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        pad[:local.shape[0]] = local
+        if local.dtype.is_complex:
+            send = torch.view_as_real(pad).contiguous()
+        else:
+            send = pad.contiguous()
+        out = [torch.empty_like(send) for _ in range(self.world)]
+        self.dist.all_gather(out, send, group=self.group)
+        parts = []
+        for r in range(self.world):
+            lo, hi = shard_bounds(K_total, self.world, r)
+            blk = out[r][:hi - lo]
+            parts.append(torch.view_as_complex(blk)
+                         if local.dtype.is_complex else blk)
+        return torch.cat(parts, dim=0)
+
+    def all_reduce_sum(self, t):
+        """In-place sum over ranks of a real or complex tensor."""
+        v = self.torch.view_as_real(t) if t.dtype.is_complex else t
+        self.dist.all_reduce(v, group=self.group)
+        return t

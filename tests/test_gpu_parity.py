@@ -352,3 +352,21 @@ def test_property_overlap_conserved_full_size(krotov):
     norms = (Phi.conj() * Phi).sum(dim=2).real
     assert (norms - 1).abs().max().item() < 1e-12
     torch.cuda.synchronize()
+
+
+def test_sharded_two_gpus_matches_single_gpu(krotov):
+    """Objectives sharded over 2 GPUs with the in-kernel per-time-step
+    exchange over NVLink (tests/multigpu_check.py under torchrun)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
+           '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', '29613',
+           os.path.join(root, 'tests', 'multigpu_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
