@@ -93,6 +93,47 @@ class _LazyObjectiveStates:
         return (self[n] for n in range(len(self)))
 
 
+class _LazyFinalStates:
+    """List-like ``fw_states_T``: the K final states phi_k(T), downloaded from
+    the device (and, when sharded, gathered over the ranks) only when a hook,
+    a custom chi_constructor or the caller touches them.  The snapshot is
+    taken on first access or, at the latest, by :meth:`freeze` right before
+    the device buffer is overwritten by the next iteration."""
+
+    def __init__(self, fetch, K):
+        self._fetch, self._K, self._items = fetch, K, None
+
+    def freeze(self, needed):
+        """Drop the device reference; materialise first if `needed`."""
+        if self._items is None and self._fetch is not None and needed:
+            self._items = self._fetch()
+        self._fetch = None
+
+    def _list(self):
+        if self._items is None:
+            if self._fetch is None:
+                raise RuntimeError(
+                    "fw_states_T of a past iteration were not kept; copy "
+                    "them inside the hook if they are needed later")
+            self._items = self._fetch()
+        return self._items
+
+    def __len__(self):
+        return self._K
+
+    def __getitem__(self, i):
+        return self._list()[i]
+
+    def __iter__(self):
+        return iter(self._list())
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __reduce__(self):
+        return (list, (list(self),))
+
+
 def _check_lowerable(propagator, objectives):
     props = propagator if isinstance(propagator, list) else [propagator]
     if isinstance(propagator, list):
@@ -274,6 +315,18 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         arr = eng.download(p_t)
         return [arr[l].copy() for l in range(L)]
 
+    def lazy_states(t):
+        if shard is not None:
+            # the gather is a collective: do it now, download lazily
+            t = shard.all_gather_rows(t, K_total)
+
+            def fetch(tt=t):
+                arr = eng.download(tt)
+                return [cp.unvec(arr[k].copy(), templates[k])
+                        for k in range(K)]
+            return _LazyFinalStates(fetch, K)
+        return _LazyFinalStates(lambda: states_to_host(t), K)
+
     g_a_integrals = np.zeros(L)
     if continue_from is None:
         result = Result()
@@ -313,8 +366,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     host_loop = (info_hook is not None or check_convergence is not None
                  or chi_kind is None or second_order)
     tau_vals = tau_to_host(tau_t)
-    if fw_states_T is None and (host_loop or iter_stop <= iter_start):
-        fw_states_T = states_to_host(phiT)
+    if fw_states_T is None:
+        fw_states_T = lazy_states(phiT)
 
     forward_states = forward_states0 = None
     if second_order:
@@ -364,6 +417,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     # hooks may already have modified lambda_vals / guess_pulses at iteration 0
     # (tests/test_infohooks.py:30-37 halves lambda_a in every call)
     lam_snapshot = np.array(lambda_vals, dtype=np.float64)
+    first_iteration = iter_start + 1
     if info_hook is not None:
         eng.set_lambda(lambda_vals)
         new_guess = eng.pulses_to_device(guess_pulses)
@@ -388,12 +442,14 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             eng.chi_builtin(chi_kind, phiT, tau_t, K_total=K_total,
                             shard=shard)
         else:
-            if fw_states_T is None:
-                fw_states_T = states_to_host(phiT)
             chis = chi_constructor(fw_states_T=fw_states_T,
                                    objectives=objectives, tau_vals=tau_vals)
             chi_norms = list(eng.chi_from_host(
                 [cp.vec(c) for c in chis[lo:hi]]))
+
+        # phi(T) of the previous iteration is overwritten by the sweep below
+        if isinstance(fw_states_T, _LazyFinalStates):
+            fw_states_T.freeze(needed=False)
 
         # backward propagation under the guess pulses (optimize.py:413-425)
         eng.sweep_backward(guess_t)
@@ -419,16 +475,18 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             continue
 
         # ---- host bookkeeping (hooks present) -----------------------------
-        torch.cuda.synchronize(eng.device)
+        # the guess pulses of this iteration are the optimized pulses of the
+        # previous one and are already on the host
+        guess_pulses_host = optimized_pulses if krotov_iteration > \
+            first_iteration else guess_pulses
+        optimized_pulses = pulses_to_host(opt_t)   # synchronises the stream
+        g_a_integrals[:] = eng.download(eng.g_a)[:L]
+        tau_vals = tau_to_host(tau_t)
         st = eng.status()
         if st != 0:
             raise RuntimeError("sweep kernel reported exchange failure %d"
                                % st)
-        guess_pulses_host = pulses_to_host(guess_t)
-        optimized_pulses = pulses_to_host(opt_t)
-        g_a_integrals[:] = eng.download(eng.g_a)[:L]
-        fw_states_T = states_to_host(phiT)
-        tau_vals = tau_to_host(tau_t)
+        fw_states_T = lazy_states(phiT)
         backward_states = _LazyStates(eng.X, cp, eng)
         if second_order:
             forward_states = _LazyStates(Phi1, cp, eng)
@@ -436,6 +494,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         toc = time.time()
 
         if info_hook is not None:
+            opt_snapshot = [p.copy() for p in optimized_pulses]
             info = info_hook(
                 backward_states=backward_states,
                 forward_states=forward_states,
@@ -449,9 +508,9 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             if not np.array_equal(lam_snapshot, np.asarray(lambda_vals)):
                 eng.set_lambda(lambda_vals)
                 lam_snapshot = np.array(lambda_vals, dtype=np.float64)
-            new_opt = eng.pulses_to_device(optimized_pulses)
-            if not torch.equal(new_opt, opt_t):
-                opt_t.copy_(new_opt)
+            if not all(np.array_equal(a, b) for a, b
+                       in zip(optimized_pulses, opt_snapshot)):
+                opt_t.copy_(eng.pulses_to_device(optimized_pulses))
         result.iters.append(krotov_iteration)
         result.iter_seconds.append(int(toc - tic))
         result.iter_seconds_device.append(toc - tic)
@@ -526,6 +585,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         result.states = states_to_host(phiT)
 
     # ---- finalize (optimize.py:583-590) -----------------------------------
+    if isinstance(result.states, _LazyFinalStates):
+        result.states = list(result.states)
     result.end_local_time = time.localtime()
     result.optimized_controls = [
         pulse_onto_tlist(np.asarray(p)) for p in result.optimized_controls]
