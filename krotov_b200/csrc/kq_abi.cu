@@ -157,7 +157,7 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
   g.R = R;
   g.G = 32 / R;
   const size_t fixed = (2 * KQ_LMAX * 32 + 2 * KQ_LMAX) * sizeof(double);
-  const size_t base = (size_t)NN + 2 * N + (M + 1) / 2;
+  const size_t base = (size_t)NN + 2 * ((N + 3) & ~3) + (M + 1) / 2;
   const size_t with_mu = base + (update ? (size_t)L * NN : 0);
   const size_t with_all = with_mu + (size_t)M * NN;
   size_t stride;
@@ -180,6 +180,7 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
   const size_t per_warp = stride * sizeof(cplx) * g.G;
   int max_warps = (int)((kSmemBudget - fixed) / per_warp);
   if (max_warps > 16) max_warps = 16;  // kernel is built for <= 512 threads
+  if (N > 16 && N <= 32 && max_warps > 8) max_warps = 8;  // register-row mode: 256 threads
   if (max_warps < 1) max_warps = 1;
   const int warps_needed = (K + g.G - 1) / g.G;
   int wpb;
@@ -292,24 +293,37 @@ int launch_fwupd_small(const KqSweepArgs& a, const Plan& pl, int fsel, bool seco
                 : launch(k_fwupd_small<N, 2, false, 256>, pl, coop, st, params);
 }
 
-template <int RPL>
-int launch_warp(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, bool update,
-                cudaStream_t st) {
+template <int RPL, int MODE>
+int launch_warp_mode(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, bool update,
+                     cudaStream_t st) {
   void* params[] = {(void*)&a, (void*)&pl.geom};
   const bool coop = update && pl.grid > 1;
   if (!update) {
     switch (fsel) {
-      case 0: return launch(k_sweep_warp<RPL, 0, false, false>, pl, false, st, params);
-      case 1: return launch(k_sweep_warp<RPL, 1, false, false>, pl, false, st, params);
-      default: return launch(k_sweep_warp<RPL, 2, false, false>, pl, false, st, params);
+      case 0: return launch(k_sweep_warp<RPL, 0, false, false, MODE>, pl, false, st, params);
+      case 1: return launch(k_sweep_warp<RPL, 1, false, false, MODE>, pl, false, st, params);
+      default: return launch(k_sweep_warp<RPL, 2, false, false, MODE>, pl, false, st, params);
     }
   }
   if (fsel == 0) {
-    return second ? launch(k_sweep_warp<RPL, 0, true, true>, pl, coop, st, params)
-                  : launch(k_sweep_warp<RPL, 0, false, true>, pl, coop, st, params);
+    return second ? launch(k_sweep_warp<RPL, 0, true, true, MODE>, pl, coop, st, params)
+                  : launch(k_sweep_warp<RPL, 0, false, true, MODE>, pl, coop, st, params);
   }
-  return second ? launch(k_sweep_warp<RPL, 2, true, true>, pl, coop, st, params)
-                : launch(k_sweep_warp<RPL, 2, false, true>, pl, coop, st, params);
+  return second ? launch(k_sweep_warp<RPL, 2, true, true, MODE>, pl, coop, st, params)
+                : launch(k_sweep_warp<RPL, 2, false, true, MODE>, pl, coop, st, params);
+}
+
+int launch_warp(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, bool update,
+                cudaStream_t st) {
+  const bool allsm = pl.geom.terms_in_smem && (!update || pl.geom.mu_in_smem);
+  if (pl.rpl == 1) {
+    if (allsm && a.N <= 8) return launch_warp_mode<1, 8>(a, pl, fsel, second, update, st);
+    if (allsm && a.N <= 16) return launch_warp_mode<1, 16>(a, pl, fsel, second, update, st);
+    if (allsm && a.N <= 32) return launch_warp_mode<1, 32>(a, pl, fsel, second, update, st);
+    return launch_warp_mode<1, 0>(a, pl, fsel, second, update, st);
+  }
+  return allsm ? launch_warp_mode<2, 1>(a, pl, fsel, second, update, st)
+               : launch_warp_mode<2, 0>(a, pl, fsel, second, update, st);
 }
 
 int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_c128* state0,
@@ -342,8 +356,7 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
       default: return launch_prop_small<4>(a, pl, fsel, st);
     }
   }
-  return pl.rpl == 1 ? launch_warp<1>(a, pl, fsel, false, false, st)
-                     : launch_warp<2>(a, pl, fsel, false, false, st);
+  return launch_warp(a, pl, fsel, false, false, st);
 }
 
 // ---- boundary condition / overlaps --------------------------------------
@@ -523,8 +536,7 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
       default: return launch_fwupd_small<4>(a, pl, fsel, second, st);
     }
   }
-  return pl.rpl == 1 ? launch_warp<1>(a, pl, fsel, second, true, st)
-                     : launch_warp<2>(a, pl, fsel, second, true, st);
+  return launch_warp(a, pl, fsel, second, true, st);
 }
 
 int kq_chi_boundary(const kq_problem* p, int kind, int32_t K_total, const kq_c128* phiT,

@@ -22,9 +22,38 @@ struct KqWarpGeom {
   int obj_stride;     // per-objective shared memory, in cplx units
 };
 
-template <int RPL, int FSEL, bool SECOND, bool UPDATE>
-__global__ void __launch_bounds__(512, 1)
+// w = sum_c Mcol[c*N + row] * x[c]  (column-major matrix, unrolled by 4)
+__device__ __forceinline__ cplx matvec_row(const cplx* __restrict__ Mcol,
+                                           const cplx* __restrict__ x, int N, int row) {
+  cplx w0 = c_zero(), w1 = c_zero(), w2 = c_zero(), w3 = c_zero();
+  const cplx* m = Mcol + row;
+  int c = 0;
+  for (; c + 3 < N; c += 4) {
+    const cplx a0 = m[(size_t)c * N], a1 = m[(size_t)(c + 1) * N];
+    const cplx a2 = m[(size_t)(c + 2) * N], a3 = m[(size_t)(c + 3) * N];
+    const cplx x0 = x[c], x1 = x[c + 1], x2 = x[c + 2], x3 = x[c + 3];
+    w0 = c_fma(a0, x0, w0);
+    w1 = c_fma(a1, x1, w1);
+    w2 = c_fma(a2, x2, w2);
+    w3 = c_fma(a3, x3, w3);
+  }
+  for (; c < N; ++c) w0 = c_fma(m[(size_t)c * N], x[c], w0);
+  return c_add(c_add(w0, w1), c_add(w2, w3));
+}
+
+// MODE 0: generic (terms / mu may stay in global memory).
+// MODE 1: generator terms and mu resident in shared memory (pointers are then
+//         known to be shared-space: LDS instead of generic loads).
+// MODE 8/16/32: as 1, and each lane keeps its row of the assembled generator
+//         A in registers (N <= MODE, RPL = 1): a Horner step is then one
+//         broadcast LDS.128 of the state element + 4 DFMA per column, with no
+//         shared-memory round trip for A.
+template <int RPL, int FSEL, bool SECOND, bool UPDATE, int MODE>
+__global__ void __launch_bounds__(MODE == 32 ? 256 : 512, 1)
 k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
+  constexpr bool ALLSM = MODE >= 1;
+  constexpr int AREG = (MODE >= 8) ? MODE : 0;
+  static_assert(AREG == 0 || RPL == 1, "register rows need one row per lane");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const KqTables& T = c_kq_tables;
   const int K = a.K, N = a.N, NT = a.NT, M = a.M, L = a.L, NN = N * N;
@@ -43,21 +72,22 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   double* tot = red + 2 * KQ_LMAX * 32;               // [2][KQ_LMAX]
   cplx* objbase = reinterpret_cast<cplx*>(tot + 2 * KQ_LMAX) +
                   (size_t)(warp * G + grp) * g.obj_stride;
+  const int NP4 = (N + 3) & ~3;         // state buffers padded to a multiple of 4
   cplx* sA = objbase;                   // [N*N] column-major
-  cplx* xb = sA + NN;                   // [2][N]
-  double* scoef = reinterpret_cast<double*>(xb + 2 * N);  // [M] current coefficients
+  cplx* xb = sA + NN;                   // [2][NP4], pads stay zero
+  double* scoef = reinterpret_cast<double*>(xb + 2 * NP4);  // [M] current coefficients
   cplx* sterms = reinterpret_cast<cplx*>(scoef + ((M + 1) & ~1));
-  cplx* smu = sterms + (g.terms_in_smem ? (size_t)M * NN : 0);
-  const cplx* terms = a.ops + (size_t)kk * M * NN;
-  const cplx* mu = UPDATE ? a.mu + (size_t)kk * L * NN : nullptr;
-  if (g.terms_in_smem) {
-    for (int e = lig; e < M * NN; e += R) sterms[e] = terms[e];
-    terms = sterms;
+  cplx* smu = sterms + ((ALLSM || g.terms_in_smem) ? (size_t)M * NN : 0);
+  const cplx* gterms = a.ops + (size_t)kk * M * NN;
+  const cplx* gmu = UPDATE ? a.mu + (size_t)kk * L * NN : nullptr;
+  if (ALLSM || g.terms_in_smem) {
+    for (int e = lig; e < M * NN; e += R) sterms[e] = gterms[e];
   }
-  if (UPDATE && g.mu_in_smem) {
-    for (int e = lig; e < L * NN; e += R) smu[e] = mu[e];
-    mu = smu;
+  if (UPDATE && (ALLSM || g.mu_in_smem)) {
+    for (int e = lig; e < L * NN; e += R) smu[e] = gmu[e];
   }
+  const cplx* terms = ALLSM ? sterms : (g.terms_in_smem ? sterms : gterms);
+  const cplx* mu = ALLSM ? smu : ((UPDATE && g.mu_in_smem) ? smu : gmu);
   const int* t2p = a.term2pulse + (size_t)kk * M;
   const double* opn = a.op_norm + (size_t)kk * M;
 
@@ -75,6 +105,11 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
     if (UPDATE && act[q]) chi[q] = a.X[((size_t)0 * K + kk) * N + row[q]];
     if (act[q]) xb[row[q]] = y[q];
   }
+  for (int e = N + lig; e < NP4; e += R) {
+    xb[e] = c_zero();
+    xb[NP4 + e] = c_zero();
+  }
+  cplx arow[AREG > 0 ? AREG : 1];
   const double cnorm = (UPDATE && valid) ? a.chi_norms[kk] : 0.0;
   const int n_first = (!UPDATE && a.backward) ? NT - 1 : 0;
   const int n_step = (!UPDATE && a.backward) ? -1 : 1;
@@ -107,21 +142,14 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
       }
       const double sig = SECOND ? a.sigma[n] : 0.0;
       // ---- Im <chi| mu_l |phi>, summed over all objectives -----------------
-      const cplx* xcur = xb + p * N;
+      const cplx* xcur = xb + p * NP4;
       for (int l = 0; l < L; ++l) {
         double val = 0.0, val2 = 0.0;
         const cplx* Ml = mu + (size_t)l * NN;
 #pragma unroll
         for (int q = 0; q < RPL; ++q) {
           if (act[q]) {
-            cplx w0 = c_zero(), w1 = c_zero();
-            int c = 0;
-            for (; c + 1 < N; c += 2) {
-              w0 = c_fma(Ml[c * N + row[q]], xcur[c], w0);
-              w1 = c_fma(Ml[(c + 1) * N + row[q]], xcur[c + 1], w1);
-            }
-            if (c < N) w0 = c_fma(Ml[c * N + row[q]], xcur[c], w0);
-            const cplx w = c_add(w0, w1);
+            const cplx w = matvec_row(Ml, xcur, N, row[q]);
             val += c_im_conj_mul(chi[q], w);
             if (SECOND) val2 += c_im_conj_mul(dphi[q], w);
           }
@@ -196,11 +224,32 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
     double x = 0.0;
     for (int m = 0; m < M; ++m) x = fma(fabs(scoef[m]), opn[m], x);
     x *= dtn;
-    // assemble A = sum_m coef_m T_m (all lanes of the group, strided elements)
-    for (int e = lig; e < NN; e += R) {
-      cplx acc = c_zero();
-      for (int m = 0; m < M; ++m) acc = c_fma_real(scoef[m], terms[(size_t)m * NN + e], acc);
-      sA[e] = acc;
+    if (AREG > 0) {
+      // assemble this lane's row of A = sum_m coef_m T_m in registers
+#pragma unroll
+      for (int c = 0; c < AREG; ++c) arow[c] = c_zero();
+      if (act[0]) {
+        for (int m = 0; m < M; ++m) {
+          const double cm = scoef[m];
+          const cplx* tm = terms + (size_t)m * NN + row[0];
+#pragma unroll
+          for (int cb = 0; cb < AREG; cb += 4) {
+            if (cb >= N) break;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = cb + i;
+              if (c < N) arow[c] = c_fma_real(cm, tm[(size_t)c * N], arow[c]);
+            }
+          }
+        }
+      }
+    } else {
+      // assemble A = sum_m coef_m T_m (all lanes of the group, strided elements)
+      for (int e = lig; e < NN; e += R) {
+        cplx acc = c_zero();
+        for (int m = 0; m < M; ++m) acc = c_fma_real(scoef[m], terms[(size_t)m * NN + e], acc);
+        sA[e] = acc;
+      }
     }
     // warp-uniform Taylor plan from the largest bound in the warp
     {
@@ -218,20 +267,32 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
       for (int q = 0; q < RPL; ++q) v[q] = y[q];
       for (int j = mdeg; j >= 1; --j) {
         const double cj = h * T.inv[j];
-        const cplx* xcur = xb + p * N;
-        cplx* xnext = xb + (p ^ 1) * N;
+        const cplx* xcur = xb + p * NP4;
+        cplx* xnext = xb + (p ^ 1) * NP4;
+        if (AREG > 0) {
+          if (act[0]) {
+            cplx w0 = c_zero(), w1 = c_zero(), w2 = c_zero(), w3 = c_zero();
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) {
-          if (act[q]) {
-            cplx w0 = c_zero(), w1 = c_zero();
-            int c = 0;
-            for (; c + 1 < N; c += 2) {
-              w0 = c_fma(sA[c * N + row[q]], xcur[c], w0);
-              w1 = c_fma(sA[(c + 1) * N + row[q]], xcur[c + 1], w1);
+            for (int cb = 0; cb < AREG; cb += 4) {
+              if (cb >= N) break;
+              // arow is zero beyond N and the state pads are zero
+              w0 = c_fma(arow[cb], xcur[cb], w0);
+              w1 = c_fma(arow[cb + 1], xcur[cb + 1], w1);
+              w2 = c_fma(arow[cb + 2], xcur[cb + 2], w2);
+              w3 = c_fma(arow[cb + 3], xcur[cb + 3], w3);
             }
-            if (c < N) w0 = c_fma(sA[c * N + row[q]], xcur[c], w0);
-            y[q] = c_fma_real(cj, apply_f<FSEL>(c_add(w0, w1)), v[q]);
-            xnext[row[q]] = y[q];
+            const cplx w = c_add(c_add(w0, w1), c_add(w2, w3));
+            y[0] = c_fma_real(cj, apply_f<FSEL>(w), v[0]);
+            xnext[row[0]] = y[0];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < RPL; ++q) {
+            if (act[q]) {
+              const cplx w = matvec_row(sA, xcur, N, row[q]);
+              y[q] = c_fma_real(cj, apply_f<FSEL>(w), v[q]);
+              xnext[row[q]] = y[q];
+            }
           }
         }
         __syncwarp();
