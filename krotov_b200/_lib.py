@@ -17,10 +17,12 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(CSRC, 'libkrotov_b200.so')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
-    '-std=c++17', '-shared', '-Xcompiler', '-fPIC',
+    '-std=c++17', '-Xcompiler', '-fPIC',
 ]
+LINK_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-shared',
+              '-Xcompiler', '-fPIC']
 
 
 class EngineUnavailable(RuntimeError):
@@ -92,21 +94,45 @@ EXPORTS = tuple(_SIGNATURES)
 _lib = None
 
 
-def build_library(verbose=False):
-    """Compile ``csrc/kq_abi.cu`` into ``csrc/libkrotov_b200.so`` for
-    sm_100a.  nvcc cross-compiles without a GPU."""
-    src = os.path.join(CSRC, 'kq_abi.cu')
-    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
-                    if f.endswith('.cuh')]
-    deps.append(os.path.join(INCLUDE, 'krotov_b200.h'))
-    if os.path.exists(LIB_PATH) and all(
-            os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
-        return LIB_PATH
+def build_library(verbose=False, jobs=None):
+    """Compile every ``csrc/*.cu`` translation unit for sm_100a (in parallel)
+    and link them into ``csrc/libkrotov_b200.so``.  nvcc cross-compiles
+    without a GPU."""
+    from concurrent.futures import ThreadPoolExecutor
+    sources = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                     if f.endswith('.cu'))
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+               if f.endswith('.cuh')]
+    headers.append(os.path.join(INCLUDE, 'krotov_b200.h'))
+    newest_hdr = max(os.path.getmtime(h) for h in headers)
+    objdir = os.path.join(CSRC, 'build')
+    os.makedirs(objdir, exist_ok=True)
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', LIB_PATH, src]
-    if verbose:
-        print(' '.join(cmd))
-    subprocess.run(cmd, check=True)
+    todo, objects = [], []
+    for src in sources:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
+        objects.append(obj)
+        if not os.path.exists(obj) or os.path.getmtime(obj) < max(
+                os.path.getmtime(src), newest_hdr):
+            todo.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc] + COMPILE_FLAGS + ['-c', '-o', obj, src]
+        if verbose:
+            print(' '.join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
+
+    if todo:
+        with ThreadPoolExecutor(jobs or min(len(todo), os.cpu_count() or 4)) \
+                as pool:
+            list(pool.map(compile_one, todo))
+    if todo or not os.path.exists(LIB_PATH) or any(
+            os.path.getmtime(LIB_PATH) < os.path.getmtime(o) for o in objects):
+        cmd = [nvcc] + LINK_FLAGS + ['-o', LIB_PATH] + objects
+        if verbose:
+            print(' '.join(cmd), flush=True)
+        subprocess.run(cmd, check=True)
     return LIB_PATH
 
 

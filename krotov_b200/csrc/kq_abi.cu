@@ -10,17 +10,15 @@
 #include <mutex>
 #include <string>
 
-#include "../../include/krotov_b200.h"
-#include "kq_common.cuh"
-#include "kq_small.cuh"
-#include "kq_spec.cuh"
-#include "kq_warp.cuh"
+#include "kq_host.cuh"
 
 namespace {
 
 thread_local std::string g_err;
 
-int fail(int code, const char* fmt, ...) {
+}  // namespace
+
+int kq_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -30,13 +28,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define KQ_CUDA(call)                                                              \
-  do {                                                                             \
-    cudaError_t e_ = (call);                                                       \
-    if (e_ != cudaSuccess)                                                         \
-      return fail(KQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                  __FILE__, __LINE__);                                             \
-  } while (0)
+KQ_DEFINE_TABLES_UPLOAD(kq_tables_upload_abi)
+
+namespace {
+
+#define fail kq_fail
 
 constexpr int kMaxDevices = 64;
 constexpr int kMaxBlocks = KQ_MAX_BLOCKS;
@@ -80,7 +76,16 @@ int device_init(int* dev_out) {
   if (!d.ready) {
     KqTables T;
     build_tables(T);
-    KQ_CUDA(cudaMemcpyToSymbol(c_kq_tables, &T, sizeof T));
+    // every translation unit holds its own constant copy of the tables
+    int (*const uploads[])(const KqTables*) = {
+        kq_tables_upload_abi,      kq_tables_upload_small,    kq_tables_upload_spec_prop,
+        kq_tables_upload_spec_fw2, kq_tables_upload_spec_fw3, kq_tables_upload_spec_fw4,
+        kq_tables_upload_warp0,    kq_tables_upload_warp8,    kq_tables_upload_warp16,
+        kq_tables_upload_warp32};
+    for (auto up : uploads) {
+      const int rc = up(&T);
+      if (rc) return rc;
+    }
     KQ_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
     KQ_CUDA(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     KQ_CUDA(cudaDeviceGetAttribute(&d.coop, cudaDevAttrCooperativeLaunch, dev));
@@ -101,15 +106,6 @@ int check_problem(const kq_problem* p) {
     return fail(KQ_ERR_ARG, "problem has NULL operator/time arrays");
   return KQ_OK;
 }
-
-struct Plan {
-  int spec;    // specialised M=2 (L=1) straight-line kernels (kq_spec.cuh)
-  int family;  // 0 thread-per-objective, 1 lane-per-row
-  int grid, block;
-  size_t smem;
-  KqWarpGeom geom;
-  int rpl;
-};
 
 int round_up(int v, int q) { return (v + q - 1) / q * q; }
 
@@ -157,7 +153,10 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
   g.R = R;
   g.G = 32 / R;
   const size_t fixed = (2 * KQ_LMAX * 32 + 2 * KQ_LMAX) * sizeof(double);
-  const size_t base = (size_t)NN + 2 * ((N + 3) & ~3) + (M + 1) / 2;
+  // state double buffer: padded to the register-row capacity (8/16/32) for
+  // N <= 32 (kq_warp.cuh MODE >= 8), else to a multiple of 4
+  const int npad = (N <= 8) ? 8 : (N <= 16 ? 16 : (N <= 32 ? 32 : ((N + 3) & ~3)));
+  const size_t base = (size_t)NN + 2 * npad + (M + 1) / 2;
   const size_t with_mu = base + (update ? (size_t)L * NN : 0);
   const size_t with_all = with_mu + (size_t)M * NN;
   size_t stride;
@@ -180,7 +179,8 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
   const size_t per_warp = stride * sizeof(cplx) * g.G;
   int max_warps = (int)((kSmemBudget - fixed) / per_warp);
   if (max_warps > 16) max_warps = 16;  // kernel is built for <= 512 threads
-  if (N > 16 && N <= 32 && max_warps > 8) max_warps = 8;  // register-row mode: 256 threads
+  if (N > 8 && N <= 16 && max_warps > 8) max_warps = 8;   // register-row modes are built
+  if (N > 16 && N <= 32 && max_warps > 4) max_warps = 4;  // for 256 / 128 threads
   if (max_warps < 1) max_warps = 1;
   const int warps_needed = (K + g.G - 1) / g.G;
   int wpb;
@@ -214,116 +214,15 @@ KqSweepArgs base_args(const kq_problem* p) {
   return a;
 }
 
-template <typename Kern>
-int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** params) {
-  KQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  if (cooperative) {
-    int per_sm = 0;
-    KQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl.block, pl.smem));
-    int dev = 0, sms = 0;
-    KQ_CUDA(cudaGetDevice(&dev));
-    KQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if ((long long)per_sm * sms < pl.grid)
-      return fail(KQ_ERR_UNSUPPORTED,
-                  "fused sweep needs %d co-resident CTAs but only %d fit (K too large)", pl.grid,
-                  per_sm * sms);
-    KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params,
-                                        pl.smem, st));
-  } else {
-    KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params, pl.smem, st));
-  }
-  return KQ_OK;
-}
-
-template <int N>
-int launch_prop_small(const KqSweepArgs& a, const Plan& pl, int fsel, cudaStream_t st) {
-  void* params[] = {(void*)&a};
-  if (pl.spec) {
-    constexpr int NS = (N >= 2) ? N : 2;
-    switch (fsel) {
-      case 0: return launch(k_prop_spec<NS, 0>, pl, false, st, params);
-      case 1: return launch(k_prop_spec<NS, 1>, pl, false, st, params);
-      default: return launch(k_prop_spec<NS, 2>, pl, false, st, params);
-    }
-  }
-  switch (fsel) {
-    case 0: return launch(k_prop_small<N, 0>, pl, false, st, params);
-    case 1: return launch(k_prop_small<N, 1>, pl, false, st, params);
-    default: return launch(k_prop_small<N, 2>, pl, false, st, params);
-  }
-}
-
-template <int N>
-int launch_fwupd_small(const KqSweepArgs& a, const Plan& pl, int fsel, bool second,
-                       cudaStream_t st) {
-  void* params[] = {(void*)&a};
-  const bool coop = pl.grid > 1;
-  if (pl.spec) {
-    constexpr int NS = (N >= 2) ? N : 2;
-    constexpr int BIG = (NS <= 2) ? 1024 : 256;
-    if (NS <= 2 && pl.block > 256) {
-      if (fsel == 0) {
-        return second ? launch(k_fwupd_spec<NS, 0, true, BIG>, pl, coop, st, params)
-                      : launch(k_fwupd_spec<NS, 0, false, BIG>, pl, coop, st, params);
-      }
-      return second ? launch(k_fwupd_spec<NS, 2, true, BIG>, pl, coop, st, params)
-                    : launch(k_fwupd_spec<NS, 2, false, BIG>, pl, coop, st, params);
-    }
-    if (fsel == 0) {
-      return second ? launch(k_fwupd_spec<NS, 0, true, 256>, pl, coop, st, params)
-                    : launch(k_fwupd_spec<NS, 0, false, 256>, pl, coop, st, params);
-    }
-    return second ? launch(k_fwupd_spec<NS, 2, true, 256>, pl, coop, st, params)
-                  : launch(k_fwupd_spec<NS, 2, false, 256>, pl, coop, st, params);
-  }
-  if (N <= 2 && pl.block > 256) {
-    constexpr int BT = (N <= 2) ? 1024 : 256;
-    if (fsel == 0) {
-      return second ? launch(k_fwupd_small<N, 0, true, BT>, pl, coop, st, params)
-                    : launch(k_fwupd_small<N, 0, false, BT>, pl, coop, st, params);
-    }
-    return second ? launch(k_fwupd_small<N, 2, true, BT>, pl, coop, st, params)
-                  : launch(k_fwupd_small<N, 2, false, BT>, pl, coop, st, params);
-  }
-  if (fsel == 0) {
-    return second ? launch(k_fwupd_small<N, 0, true, 256>, pl, coop, st, params)
-                  : launch(k_fwupd_small<N, 0, false, 256>, pl, coop, st, params);
-  }
-  return second ? launch(k_fwupd_small<N, 2, true, 256>, pl, coop, st, params)
-                : launch(k_fwupd_small<N, 2, false, 256>, pl, coop, st, params);
-}
-
-template <int RPL, int MODE>
-int launch_warp_mode(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, bool update,
-                     cudaStream_t st) {
-  void* params[] = {(void*)&a, (void*)&pl.geom};
-  const bool coop = update && pl.grid > 1;
-  if (!update) {
-    switch (fsel) {
-      case 0: return launch(k_sweep_warp<RPL, 0, false, false, MODE>, pl, false, st, params);
-      case 1: return launch(k_sweep_warp<RPL, 1, false, false, MODE>, pl, false, st, params);
-      default: return launch(k_sweep_warp<RPL, 2, false, false, MODE>, pl, false, st, params);
-    }
-  }
-  if (fsel == 0) {
-    return second ? launch(k_sweep_warp<RPL, 0, true, true, MODE>, pl, coop, st, params)
-                  : launch(k_sweep_warp<RPL, 0, false, true, MODE>, pl, coop, st, params);
-  }
-  return second ? launch(k_sweep_warp<RPL, 2, true, true, MODE>, pl, coop, st, params)
-                : launch(k_sweep_warp<RPL, 2, false, true, MODE>, pl, coop, st, params);
-}
-
 int launch_warp(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, bool update,
                 cudaStream_t st) {
   const bool allsm = pl.geom.terms_in_smem && (!update || pl.geom.mu_in_smem);
-  if (pl.rpl == 1) {
-    if (allsm && a.N <= 8) return launch_warp_mode<1, 8>(a, pl, fsel, second, update, st);
-    if (allsm && a.N <= 16) return launch_warp_mode<1, 16>(a, pl, fsel, second, update, st);
-    if (allsm && a.N <= 32) return launch_warp_mode<1, 32>(a, pl, fsel, second, update, st);
-    return launch_warp_mode<1, 0>(a, pl, fsel, second, update, st);
+  if (pl.rpl == 1 && allsm) {
+    if (a.N <= 8) return kq_launch_warp8(a, pl, fsel, second, update, st);
+    if (a.N <= 16) return kq_launch_warp16(a, pl, fsel, second, update, st);
+    if (a.N <= 32) return kq_launch_warp32(a, pl, fsel, second, update, st);
   }
-  return allsm ? launch_warp_mode<2, 1>(a, pl, fsel, second, update, st)
-               : launch_warp_mode<2, 0>(a, pl, fsel, second, update, st);
+  return kq_launch_warp0(a, pl, fsel, second, update, st);
 }
 
 int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_c128* state0,
@@ -349,12 +248,7 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   const int fsel = p->is_super ? 2 : (backward ? 1 : 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.family == 0) {
-    switch (p->N) {
-      case 1: return launch_prop_small<1>(a, pl, fsel, st);
-      case 2: return launch_prop_small<2>(a, pl, fsel, st);
-      case 3: return launch_prop_small<3>(a, pl, fsel, st);
-      default: return launch_prop_small<4>(a, pl, fsel, st);
-    }
+    return pl.spec ? kq_launch_prop_spec(a, pl, fsel, st) : kq_launch_prop_small(a, pl, fsel, st);
   }
   return launch_warp(a, pl, fsel, false, false, st);
 }
@@ -529,11 +423,11 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   const int fsel = p->is_super ? 2 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.family == 0) {
+    if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
     switch (p->N) {
-      case 1: return launch_fwupd_small<1>(a, pl, fsel, second, st);
-      case 2: return launch_fwupd_small<2>(a, pl, fsel, second, st);
-      case 3: return launch_fwupd_small<3>(a, pl, fsel, second, st);
-      default: return launch_fwupd_small<4>(a, pl, fsel, second, st);
+      case 2: return kq_launch_fwupd_spec2(a, pl, fsel, second, st);
+      case 3: return kq_launch_fwupd_spec3(a, pl, fsel, second, st);
+      default: return kq_launch_fwupd_spec4(a, pl, fsel, second, st);
     }
   }
   return launch_warp(a, pl, fsel, second, true, st);

@@ -23,6 +23,8 @@ typedef double2 cplx;
 // the per-rank (cross-GPU) slots [2][world][KQ_LMAX] start at the beginning of
 // each rank's IPC exchange buffer (kq_comm.slots[r])
 #define KQ_RANK_SLOT_OFFSET ((size_t)0)
+#define KQ_NTC 512   // time steps of per-step scalars staged per chunk (kq_spec.cuh)
+#define KQ_RING 4    // depth of the TMA ring for state rows (kq_spec.cuh)
 #define KQ_TAYLOR_BINS 64
 #define KQ_TAYLOR_MAXM 32
 
@@ -31,9 +33,9 @@ struct KqTables {
   double inv[KQ_TAYLOR_MAXM + 1];   // 1/j
 };
 
-// One translation unit (kq_abi.cu) includes these headers; the tables are
-// uploaded once per device by kq_tables_init().
-__constant__ KqTables c_kq_tables;
+// Every translation unit has its own copy of the tables, uploaded once per
+// device by its kq_tables_upload_* function (kq_host.cuh).
+static __constant__ KqTables c_kq_tables;
 
 __device__ __forceinline__ cplx c_make(double x, double y) { return make_double2(x, y); }
 __device__ __forceinline__ cplx c_zero() { return make_double2(0.0, 0.0); }

@@ -1,0 +1,92 @@
+// Host-side declarations shared by the translation units of
+// libkrotov_b200.so.  The kernels are instantiated in several .cu files so
+// that they compile in parallel; each file has its own copy of the constant
+// Taylor tables (uploaded by its kq_tables_upload_* function).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/krotov_b200.h"
+#include "kq_common.cuh"
+#include "kq_small.cuh"   // KqSweepArgs
+#include "kq_warp_geom.cuh"
+
+int kq_fail(int code, const char* fmt, ...);
+
+#define KQ_CUDA(call)                                                                 \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess)                                                            \
+      return kq_fail(KQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                             \
+  } while (0)
+
+struct KqPlan {
+  int spec;    // specialised M=2 (L=1) straight-line kernels (kq_spec.cuh)
+  int family;  // 0 thread-per-objective, 1 lane-per-row
+  int grid, block;
+  size_t smem;
+  KqWarpGeom geom;
+  int rpl;
+};
+
+
+typedef KqPlan Plan;
+
+template <typename Kern>
+int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** params) {
+  KQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  if (cooperative) {
+    int per_sm = 0;
+    KQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl.block, pl.smem));
+    int dev = 0, sms = 0;
+    KQ_CUDA(cudaGetDevice(&dev));
+    KQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if ((long long)per_sm * sms < pl.grid)
+      return kq_fail(KQ_ERR_UNSUPPORTED,
+                  "fused sweep needs %d co-resident CTAs but only %d fit (K too large)", pl.grid,
+                  per_sm * sms);
+    KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params,
+                                        pl.smem, st));
+  } else {
+    KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params, pl.smem, st));
+  }
+  return KQ_OK;
+}
+
+
+#define KQ_DEFINE_TABLES_UPLOAD(name)                                   \
+  int name(const KqTables* T) {                                         \
+    KQ_CUDA(cudaMemcpyToSymbol(c_kq_tables, T, sizeof(KqTables)));      \
+    return KQ_OK;                                                       \
+  }
+
+// per-translation-unit entry points
+int kq_tables_upload_abi(const KqTables* T);
+int kq_tables_upload_small(const KqTables* T);
+int kq_tables_upload_spec_prop(const KqTables* T);
+int kq_tables_upload_spec_fw2(const KqTables* T);
+int kq_tables_upload_spec_fw3(const KqTables* T);
+int kq_tables_upload_spec_fw4(const KqTables* T);
+int kq_tables_upload_warp0(const KqTables* T);
+int kq_tables_upload_warp8(const KqTables* T);
+int kq_tables_upload_warp16(const KqTables* T);
+int kq_tables_upload_warp32(const KqTables* T);
+
+int kq_launch_prop_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
+int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                          cudaStream_t st);
+int kq_launch_prop_spec(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
+int kq_launch_fwupd_spec2(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                          cudaStream_t st);
+int kq_launch_fwupd_spec3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                          cudaStream_t st);
+int kq_launch_fwupd_spec4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                          cudaStream_t st);
+int kq_launch_warp0(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
+                    cudaStream_t st);
+int kq_launch_warp8(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
+                    cudaStream_t st);
+int kq_launch_warp16(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
+                     cudaStream_t st);
+int kq_launch_warp32(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
+                     cudaStream_t st);

@@ -24,8 +24,6 @@
 #include "kq_common.cuh"
 #include "kq_small.cuh"
 
-#define KQ_NTC 512   // time steps of scalars staged per chunk
-#define KQ_RING 4    // depth of the TMA ring for state rows
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

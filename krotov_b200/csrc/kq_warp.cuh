@@ -14,13 +14,7 @@
 #include "kq_common.cuh"
 #include "kq_small.cuh"  // KqSweepArgs
 
-struct KqWarpGeom {
-  int R;              // lanes per objective
-  int G;              // objectives per warp
-  int terms_in_smem;  // generator terms resident in shared memory
-  int mu_in_smem;
-  int obj_stride;     // per-objective shared memory, in cplx units
-};
+#include "kq_warp_geom.cuh"
 
 // w = sum_c Mcol[c*N + row] * x[c]  (column-major matrix, unrolled by 4)
 __device__ __forceinline__ cplx matvec_row(const cplx* __restrict__ Mcol,
@@ -49,7 +43,7 @@ __device__ __forceinline__ cplx matvec_row(const cplx* __restrict__ Mcol,
 //         broadcast LDS.128 of the state element + 4 DFMA per column, with no
 //         shared-memory round trip for A.
 template <int RPL, int FSEL, bool SECOND, bool UPDATE, int MODE>
-__global__ void __launch_bounds__(MODE == 32 ? 256 : 512, 1)
+__global__ void __launch_bounds__(MODE >= 32 ? 128 : (MODE >= 16 ? 256 : 512), 1)
 k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   constexpr bool ALLSM = MODE >= 1;
   constexpr int AREG = (MODE >= 8) ? MODE : 0;
@@ -65,14 +59,15 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   const bool valid = ob < K;
   const int kk = valid ? ob : K - 1;
   const int nblk = gridDim.x;
-  const bool writer = UPDATE && (blockIdx.x == 0 && tid == 0);
 
   // ---- shared memory carve-up ------------------------------------------
   double* red = reinterpret_cast<double*>(smem_raw);  // [2][KQ_LMAX][32]
   double* tot = red + 2 * KQ_LMAX * 32;               // [2][KQ_LMAX]
   cplx* objbase = reinterpret_cast<cplx*>(tot + 2 * KQ_LMAX) +
                   (size_t)(warp * G + grp) * g.obj_stride;
-  const int NP4 = (N + 3) & ~3;         // state buffers padded to a multiple of 4
+  // state buffers padded (pads stay zero): to the register-row capacity in
+  // MODE >= 8 so that the matvec is branch-free, else to a multiple of 4
+  const int NP4 = (AREG > 0) ? AREG : ((N + 3) & ~3);
   cplx* sA = objbase;                   // [N*N] column-major
   cplx* xb = sA + NN;                   // [2][NP4], pads stay zero
   double* scoef = reinterpret_cast<double*>(xb + 2 * NP4);  // [M] current coefficients
@@ -119,9 +114,8 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
     for (int q = 0; q < RPL; ++q)
       if (act[q]) a.store[(r0 * K + ob) * N + row[q]] = y[q];
   }
-  double ga[KQ_LMAX];
-#pragma unroll
-  for (int l = 0; l < KQ_LMAX; ++l) ga[l] = 0.0;
+  double ga = 0.0;       // lane l of warp 0 in CTA 0 accumulates g_a[l]
+  const bool solo = UPDATE && (nwarps == 1) && (nblk == 1) && (a.world == 1);
   bool failed = false;
   int p = 0;  // xb[p] holds the current state
   __syncwarp();
@@ -141,6 +135,13 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
         }
       }
       const double sig = SECOND ? a.sigma[n] : 0.0;
+      // per-pulse scalars of this step, loaded before the reduction so that no
+      // global load or division sits on the sequential chain
+      double pg = 0.0, psl = 0.0;
+      if (lane < L) {
+        pg = a.pulses[(size_t)lane * NT + n];
+        psl = a.shape[(size_t)lane * NT + n] / a.lambda_a[lane];   // optimize.py:474
+      }
       // ---- Im <chi| mu_l |phi>, summed over all objectives -----------------
       const cplx* xcur = xb + p * NP4;
       for (int l = 0; l < L; ++l) {
@@ -157,8 +158,15 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
         val *= cnorm;
         if (SECOND) val = fma(0.5 * sig, valid ? val2 : 0.0, val);
         val = warp_allreduce_sum(val);
-        if (lane == 0) red[(par * KQ_LMAX + l) * 32 + warp] = val;
+        if (solo) {
+          if (lane == 0) tot[par * KQ_LMAX + l] = val;
+        } else if (lane == 0) {
+          red[(par * KQ_LMAX + l) * 32 + warp] = val;
+        }
       }
+      if (solo) {
+        __syncwarp();
+      } else {
       __syncthreads();
       if (warp == 0) {
         const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
@@ -197,28 +205,37 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
         }
       }
       __syncthreads();
-      if (writer) {
-        for (int l = 0; l < L; ++l) {
-          const double d1 = tot[par * KQ_LMAX + l];
-          const double sl = a.shape[(size_t)l * NT + n] / a.lambda_a[l];
-          a.opt_pulses[(size_t)l * NT + n] =
-              __dadd_rn(a.pulses[(size_t)l * NT + n], __dmul_rn(sl, d1));
-          ga[l] = __dadd_rn(ga[l], __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), dtn));
+      }
+      // updated pulse values (optimize.py:471-477); every warp computes them
+      // redundantly for its own coefficients, warp 0 of CTA 0 records them
+      double eps_new = 0.0;
+      if (lane < L) {
+        const double d1 = tot[par * KQ_LMAX + lane];
+        eps_new = __dadd_rn(pg, __dmul_rn(psl, d1));
+        if (blockIdx.x == 0 && warp == 0) {
+          a.opt_pulses[(size_t)lane * NT + n] = eps_new;
+          ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(psl, __dmul_rn(d1, d1)), dtn));
         }
+      }
+      // coefficients of this step's generator under the updated pulses
+      for (int m = lig; m < M; m += R) {
+        const int l = t2p[m];
+        scoef[m] = (l == -1) ? 1.0 : 0.0;
+      }
+      for (int l = 0; l < L; ++l) {
+        const double e = __shfl_sync(0xffffffffu, eps_new, l);
+        for (int m = lig; m < M; m += R)
+          if (t2p[m] == l) scoef[m] = e;
       }
     }
-    // ---- coefficients of this step's generator ----------------------------
-    for (int m = lig; m < M; m += R) {
-      const int l = t2p[m];
-      double c = (l == -1) ? 1.0 : 0.0;
-      if (l >= 0) {
-        c = a.pulses[(size_t)l * NT + n];
-        if (UPDATE) {
-          const double sl = a.shape[(size_t)l * NT + n] / a.lambda_a[l];
-          c = __dadd_rn(c, __dmul_rn(sl, tot[par * KQ_LMAX + l]));
-        }
+    if (!UPDATE) {
+      // ---- coefficients of this step's generator --------------------------
+      for (int m = lig; m < M; m += R) {
+        const int l = t2p[m];
+        double c = (l == -1) ? 1.0 : 0.0;
+        if (l >= 0) c = a.pulses[(size_t)l * NT + n];
+        scoef[m] = c;
       }
-      scoef[m] = c;
     }
     __syncwarp();
     double x = 0.0;
@@ -233,13 +250,9 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
           const double cm = scoef[m];
           const cplx* tm = terms + (size_t)m * NN + row[0];
 #pragma unroll
-          for (int cb = 0; cb < AREG; cb += 4) {
-            if (cb >= N) break;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int c = cb + i;
-              if (c < N) arow[c] = c_fma_real(cm, tm[(size_t)c * N], arow[c]);
-            }
+          for (int c = 0; c < AREG; ++c) {
+            const cplx t = (c < N) ? tm[(size_t)c * N] : c_zero();
+            arow[c] = c_fma_real(cm, t, arow[c]);
           }
         }
       }
@@ -271,15 +284,18 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
         cplx* xnext = xb + (p ^ 1) * NP4;
         if (AREG > 0) {
           if (act[0]) {
+            // branch-free: arow is zero beyond N and the state pads are zero;
+            // all AREG broadcast loads are issued before the FMAs
+            cplx xv[AREG > 0 ? AREG : 1];
+#pragma unroll
+            for (int c = 0; c < AREG; ++c) xv[c] = xcur[c];
             cplx w0 = c_zero(), w1 = c_zero(), w2 = c_zero(), w3 = c_zero();
 #pragma unroll
             for (int cb = 0; cb < AREG; cb += 4) {
-              if (cb >= N) break;
-              // arow is zero beyond N and the state pads are zero
-              w0 = c_fma(arow[cb], xcur[cb], w0);
-              w1 = c_fma(arow[cb + 1], xcur[cb + 1], w1);
-              w2 = c_fma(arow[cb + 2], xcur[cb + 2], w2);
-              w3 = c_fma(arow[cb + 3], xcur[cb + 3], w3);
+              w0 = c_fma(arow[cb], xv[cb], w0);
+              w1 = c_fma(arow[cb + 1], xv[cb + 1], w1);
+              w2 = c_fma(arow[cb + 2], xv[cb + 2], w2);
+              w3 = c_fma(arow[cb + 3], xv[cb + 3], w3);
             }
             const cplx w = c_add(c_add(w0, w1), c_add(w2, w3));
             y[0] = c_fma_real(cj, apply_f<FSEL>(w), v[0]);
@@ -318,8 +334,6 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
     for (int q = 0; q < RPL; ++q)
       if (act[q]) a.stateT[(size_t)ob * N + row[q]] = y[q];
   }
-  if (writer) {
-    for (int l = 0; l < L; ++l) a.g_a[l] = ga[l];
-  }
+  if (UPDATE && blockIdx.x == 0 && warp == 0 && lane < L) a.g_a[lane] = ga;
   if (UPDATE && failed) atomicExch(a.status, (int)-4);
 }
