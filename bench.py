@@ -226,13 +226,18 @@ def run_ours(args):
     (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(
         objectives, wl.pulse_options, wl.tlist)
     K = len(objectives)
-    lo, hi = shard_bounds(K, world, rank)
+    selector = GPUShards(mode=args.shard_mode)
+    n_state = len(wl.lowered()['psi0'][0])
+    mode = selector.choose(K, n_state) if world > 1 else None
+    lo, hi = shard_bounds(K, world, rank) if mode == 'exchange' else (0, K)
     cp = compile_problem(objectives[lo:hi], controls, mapping[lo:hi],
                          wl.tlist)
     eng = SweepEngine(cp, shp, lam)
-    shard = None
-    if world > 1:
+    shard = gather_comm = None
+    if mode == 'exchange':
         shard = ShardComm(dist, None, eng.device).attach(eng)
+    elif mode == 'gather':
+        gather_comm = ShardComm(dist, None, eng.device).attach_gather(eng)
     N, NT, L = cp.N, cp.NT, cp.L
     stream = torch.cuda.current_stream()
 
@@ -311,7 +316,7 @@ def run_ours(args):
         wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
         propagator=krotov.propagators.expm,
         chi_constructor=chi_of(krotov, wl), info_hook=hook,
-        iter_stop=n_e2e, parallel_map=GPUShards() if world > 1 else None)
+        iter_stop=n_e2e, parallel_map=selector if world > 1 else None)
     t_call = time.perf_counter() - t0
     steady = (stamps[-1] - stamps[args.warmup]) / args.steps
     e2e_value = 1.0 / steady
@@ -380,7 +385,7 @@ def run_ours(args):
             "config": dict(WORKLOAD, l2="flushed between timed iterations "
                            "(256 MB write)", parallelism=(
                                "1 GPU" if world == 1 else
-                               "objectives sharded over %d GPUs" % world)),
+                               "%d GPUs, GPUShards mode '%s'" % (world, mode))),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
             "wall_seconds_timed_region": wall,
@@ -388,6 +393,8 @@ def run_ours(args):
         print(json.dumps(line))
     if shard is not None:
         shard.close()
+    if gather_comm is not None:
+        gather_comm.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -400,6 +407,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu', action='store_true',
                     help='skip the CPU baseline leg')
+    ap.add_argument('--shard-mode', default='auto',
+                    choices=['auto', 'exchange', 'gather'],
+                    help='multi-GPU distribution of the fused sweep')
     ap.add_argument('--workload', default='C4',
                     help='C4 (contract workload) or C1/C2/C3/C5/C4sat for '
                          'additional measurements')

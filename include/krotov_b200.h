@@ -112,6 +112,13 @@ int kq_comm_open(const unsigned char* handle64, void** ptr);
 int kq_comm_close(void* ptr);
 int kq_comm_free(void* ptr);
 
+/* Stream-ordered barrier over the ranks of `comm` (one tiny kernel: flag-tagged
+ * stores into every peer's exchange buffer, bounded spin on the local one).
+ * `tag` must be non-zero and increase with every call; `workspace` (may be
+ * NULL) receives KQ_ERR_EXCHANGE in its status word on time-out. */
+int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace,
+                    void* stream);
+
 /* Bytes of zero-initialised device workspace kq_sweep_forward_update needs
  * (status word + cross-CTA exchange slots). */
 size_t kq_workspace_bytes(const kq_problem* p);
@@ -128,6 +135,18 @@ int kq_propagate_forward(const kq_problem* p, const double* pulses,
  * generator: X[NT] = chiT, X[n] = exp(conj(f) A^dag_n dt_n) X[n+1]. */
 int kq_sweep_backward(const kq_problem* p, const double* guess_pulses,
                       const kq_c128* chiT, kq_c128* X, void* stream);
+
+/* 'gather' multi-GPU mode: backward propagation of the objectives
+ * [k_lo, k_lo+k_cnt) only into this rank's store X_peers[self], followed by a
+ * copy kernel that writes that block of columns into the [NT+1][K][N] stores
+ * of all peers (X_peers: HOST array of n_peer device pointers mapped with
+ * kq_comm_alloc/kq_comm_open; wide P2P stores over NVLink).  After a
+ * kq_comm_barrier every GPU holds the complete X and runs the fused sweep
+ * replicated, without any per-step exchange.  chiT is the full [K][N] array. */
+int kq_sweep_backward_range(const kq_problem* p, const double* guess_pulses,
+                            const kq_c128* chiT, void* const* X_peers,
+                            int32_t n_peer, int32_t self, int32_t k_lo,
+                            int32_t k_cnt, void* stream);
 
 /* Fused sequential sweep: for n = 0..NT-1
  *   d_l   = Im sum_k [ chi_norms[k] <X[n][k]| mu_lk |phi_k>

@@ -62,6 +62,9 @@ _SIGNATURES = {
                                     ctypes.POINTER(ctypes.c_void_p)]),
     'kq_comm_close': (ctypes.c_int, [ctypes.c_void_p]),
     'kq_comm_free': (ctypes.c_int, [ctypes.c_void_p]),
+    'kq_comm_barrier': (ctypes.c_int, [ctypes.POINTER(KqComm),
+                                       ctypes.c_uint32, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
     'kq_workspace_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
     'kq_comm_slot_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
     'kq_propagate_forward': (ctypes.c_int, [
@@ -70,6 +73,10 @@ _SIGNATURES = {
     'kq_sweep_backward': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p]),
+    'kq_sweep_backward_range': (ctypes.c_int, [
+        ctypes.POINTER(KqProblem), ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32,
+        ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]),
     'kq_sweep_forward_update': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

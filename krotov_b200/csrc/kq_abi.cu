@@ -211,6 +211,8 @@ KqSweepArgs base_args(const kq_problem* p) {
   a.shape = p->shape;
   a.lambda_a = p->lambda_a;
   a.world = 1;
+  a.k_lo = 0;
+  a.k_cnt = p->K;
   return a;
 }
 
@@ -226,9 +228,12 @@ int launch_warp(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, boo
 }
 
 int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_c128* state0,
-             kq_c128* stateT, kq_c128* store, void* stream) {
+             kq_c128* stateT, kq_c128* store, void* stream, int k_lo = 0, int k_cnt = -1) {
   int rc = check_problem(p);
   if (rc) return rc;
+  if (k_cnt < 0) k_cnt = p->K - k_lo;
+  if (k_lo < 0 || k_cnt < 1 || k_lo + k_cnt > p->K)
+    return fail(KQ_ERR_ARG, "invalid objective range [%d, %d) of %d", k_lo, k_lo + k_cnt, p->K);
   if (!pulses && p->L > 0) return fail(KQ_ERR_ARG, "pulses is NULL");
   if (!state0) return fail(KQ_ERR_ARG, "initial state is NULL");
   if (!stateT && !store) return fail(KQ_ERR_ARG, "both outputs are NULL");
@@ -236,9 +241,13 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   rc = device_init(&dev);
   if (rc) return rc;
   Plan pl;
-  rc = make_plan(p, false, false, g_dev[dev].sms, pl);
+  kq_problem sub = *p;   // launch geometry for the objectives actually propagated
+  sub.K = k_cnt;
+  rc = make_plan(&sub, false, false, g_dev[dev].sms, pl);
   if (rc) return rc;
   KqSweepArgs a = base_args(p);
+  a.k_lo = k_lo;
+  a.k_cnt = k_cnt;
   a.ops = reinterpret_cast<const cplx*>(backward ? p->ops_adj : p->ops);
   a.pulses = pulses;
   a.state0 = reinterpret_cast<const cplx*>(state0);
@@ -261,6 +270,41 @@ __global__ void k_overlaps(int K, int N, const cplx* __restrict__ a, const cplx*
   cplx acc = c_zero();
   for (int i = 0; i < N; ++i) acc = c_fma_conj(a[(size_t)k * N + i], b[(size_t)k * N + i], acc);
   out[k] = acc;
+}
+
+// Copy the column block [col0, col0+ncol) of every row of this rank's store to
+// the same place in every peer's store (wide P2P stores over NVLink).
+struct KqScatterArgs {
+  cplx* dst[KQ_MAX_WORLD];
+  int n_peer, self, rows, ncol;
+  size_t row_stride, col0;
+};
+__global__ void k_scatter_rows(const KqScatterArgs a) {
+  const long long total = (long long)a.rows * a.ncol;
+  const cplx* src = a.dst[a.self];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const size_t idx = (size_t)(i / a.ncol) * a.row_stride + a.col0 + (size_t)(i % a.ncol);
+    const cplx v = src[idx];
+    for (int g = 0; g < a.n_peer; ++g)
+      if (g != a.self) a.dst[g][idx] = v;
+  }
+}
+
+// Cross-GPU barrier on the stream: every rank announces `tag` in every peer's
+// exchange buffer and waits until all ranks have announced it in its own.
+// Kernel boundaries order it after the P2P stores of the preceding kernel.
+__global__ void k_comm_barrier(KqSlot* const* peer_slots, int rank, int world, uint32_t tag,
+                               int* status) {
+  const int r = threadIdx.x;
+  const size_t off = (size_t)2 * KQ_MAX_WORLD * KQ_LMAX;   // after the per-step slots
+  bool failed = false;
+  if (r < world) {
+    __threadfence_system();
+    slot_store(peer_slots[r] + off + rank, 0.0, tag);
+    slot_wait(peer_slots[rank] + off + r, tag, failed);
+  }
+  if (failed && status) atomicExch(status, (int)-4);
 }
 
 // chi_k(T) of functionals.py:177-197 (ss), 225-253 (sm), 293-317 (re),
@@ -346,7 +390,18 @@ int kq_comm_free(void* ptr) {
 const char* kq_last_error(void) { return g_err.c_str(); }
 
 size_t kq_comm_slot_bytes(const kq_problem*) {
-  return (size_t)2 * kMaxWorld * KQ_LMAX * sizeof(KqSlot);
+  return ((size_t)2 * kMaxWorld * KQ_LMAX + kMaxWorld) * sizeof(KqSlot);
+}
+
+int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* stream) {
+  if (!comm || comm->world < 1 || comm->world > kMaxWorld || !comm->slots)
+    return fail(KQ_ERR_ARG, "invalid kq_comm");
+  if (tag == 0) return fail(KQ_ERR_ARG, "barrier tag must be non-zero");
+  k_comm_barrier<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<KqSlot* const*>(comm->slots), comm->rank, comm->world, tag,
+      reinterpret_cast<int*>(workspace));
+  KQ_CUDA(cudaGetLastError());
+  return KQ_OK;
 }
 
 size_t kq_workspace_bytes(const kq_problem*) {
@@ -376,6 +431,30 @@ int kq_sweep_backward(const kq_problem* p, const double* guess_pulses, const kq_
                       kq_c128* X, void* stream) {
   if (!X) return fail(KQ_ERR_ARG, "X is NULL");
   return run_prop(p, true, guess_pulses, chiT, nullptr, X, stream);
+}
+
+int kq_sweep_backward_range(const kq_problem* p, const double* guess_pulses,
+                            const kq_c128* chiT, void* const* X_peers, int32_t n_peer,
+                            int32_t self, int32_t k_lo, int32_t k_cnt, void* stream) {
+  if (!X_peers || n_peer < 1 || n_peer > kMaxWorld || self < 0 || self >= n_peer)
+    return fail(KQ_ERR_ARG, "invalid peer table");
+  int rc = run_prop(p, true, guess_pulses, chiT, nullptr,
+                    reinterpret_cast<kq_c128*>(X_peers[self]), stream, k_lo, k_cnt);
+  if (rc || n_peer == 1) return rc;
+  // broadcast this rank's block of columns of X to every peer (P2P stores)
+  KqScatterArgs sa;
+  sa.n_peer = n_peer;
+  sa.self = self;
+  for (int g = 0; g < n_peer; ++g) sa.dst[g] = reinterpret_cast<cplx*>(X_peers[g]);
+  sa.rows = p->NT + 1;
+  sa.row_stride = (size_t)p->K * p->N;
+  sa.col0 = (size_t)k_lo * p->N;
+  sa.ncol = k_cnt * p->N;
+  const long long total = (long long)sa.rows * sa.ncol;
+  int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
+  k_scatter_rows<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(sa);
+  KQ_CUDA(cudaGetLastError());
+  return KQ_OK;
 }
 
 int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, double* opt_pulses,

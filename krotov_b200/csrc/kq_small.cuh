@@ -41,7 +41,14 @@ struct KqSweepArgs {
   int rank, world;
   uint32_t tag_base;
   int backward;
+  // propagation sweeps only: objectives [k_lo, k_lo + k_cnt) are propagated
+  // (K stays the row stride of the stores)
+  int k_lo, k_cnt;
 };
+
+__device__ __forceinline__ void kq_store(const KqSweepArgs& a, size_t idx, cplx v) {
+  a.store[idx] = v;
+}
 
 // y <- exp(f * A * dt) y,   A column-major N x N in registers.
 template <int N, int FSEL>
@@ -101,9 +108,9 @@ k_prop_small(const KqSweepArgs a) {
   const KqTables& T = c_kq_tables;
   constexpr int NN = N * N;
   const int BT = blockDim.x, tid = threadIdx.x;
-  const int k = blockIdx.x * BT + tid;
+  const int k = a.k_lo + blockIdx.x * BT + tid;
   const int K = a.K, NT = a.NT, M = a.M;
-  if (k >= K) return;  // no block-level synchronisation in this kernel
+  if (k >= a.k_lo + a.k_cnt) return;  // no block-level synchronisation in this kernel
   SmallSmem<N> sm(smem_raw, M, a.L, BT, false);
 
   int t2p[KQ_MMAX_SMALL];
@@ -128,7 +135,7 @@ k_prop_small(const KqSweepArgs a) {
   if (a.store) {
     const size_t row = a.backward ? (size_t)NT : 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) a.store[(row * K + k) * N + i] = y[i];
+    for (int i = 0; i < N; ++i) kq_store(a, (row * K + k) * N + i, y[i]);
   }
   // coefficients of the first step
   double coef[KQ_MMAX_SMALL];
@@ -163,7 +170,7 @@ k_prop_small(const KqSweepArgs a) {
     if (a.store) {
       const size_t row = a.backward ? (size_t)n : (size_t)n + 1;
 #pragma unroll
-      for (int i = 0; i < N; ++i) a.store[(row * K + k) * N + i] = y[i];
+      for (int i = 0; i < N; ++i) kq_store(a, (row * K + k) * N + i, y[i]);
     }
 #pragma unroll
     for (int m = 0; m < KQ_MMAX_SMALL; ++m) coef[m] = coef_next[m];

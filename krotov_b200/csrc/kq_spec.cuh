@@ -183,11 +183,13 @@ struct PropCtx {
   const double* sp;
   const unsigned char* splan;
   const double* pulse;   // global pulse row when not staged
-  cplx* store;           // row pointer base for this objective, or null
+  bool store;            // states are stored
+  size_t kofs;           // k*N
   size_t row_stride;     // K*N
   bool driven, staged, valid;
   double c1_fixed, opn0, opn1;
   int base, dir;         // chunk base index, +1 forward / -1 backward
+  const KqSweepArgs* args;
 };
 
 // Run consecutive steps j (moving by c.dir) while their planned degree is MT.
@@ -215,7 +217,7 @@ __device__ __forceinline__ int prop_run(PropCtx<N, INREG>& c, int j, int jend) {
     if (c.store && c.valid) {
       const size_t row = (c.dir < 0) ? (size_t)n : (size_t)n + 1;
 #pragma unroll
-      for (int i = 0; i < N; ++i) c.store[row * c.row_stride + i] = out[i];
+      for (int i = 0; i < N; ++i) kq_store(*c.args, row * c.row_stride + c.kofs + i, out[i]);
     }
     j += c.dir;
   }
@@ -229,9 +231,9 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   constexpr bool INREG = (N <= 3);
   const int BT = blockDim.x, tid = threadIdx.x;
   const int K = a.K, NT = a.NT;
-  int k = blockIdx.x * BT + tid;
-  const bool valid = k < K;
-  if (!valid) k = K - 1;  // shadow thread: keeps the CTA converged
+  int k = a.k_lo + blockIdx.x * BT + tid;
+  const bool valid = k < a.k_lo + a.k_cnt;
+  if (!valid) k = a.k_lo + a.k_cnt - 1;  // shadow thread: keeps the CTA converged
   double* sdt = reinterpret_cast<double*>(smem_raw);
   double* sp = sdt + KQ_NTC;
   unsigned char* splan = reinterpret_cast<unsigned char*>(sp + KQ_NTC);
@@ -250,8 +252,10 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   c.sdt = sdt;
   c.sp = sp;
   c.splan = splan;
-  c.store = a.store ? a.store + (size_t)k * N : nullptr;
+  c.store = a.store != nullptr;
+  c.kofs = (size_t)k * N;
   c.row_stride = (size_t)K * N;
+  c.args = &a;
   c.dir = a.backward ? -1 : 1;
   // CTA-wide norm bounds for the per-step Taylor plan
   const double O0 = block_max(c.opn0, scratch);
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   if (a.store && valid) {
     const size_t row = a.backward ? (size_t)NT : 0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) c.store[row * c.row_stride + i] = c.y[i];
+    for (int i = 0; i < N; ++i) kq_store(a, row * c.row_stride + c.kofs + i, c.y[i]);
   }
   const int nchunks = (NT + KQ_NTC - 1) / KQ_NTC;
   for (int cc = 0; cc < nchunks; ++cc) {

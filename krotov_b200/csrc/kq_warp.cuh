@@ -55,9 +55,10 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   const int nwarps = blockDim.x >> 5;
   const int R = g.R, G = g.G;
   const int grp = lane / R, lig = lane - grp * R;
-  const int ob = (blockIdx.x * nwarps + warp) * G + grp;
-  const bool valid = ob < K;
-  const int kk = valid ? ob : K - 1;
+  const int k_end = UPDATE ? K : a.k_lo + a.k_cnt;
+  const int ob = (UPDATE ? 0 : a.k_lo) + (blockIdx.x * nwarps + warp) * G + grp;
+  const bool valid = ob < k_end;
+  const int kk = valid ? ob : k_end - 1;
   const int nblk = gridDim.x;
 
   // ---- shared memory carve-up ------------------------------------------
@@ -112,7 +113,10 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
     const size_t r0 = (!UPDATE && a.backward) ? (size_t)NT : 0;
 #pragma unroll
     for (int q = 0; q < RPL; ++q)
-      if (act[q]) a.store[(r0 * K + ob) * N + row[q]] = y[q];
+      if (act[q]) {
+        if (UPDATE) a.store[(r0 * K + ob) * N + row[q]] = y[q];
+        else kq_store(a, (r0 * K + ob) * N + row[q], y[q]);
+      }
   }
   double ga = 0.0;       // lane l of warp 0 in CTA 0 accumulates g_a[l]
   const bool solo = UPDATE && (nwarps == 1) && (nblk == 1) && (a.world == 1);
@@ -326,7 +330,10 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
       const size_t r1 = (!UPDATE && a.backward) ? (size_t)n : (size_t)n + 1;
 #pragma unroll
       for (int q = 0; q < RPL; ++q)
-        if (act[q]) a.store[(r1 * K + ob) * N + row[q]] = y[q];
+        if (act[q]) {
+          if (UPDATE) a.store[(r1 * K + ob) * N + row[q]] = y[q];
+          else kq_store(a, (r1 * K + ob) * N + row[q], y[q]);
+        }
     }
   }
   if (a.stateT && valid) {

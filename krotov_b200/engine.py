@@ -79,7 +79,8 @@ class SweepEngine:
         nbytes = self.lib.kq_workspace_bytes(self._p)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self.epoch = 0
-        self.comm = None
+        self.comm = None      # KqComm: per-time-step exchange ('exchange' mode)
+        self.gather = None    # dict set by ShardComm.attach_gather
         K, N, NT = cp.K, cp.N, cp.NT
         self.X = torch.empty((NT + 1, K, N), dtype=c128, device=dev)
         self.chi = torch.empty((K, N), dtype=c128, device=dev)
@@ -145,9 +146,23 @@ class SweepEngine:
     def sweep_backward(self, pulses_t):
         """Backward propagation of :attr:`chi` into :attr:`X`
         (optimize.py:849-886)."""
-        check(self.lib.kq_sweep_backward(
-            self._p, _ptr(pulses_t), _ptr(self.chi), _ptr(self.X),
-            self._stream()))
+        g = self.gather
+        if g is None:
+            check(self.lib.kq_sweep_backward(
+                self._p, _ptr(pulses_t), _ptr(self.chi), _ptr(self.X),
+                self._stream()))
+        else:
+            # 'gather' mode: this rank's block of objectives, stored on every
+            # GPU; the stores alternate so that a fast rank cannot overwrite
+            # rows a slower rank is still reading in its fused sweep
+            g['flip'] ^= 1
+            self.X = g['stores'][g['flip']]
+            check(self.lib.kq_sweep_backward_range(
+                self._p, _ptr(pulses_t), _ptr(self.chi), g['tables'][g['flip']],
+                g['comm'].world, g['comm'].rank, g['lo'], g['hi'] - g['lo'],
+                self._stream()))
+            self.launches += 1          # the column-block scatter kernel
+            g['comm'].stream_barrier()
         self.launches += 1
         return self.X
 

@@ -272,6 +272,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     # ---- sharding over GPUs (parallel_map=GPUShards()) ---------------------
     K_total = len(objectives)
     shard = None
+    shard_mode = None
     lo, hi = 0, K_total
     if isinstance(parallel_map, GPUShards):
         if second_order:
@@ -281,7 +282,11 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         if world > 1:
             if K_total < world:
                 raise ValueError("fewer objectives than GPUs")
-            lo, hi = shard_bounds(K_total, world, rank)
+            from ._dense import dense as _dense
+            n_state = _dense(objectives[0].initial_state).size
+            shard_mode = parallel_map.choose(K_total, n_state)
+            if shard_mode == 'exchange':
+                lo, hi = shard_bounds(K_total, world, rank)
     local_objectives = objectives[lo:hi]
     cp = compile_problem(local_objectives, controls, pulses_mapping[lo:hi],
                          tlist, mu=None if mu is derivative_wrt_pulse else mu,
@@ -289,8 +294,13 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     _check_overlap(overlap, cp)
     eng = SweepEngine(cp, shape_arrays, lambda_vals, device=device)
     torch = eng.torch
+    gather_comm = None
     if (hi - lo) != K_total:
         shard = ShardComm(dist, group, eng.device).attach(eng)
+    elif shard_mode == 'gather':
+        # every rank holds the complete problem; only the backward sweep is
+        # sharded (engine.sweep_backward)
+        gather_comm = ShardComm(dist, group, eng.device).attach_gather(eng)
     chi_kind = _BUILTIN_CHI.get(chi_constructor)
     if chi_kind is not None and cp.targets is None:
         chi_kind = None  # built-ins need state targets; let the host raise
@@ -594,4 +604,6 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     result.h2d_bytes, result.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
     if shard is not None:
         shard.close()
+    if gather_comm is not None:
+        gather_comm.close()
     return result

@@ -47,15 +47,38 @@ def shard_bounds(K, world, rank):
 
 
 class GPUShards:
-    """Selector for sharded execution (value of `parallel_map`).
+    """Selector for multi-GPU execution (value of `parallel_map`).
 
     Args:
         group: ``torch.distributed`` process group (default: WORLD).  The
             group must already be initialised (backend ``nccl`` on GPUs).
+        mode: how the sequential update sweep is distributed.
+
+            ``'exchange'``: every rank owns a block of objectives for all
+            sweeps; the fused sweep kernels exchange their partial sums over
+            NVLink at every time step (about 2 microseconds per step).  Pays
+            off when the per-step work of a block is much larger than that.
+
+            ``'gather'``: the backward sweep is sharded and each kernel writes
+            the backward states it produces into the stores of ALL GPUs (P2P
+            stores); after one NCCL barrier every GPU runs the complete fused
+            sweep redundantly, with no per-step exchange.  Best for small
+            state vectors, where the sweep is bound by the chain of nt-1
+            dependent steps and not by throughput.
+
+            ``'auto'`` (default): ``'gather'`` if ``K * N * N <= 65536``.
     """
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, mode='auto'):
+        if mode not in ('auto', 'exchange', 'gather'):
+            raise ValueError("mode must be 'auto', 'exchange' or 'gather'")
         self.group = group
+        self.mode = mode
+
+    def choose(self, K, N):
+        if self.mode != 'auto':
+            return self.mode
+        return 'gather' if K * N * N <= 65536 else 'exchange'
 
     def resolve(self):
         import torch.distributed as dist
@@ -77,12 +100,13 @@ class ShardComm:
         self.world = dist.get_world_size(group)
         self.device = device
         self._own = None
+        self._owned = []     # further IPC allocations owned by this rank
         self._peers = []
         self.slots_t = None
 
-    def attach(self, eng):
+    def attach(self, eng, for_exchange=True):
         """Allocate this rank's IPC exchange buffer, map the peers' buffers
-        and hand the pointer table to the engine."""
+        and (for 'exchange' mode) hand the pointer table to the engine."""
         lib = _lib.load()
         nbytes = lib.kq_comm_slot_bytes(eng._p)
         ptr = ctypes.c_void_p()
@@ -102,10 +126,75 @@ class ShardComm:
                 ptrs.append(peer.value)
         self.slots_t = self.torch.tensor(ptrs, dtype=self.torch.int64,
                                          device=self.device)
-        eng.comm = KqComm(rank=self.rank, world=self.world,
-                          slots=self.slots_t.data_ptr())
+        self.kqcomm = KqComm(rank=self.rank, world=self.world,
+                             slots=self.slots_t.data_ptr())
+        if for_exchange:
+            eng.comm = self.kqcomm
+        self._eng = eng
+        self._barrier_tag = 0
         self.dist.barrier(group=self.group)
         return self
+
+    def attach_gather(self, eng):
+        """'gather' mode: make both backward-state stores of `eng` writable by
+        every peer (CUDA IPC handles of the torch allocations) and tell the
+        engine which block of objectives this rank propagates backward."""
+        torch = self.torch
+        lib = _lib.load()
+        self.attach(eng, for_exchange=False)   # flag slots for the barrier
+        shape = tuple(eng.X.shape)
+        nbytes = eng.X.numel() * eng.X.element_size()
+
+        class _Raw:   # __cuda_array_interface__ view of an IPC allocation
+            def __init__(self, ptr):
+                self.__cuda_array_interface__ = dict(
+                    data=(ptr, False), shape=shape + (2,), typestr='<f8',
+                    version=2, strides=None)
+
+        own, handles = [], []
+        for _ in range(2):
+            ptr = ctypes.c_void_p()
+            handle = ctypes.create_string_buffer(64)
+            check(lib.kq_comm_alloc(nbytes, ctypes.byref(ptr), handle))
+            self._owned.append(ptr)
+            own.append(ptr.value)
+            handles.append(handle.raw)
+        stores = tuple(
+            torch.view_as_complex(torch.as_tensor(_Raw(p), device=self.device))
+            for p in own)
+        eng.X, eng.X2 = stores
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, handles, group=self.group)
+        tables = []
+        for b in range(2):
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(own[b])
+                    continue
+                peer = ctypes.c_void_p()
+                check(lib.kq_comm_open(gathered[r][b], ctypes.byref(peer)))
+                self._peers.append(peer)
+                ptrs.append(peer.value)
+            tables.append((ctypes.c_void_p * self.world)(*ptrs))
+        lo, hi = shard_bounds(eng.cp.K, self.world, self.rank)
+        eng.gather = dict(tables=tables, lo=lo, hi=hi, flip=0,
+                          stores=(eng.X, eng.X2), comm=self)
+        self.dist.barrier(group=self.group)
+        return self
+
+    def stream_barrier(self):
+        """Order the kernels of all ranks on their streams: every rank's P2P
+        stores of the backward sweep are complete before any rank starts the
+        fused sweep.  One tiny kernel per rank (flags over NVLink), no NCCL
+        call and no host synchronisation."""
+        self._barrier_tag += 1
+        eng = self._eng
+        check(_lib.load().kq_comm_barrier(
+            ctypes.byref(self.kqcomm),
+            ctypes.c_uint32(self._barrier_tag & 0xFFFFFFFF or 1),
+            ctypes.c_void_p(eng.workspace.data_ptr()), eng._stream()))
+        eng.launches += 1
 
     def close(self):
         lib = _lib.load()
@@ -117,6 +206,9 @@ class ShardComm:
         if self._own is not None:
             lib.kq_comm_free(self._own)
             self._own = None
+        for p in self._owned:
+            lib.kq_comm_free(p)
+        self._owned = []
 
     # -- once-per-iteration collectives (NCCL) ------------------------------
     def all_gather_rows(self, local, K_total):

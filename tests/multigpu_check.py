@@ -20,7 +20,12 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
-    for K, nt, chi in ((37, 120, 're'), (128, 300, 'sm'), (6, 80, 'ss')):
+    for K, nt, chi, mode in ((37, 120, 're', 'exchange'),
+                             (128, 300, 'sm', 'exchange'),
+                             (6, 80, 'ss', 'exchange'),
+                             (37, 120, 're', 'gather'),
+                             (128, 300, 'sm', 'gather'),
+                             (5, 80, 'ss', 'gather')):
         wl = krotov.workloads.tls_ensemble(K=K, nt=nt)
         chi_fn = getattr(krotov.functionals, 'chis_' + chi)
         taus = []
@@ -32,8 +37,8 @@ def main():
         res = krotov.optimize_pulses(
             wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
             propagator=krotov.propagators.expm, chi_constructor=chi_fn,
-            iter_stop=3, store_all_pulses=True, parallel_map=GPUShards(),
-            info_hook=hook)
+            iter_stop=3, store_all_pulses=True,
+            parallel_map=GPUShards(mode=mode), info_hook=hook)
         ref = krotov.optimize_pulses(
             wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
             propagator=krotov.propagators.expm, chi_constructor=chi_fn,
@@ -46,9 +51,9 @@ def main():
         dist.broadcast(t0, 0)
         same = bool(torch.equal(t, t0))
         tau_err = np.max(np.abs(taus[-1] - np.array(ref.tau_vals[-1])))
-        print("rank %d/%d K=%d chi=%s rel pulse dev vs 1 GPU = %.2e, "
-              "tau dev = %.2e, identical across ranks = %s"
-              % (rank, world, K, chi, err, tau_err, same), flush=True)
+        print("rank %d/%d K=%d chi=%s mode=%s rel pulse dev vs 1 GPU = %.2e,"
+              " tau dev = %.2e, identical across ranks = %s"
+              % (rank, world, K, chi, mode, err, tau_err, same), flush=True)
         ok = ok and err < 1e-12 and same and tau_err < 1e-12
     dist.barrier()
     dist.destroy_process_group()
