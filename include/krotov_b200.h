@@ -101,6 +101,12 @@ enum { KQ_CHI_RE = 0, KQ_CHI_SS = 1, KQ_CHI_SM = 2, KQ_CHI_HS = 3 };
 int kq_version(void);
 const char* kq_last_error(void);
 
+/* Library options (process-wide).  "time_parallel" (default 1): propagation
+ * sweeps under known pulses (kq_propagate_forward, kq_sweep_backward*) are cut
+ * into time segments that run concurrently (segment propagators -> boundary
+ * states -> states); 0 selects the purely sequential sweep. */
+int kq_set_option(const char* name, int value);
+
 /* Cross-GPU exchange buffers (one process per GPU).  kq_comm_alloc allocates
  * `bytes` of zeroed device memory on the current device and returns a 64-byte
  * CUDA IPC handle to pass to the peer processes (e.g. through

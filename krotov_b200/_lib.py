@@ -55,6 +55,7 @@ class KqComm(ctypes.Structure):
 _SIGNATURES = {
     'kq_version': (ctypes.c_int, []),
     'kq_last_error': (ctypes.c_char_p, []),
+    'kq_set_option': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     'kq_comm_alloc': (ctypes.c_int, [ctypes.c_size_t,
                                      ctypes.POINTER(ctypes.c_void_p),
                                      ctypes.c_char_p]),

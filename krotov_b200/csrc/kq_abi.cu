@@ -49,6 +49,30 @@ struct DeviceInfo {
 DeviceInfo g_dev[kMaxDevices];
 std::mutex g_mu;
 
+// Per-device scratch for the time-parallel propagation (segment propagators
+// and boundary states).  Grown on demand; calls on one device are expected to
+// be stream-ordered with respect to each other.
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+Scratch g_scratch[kMaxDevices];
+bool g_disable_segments = false;   // kq_set_option("time_parallel", 0)
+
+int get_scratch(int dev, size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  Scratch& sc = g_scratch[dev];
+  if (sc.bytes < bytes) {
+    if (sc.ptr) KQ_CUDA(cudaFree(sc.ptr));   // synchronises the device
+    sc.ptr = nullptr;
+    sc.bytes = 0;
+    KQ_CUDA(cudaMalloc(&sc.ptr, bytes));
+    sc.bytes = bytes;
+  }
+  *out = sc.ptr;
+  return KQ_OK;
+}
+
 // Taylor degree per binade: smallest m with  b^(m+1)/(m+1)! <= 2^-56,
 // b = min(1, 2^-bin) the largest scaled norm in the bin.
 void build_tables(KqTables& T) {
@@ -213,6 +237,8 @@ KqSweepArgs base_args(const kq_problem* p) {
   a.world = 1;
   a.k_lo = 0;
   a.k_cnt = p->K;
+  a.seg_len = 0;
+  a.seg_pass = 0;
   return a;
 }
 
@@ -257,7 +283,21 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   const int fsel = p->is_super ? 2 : (backward ? 1 : 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.family == 0) {
-    return pl.spec ? kq_launch_prop_spec(a, pl, fsel, st) : kq_launch_prop_small(a, pl, fsel, st);
+    if (!pl.spec) return kq_launch_prop_small(a, pl, fsel, st);
+    // time-parallel propagation: segments of seg_len steps run concurrently
+    // (pass 1: segment propagators, chain, pass 2: states), SURVEY.md §5.7
+    int nseg = 1;
+    if (p->NT >= 64 && !g_disable_segments) {
+      a.seg_len = std::max(16, (p->NT + 63) / 64);
+      nseg = (p->NT + a.seg_len - 1) / a.seg_len;
+      const size_t nP = (size_t)nseg * p->K * p->N * p->N, nB = (size_t)(nseg + 1) * p->K * p->N;
+      void* scratch = nullptr;
+      rc = get_scratch(dev, (nP + nB) * sizeof(cplx), &scratch);
+      if (rc) return rc;
+      a.seg_P = reinterpret_cast<cplx*>(scratch);
+      a.seg_B = a.seg_P + nP;
+    }
+    return kq_launch_prop_spec(a, pl, fsel, nseg, st);
   }
   return launch_warp(a, pl, fsel, false, false, st);
 }
@@ -349,7 +389,15 @@ __global__ void k_chi_boundary(int K, int N, int kind, int K_total, const cplx* 
 
 extern "C" {
 
-int kq_version(void) { return 101; }
+int kq_version(void) { return 102; }
+
+int kq_set_option(const char* name, int value) {
+  if (name && std::strcmp(name, "time_parallel") == 0) {
+    g_disable_segments = (value == 0);
+    return KQ_OK;
+  }
+  return fail(KQ_ERR_ARG, "unknown option '%s'", name ? name : "(null)");
+}
 
 // ---- cross-GPU exchange buffers (CUDA IPC) --------------------------------
 int kq_comm_alloc(size_t bytes, void** ptr, unsigned char* handle64) {

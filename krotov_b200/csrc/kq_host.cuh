@@ -24,6 +24,7 @@ struct KqPlan {
   int spec;    // specialised M=2 (L=1) straight-line kernels (kq_spec.cuh)
   int family;  // 0 thread-per-objective, 1 lane-per-row
   int grid, block;
+  int grid_y;  // segments of a time-parallel propagation (1 otherwise)
   size_t smem;
   KqWarpGeom geom;
   int rpl;
@@ -45,10 +46,11 @@ int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** 
       return kq_fail(KQ_ERR_UNSUPPORTED,
                   "fused sweep needs %d co-resident CTAs but only %d fit (K too large)", pl.grid,
                   per_sm * sms);
-    KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params,
-                                        pl.smem, st));
+    KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1), dim3(pl.block),
+                                        params, pl.smem, st));
   } else {
-    KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid), dim3(pl.block), params, pl.smem, st));
+    KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1),
+                             dim3(pl.block), params, pl.smem, st));
   }
   return KQ_OK;
 }
@@ -75,7 +77,8 @@ int kq_tables_upload_warp32(const KqTables* T);
 int kq_launch_prop_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
 int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                           cudaStream_t st);
-int kq_launch_prop_spec(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
+int kq_launch_prop_spec(const KqSweepArgs& a, const KqPlan& pl, int fsel, int nseg,
+                        cudaStream_t st);
 int kq_launch_fwupd_spec2(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                           cudaStream_t st);
 int kq_launch_fwupd_spec3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,

@@ -44,6 +44,14 @@ struct KqSweepArgs {
   // propagation sweeps only: objectives [k_lo, k_lo + k_cnt) are propagated
   // (K stays the row stride of the stores)
   int k_lo, k_cnt;
+  // time-parallel propagation (kq_spec.cuh): the sweep is cut into segments of
+  // seg_len steps (sweep order); pass 1 computes the N x N propagator of every
+  // segment into seg_P [S][K][N*N], a chain kernel turns them into the states
+  // at the segment boundaries seg_B [S+1][K][N], pass 2 propagates every
+  // segment from its boundary state and stores all states.  seg_pass 0 = off.
+  int seg_len, seg_pass;
+  cplx* seg_P;
+  cplx* seg_B;
 };
 
 __device__ __forceinline__ void kq_store(const KqSweepArgs& a, size_t idx, cplx v) {

@@ -175,10 +175,14 @@ struct SpecTerms {
 // ---------------------------------------------------------------------------
 // Propagation sweeps (optimize.py:806-886), M = 2.
 // shared: [sdt KQ_NTC][spulse KQ_NTC][splan KQ_NTC bytes][scratch 32][terms (N = 4)]
-template <int N, bool INREG>
+//
+// NVEC = 1: one state per objective.  NVEC = N: the N basis vectors are
+// propagated together (pass 1 of the time-parallel sweep: the result is the
+// propagator of the segment).  blockIdx.y selects the segment.
+template <int N, bool INREG, int NVEC>
 struct PropCtx {
   SpecTerms<N, INREG> T;
-  cplx y[N];
+  cplx y[NVEC][N];
   const double* sdt;
   const double* sp;
   const unsigned char* splan;
@@ -193,38 +197,45 @@ struct PropCtx {
 };
 
 // Run consecutive steps j (moving by c.dir) while their planned degree is MT.
-template <int N, bool INREG, int MT>
-__device__ __forceinline__ int prop_run(PropCtx<N, INREG>& c, int j, int jend) {
+template <int N, bool INREG, int NVEC, int MT>
+__device__ __forceinline__ int prop_run(PropCtx<N, INREG, NVEC>& c, int j, int jend) {
   constexpr int NN = N * N;
   while (j != jend && c.splan[j] == MT) {
     const int n = c.base + j;
     const double dtn = c.sdt[j];
     const double eps = c.driven ? (c.staged ? c.sp[j] : c.pulse[n]) : c.c1_fixed;
-    cplx At[NN], out[N];
+    cplx At[NN];
+    int s = 1, m = MT;
     if (MT > 0) {
       c.T.assemble(dtn, dtn * eps, At);
-      expmv_fixed<N, (MT > 0 ? MT : 1)>(At, c.y, out);
     } else {
-      int s, m;
       double bound;
       plan_bound(dtn * fma(fabs(eps), c.opn1, c.opn0), s, m, bound);
       const double h = dtn / (double)s;
       c.T.assemble(h, h * eps, At);
-      expmv_generic<N>(At, c.y, out, s, m);
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) c.y[i] = out[i];
-    if (c.store && c.valid) {
+    for (int v = 0; v < NVEC; ++v) {
+      cplx out[N];
+      if (MT > 0)
+        expmv_fixed<N, (MT > 0 ? MT : 1)>(At, c.y[v], out);
+      else
+        expmv_generic<N>(At, c.y[v], out, s, m);
+#pragma unroll
+      for (int i = 0; i < N; ++i) c.y[v][i] = out[i];
+    }
+    if (NVEC == 1 && c.store && c.valid) {
       const size_t row = (c.dir < 0) ? (size_t)n : (size_t)n + 1;
 #pragma unroll
-      for (int i = 0; i < N; ++i) kq_store(*c.args, row * c.row_stride + c.kofs + i, out[i]);
+      for (int i = 0; i < N; ++i)
+        kq_store(*c.args, row * c.row_stride + c.kofs + i, c.y[0][i]);
     }
     j += c.dir;
   }
   return j;
 }
 
-template <int N, int FSEL>
+template <int N, int FSEL, int NVEC>
 __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NN = N * N;
@@ -238,7 +249,7 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   double* sp = sdt + KQ_NTC;
   unsigned char* splan = reinterpret_cast<unsigned char*>(sp + KQ_NTC);
   double* scratch = reinterpret_cast<double*>(splan + KQ_NTC);
-  PropCtx<N, INREG> c;
+  PropCtx<N, INREG, NVEC> c;
   c.T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
                           reinterpret_cast<cplx*>(scratch + 32), BT, tid);
   c.opn0 = a.op_norm[k * 2 + 0];
@@ -261,18 +272,40 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   const double O0 = block_max(c.opn0, scratch);
   const double O1 = block_max(c.driven ? c.opn1 : 0.0, scratch);
   const double Oc = block_max(c.driven ? 0.0 : c.c1_fixed * c.opn1, scratch);
-#pragma unroll
-  for (int i = 0; i < N; ++i) c.y[i] = a.state0[(size_t)k * N + i];
-  if (a.store && valid) {
-    const size_t row = a.backward ? (size_t)NT : 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) kq_store(a, row * c.row_stride + c.kofs + i, c.y[i]);
+  // time window [w0, w1) of this CTA: the whole sweep, or segment blockIdx.y
+  const int seg = blockIdx.y;
+  int w0 = 0, w1 = NT;
+  if (a.seg_pass) {
+    if (a.backward) {
+      w1 = NT - seg * a.seg_len;
+      w0 = max(0, w1 - a.seg_len);
+    } else {
+      w0 = seg * a.seg_len;
+      w1 = min(NT, w0 + a.seg_len);
+    }
   }
-  const int nchunks = (NT + KQ_NTC - 1) / KQ_NTC;
-  for (int cc = 0; cc < nchunks; ++cc) {
-    const int ch = a.backward ? nchunks - 1 - cc : cc;
-    const int base = ch * KQ_NTC;
-    const int len = min(KQ_NTC, NT - base);
+  const bool first_seg = (seg == 0), last_seg = (seg == (int)gridDim.y - 1);
+  if (NVEC > 1) {
+#pragma unroll
+    for (int v = 0; v < NVEC; ++v)
+#pragma unroll
+      for (int i = 0; i < N; ++i) c.y[v][i] = c_make(v == i ? 1.0 : 0.0, 0.0);
+  } else {
+    const cplx* init = a.seg_pass ? a.seg_B + ((size_t)seg * K + k) * N
+                                  : a.state0 + (size_t)k * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) c.y[0][i] = init[i];
+    if (a.store && valid && first_seg) {
+      const size_t row = a.backward ? (size_t)NT : 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) kq_store(a, row * c.row_stride + c.kofs + i, c.y[0][i]);
+    }
+  }
+  const int c0 = w0 / KQ_NTC, c1 = (w1 - 1) / KQ_NTC;   // chunks touched by the window
+  for (int cc = 0; cc <= c1 - c0; ++cc) {
+    const int ch = a.backward ? c1 - cc : c0 + cc;
+    const int base = max(w0, ch * KQ_NTC);
+    const int len = min(w1, (ch + 1) * KQ_NTC) - base;
     __syncthreads();
     for (int i = tid; i < len; i += BT) {
       const double dti = a.dt[base + i];
@@ -298,21 +331,60 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
     const int jend = a.backward ? -1 : len;
     while (j != jend) {
       switch (splan[j]) {
-        case 1: j = prop_run<N, INREG, 1>(c, j, jend); break;
-        case 2: j = prop_run<N, INREG, 2>(c, j, jend); break;
-        case 3: j = prop_run<N, INREG, 3>(c, j, jend); break;
-        case 4: j = prop_run<N, INREG, 4>(c, j, jend); break;
-        case 5: j = prop_run<N, INREG, 5>(c, j, jend); break;
-        case 6: j = prop_run<N, INREG, 6>(c, j, jend); break;
-        case 7: j = prop_run<N, INREG, 7>(c, j, jend); break;
-        case 8: j = prop_run<N, INREG, 8>(c, j, jend); break;
-        default: j = prop_run<N, INREG, 0>(c, j, jend); break;
+        case 1: j = prop_run<N, INREG, NVEC, 1>(c, j, jend); break;
+        case 2: j = prop_run<N, INREG, NVEC, 2>(c, j, jend); break;
+        case 3: j = prop_run<N, INREG, NVEC, 3>(c, j, jend); break;
+        case 4: j = prop_run<N, INREG, NVEC, 4>(c, j, jend); break;
+        case 5: j = prop_run<N, INREG, NVEC, 5>(c, j, jend); break;
+        case 6: j = prop_run<N, INREG, NVEC, 6>(c, j, jend); break;
+        case 7: j = prop_run<N, INREG, NVEC, 7>(c, j, jend); break;
+        case 8: j = prop_run<N, INREG, NVEC, 8>(c, j, jend); break;
+        default: j = prop_run<N, INREG, NVEC, 0>(c, j, jend); break;
       }
     }
   }
-  if (a.stateT && valid) {
+  if (NVEC > 1) {
+    // propagator of the segment, column-major: column v = image of e_v
+    if (valid) {
+      cplx* P = a.seg_P + ((size_t)seg * K + k) * NN;
 #pragma unroll
-    for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = c.y[i];
+      for (int v = 0; v < NVEC; ++v)
+#pragma unroll
+        for (int i = 0; i < N; ++i) P[v * N + i] = c.y[v][i];
+    }
+  } else if (a.stateT && valid && last_seg) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = c.y[0][i];
+  }
+}
+
+// Boundary states of the segments: B[0] = state0, B[q+1] = P_q B[q].
+template <int N>
+__global__ void k_seg_chain(const KqSweepArgs a, int nseg) {
+  const int k = a.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.k_lo + a.k_cnt) return;
+  const int K = a.K;
+  cplx b[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    b[i] = a.state0[(size_t)k * N + i];
+    a.seg_B[((size_t)0 * K + k) * N + i] = b[i];
+  }
+  for (int q = 0; q < nseg; ++q) {
+    const cplx* P = a.seg_P + ((size_t)q * K + k) * N * N;
+    cplx o[N];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      cplx acc = c_zero();
+#pragma unroll
+      for (int c = 0; c < N; ++c) acc = c_fma(P[c * N + r], b[c], acc);
+      o[r] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      b[i] = o[i];
+      a.seg_B[((size_t)(q + 1) * K + k) * N + i] = o[i];
+    }
   }
 }
 
