@@ -81,6 +81,10 @@ typedef struct {
   const double*  dt;
   const double*  shape;
   const double*  lambda_a;
+  int32_t real_ops;   /* 1: every matrix in ops/ops_adj has zero imaginary part
+                         (real Hamiltonians): kernels use the purely imaginary
+                         form of f*A in Hilbert space; 0: general complex */
+  int32_t reserved;
 } kq_problem;
 
 /* Cross-GPU exchange descriptor for the per-time-step reduction of the pulse

@@ -43,6 +43,7 @@ class KqProblem(ctypes.Structure):
         ('mu', ctypes.c_void_p), ('term2pulse', ctypes.c_void_p),
         ('op_norm', ctypes.c_void_p), ('dt', ctypes.c_void_p),
         ('shape', ctypes.c_void_p), ('lambda_a', ctypes.c_void_p),
+        ('real_ops', ctypes.c_int32), ('reserved', ctypes.c_int32),
     ]
 
 
@@ -110,7 +111,7 @@ def build_library(verbose=False, jobs=None):
     sources = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)
                      if f.endswith('.cu'))
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
-               if f.endswith('.cuh')]
+               if f.endswith(('.cuh', '.inc'))]
     headers.append(os.path.join(INCLUDE, 'krotov_b200.h'))
     newest_hdr = max(os.path.getmtime(h) for h in headers)
     objdir = os.path.join(CSRC, 'build')

@@ -105,6 +105,7 @@ class CompiledProblem:
     def __init__(self):
         self.K = self.N = self.NT = self.L = self.M = 0
         self.is_super = False
+        self.real_ops = False
         self.ops = self.ops_adj = self.mu = None      # complex128 arrays
         self.term2pulse = self.op_norm = None
         self.psi0 = self.targets = None               # [K,N]
@@ -231,6 +232,8 @@ def compile_problem(objectives, controls, mapping, tlist, mu=None,
             t2p[k, m] = l
     cp.term2pulse = t2p
     cp.op_norm = np.abs(ops).sum(axis=2).max(axis=2)  # 1-norm per term
+    # real Hamiltonians: f*A is purely imaginary, kernels halve the multiplies
+    cp.real_ops = bool(np.all(ops.imag == 0.0))
     ops_adj = np.conj(np.swapaxes(ops, 2, 3))
 
     # mu table

@@ -104,6 +104,8 @@ int device_init(int* dev_out) {
     int (*const uploads[])(const KqTables*) = {
         kq_tables_upload_abi,      kq_tables_upload_small,    kq_tables_upload_spec_prop,
         kq_tables_upload_spec_fw2, kq_tables_upload_spec_fw3, kq_tables_upload_spec_fw4,
+        kq_tables_upload_spec_prop_re, kq_tables_upload_spec_fw2_re,
+        kq_tables_upload_spec_fw3_re, kq_tables_upload_spec_fw4_re,
         kq_tables_upload_warp0,    kq_tables_upload_warp8,    kq_tables_upload_warp16,
         kq_tables_upload_warp32};
     for (auto up : uploads) {
@@ -297,6 +299,8 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
       a.seg_P = reinterpret_cast<cplx*>(scratch);
       a.seg_B = a.seg_P + nP;
     }
+    // real generator matrices in Hilbert space: purely imaginary f*A
+    if (p->real_ops && !p->is_super) return kq_launch_prop_spec_re(a, pl, fsel, nseg, st);
     return kq_launch_prop_spec(a, pl, fsel, nseg, st);
   }
   return launch_warp(a, pl, fsel, false, false, st);
@@ -551,6 +555,13 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (pl.family == 0) {
     if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
+    if (p->real_ops && !p->is_super) {
+      switch (p->N) {
+        case 2: return kq_launch_fwupd_spec2_re(a, pl, fsel, second, st);
+        case 3: return kq_launch_fwupd_spec3_re(a, pl, fsel, second, st);
+        default: return kq_launch_fwupd_spec4_re(a, pl, fsel, second, st);
+      }
+    }
     switch (p->N) {
       case 2: return kq_launch_fwupd_spec2(a, pl, fsel, second, st);
       case 3: return kq_launch_fwupd_spec3(a, pl, fsel, second, st);

@@ -66,6 +66,10 @@ int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** 
 int kq_tables_upload_abi(const KqTables* T);
 int kq_tables_upload_small(const KqTables* T);
 int kq_tables_upload_spec_prop(const KqTables* T);
+int kq_tables_upload_spec_prop_re(const KqTables* T);
+int kq_tables_upload_spec_fw2_re(const KqTables* T);
+int kq_tables_upload_spec_fw3_re(const KqTables* T);
+int kq_tables_upload_spec_fw4_re(const KqTables* T);
 int kq_tables_upload_spec_fw2(const KqTables* T);
 int kq_tables_upload_spec_fw3(const KqTables* T);
 int kq_tables_upload_spec_fw4(const KqTables* T);
@@ -79,6 +83,14 @@ int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool
                           cudaStream_t st);
 int kq_launch_prop_spec(const KqSweepArgs& a, const KqPlan& pl, int fsel, int nseg,
                         cudaStream_t st);
+int kq_launch_prop_spec_re(const KqSweepArgs& a, const KqPlan& pl, int fsel, int nseg,
+                           cudaStream_t st);
+int kq_launch_fwupd_spec2_re(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                             cudaStream_t st);
+int kq_launch_fwupd_spec3_re(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                             cudaStream_t st);
+int kq_launch_fwupd_spec4_re(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                             cudaStream_t st);
 int kq_launch_fwupd_spec2(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                           cudaStream_t st);
 int kq_launch_fwupd_spec3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,

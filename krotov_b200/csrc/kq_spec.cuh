@@ -60,9 +60,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Generator element type G: `cplx` in general; `double` when every generator
+// term is a real matrix in Hilbert space -- then f*A = -+i*A_re is purely
+// imaginary, the element r stands for i*r and a product costs 2 FMAs, not 4.
+__device__ __forceinline__ cplx g_fma(cplx a, cplx y, cplx acc) { return c_fma(a, y, acc); }
+__device__ __forceinline__ cplx g_fma(double r, cplx y, cplx acc) {
+  acc.x = fma(-r, y.y, acc.x);   // (i r)(y.x + i y.y) = -r y.y + i r y.x
+  acc.y = fma(r, y.x, acc.y);
+  return acc;
+}
+template <int FSEL>
+__device__ __forceinline__ cplx g_load(cplx t, cplx) { return apply_f<FSEL>(t); }
+template <int FSEL>
+__device__ __forceinline__ double g_load(cplx t, double) {
+  return (FSEL == 0) ? -t.x : t.x;   // -i*t = i*(-t) ; +i*t = i*t   (t real)
+}
+__device__ __forceinline__ cplx g_axpy(double h, cplx a, double heps, cplx b) {
+  return make_double2(fma(heps, b.x, h * a.x), fma(heps, b.y, h * a.y));
+}
+__device__ __forceinline__ double g_axpy(double h, double a, double heps, double b) {
+  return fma(heps, b, h * a);
+}
+
 // y <- v + invj * (At y)   for At = h f A (column-major, registers)
-template <int N>
-__device__ __forceinline__ void horner_step(const cplx (&At)[N * N], const cplx (&v)[N],
+template <int N, typename G>
+__device__ __forceinline__ void horner_step(const G (&At)[N * N], const cplx (&v)[N],
                                             cplx (&y)[N], double invj) {
   cplx w[N];
 #pragma unroll
@@ -71,9 +93,9 @@ __device__ __forceinline__ void horner_step(const cplx (&At)[N * N], const cplx 
 #pragma unroll
     for (int c = 0; c < N; ++c) {
       if (c & 1)
-        a1 = c_fma(At[c * N + r], y[c], a1);
+        a1 = g_fma(At[c * N + r], y[c], a1);
       else
-        a0 = c_fma(At[c * N + r], y[c], a0);
+        a0 = g_fma(At[c * N + r], y[c], a0);
     }
     w[r] = (N > 1) ? c_add(a0, a1) : a0;
   }
@@ -82,18 +104,18 @@ __device__ __forceinline__ void horner_step(const cplx (&At)[N * N], const cplx 
 }
 
 // y <- exp(At) v with a compile-time Taylor degree M (fully unrolled, 1/j immediates).
-template <int N, int M>
-__device__ __forceinline__ void expmv_fixed(const cplx (&At)[N * N], const cplx (&v)[N],
+template <int N, int M, typename G>
+__device__ __forceinline__ void expmv_fixed(const G (&At)[N * N], const cplx (&v)[N],
                                             cplx (&y)[N]) {
 #pragma unroll
   for (int i = 0; i < N; ++i) y[i] = v[i];
 #pragma unroll
-  for (int j = M; j >= 1; --j) horner_step<N>(At, v, y, 1.0 / (double)j);
+  for (int j = M; j >= 1; --j) horner_step<N, G>(At, v, y, 1.0 / (double)j);
 }
 
 // y <- exp(At)^s v, run-time degree (generic path: s > 1 or m > KQ_MFIX)
-template <int N>
-__device__ __forceinline__ void expmv_generic(const cplx (&At)[N * N], const cplx (&v)[N],
+template <int N, typename G>
+__device__ __forceinline__ void expmv_generic(const G (&At)[N * N], const cplx (&v)[N],
                                               cplx (&y)[N], int s, int m) {
   cplx in[N];
 #pragma unroll
@@ -101,7 +123,7 @@ __device__ __forceinline__ void expmv_generic(const cplx (&At)[N * N], const cpl
   for (int rep = 0; rep < s; ++rep) {
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = in[i];
-    for (int j = m; j >= 1; --j) horner_step<N>(At, in, y, c_kq_tables.inv[j]);
+    for (int j = m; j >= 1; --j) horner_step<N, G>(At, in, y, c_kq_tables.inv[j]);
 #pragma unroll
     for (int i = 0; i < N; ++i) in[i] = y[i];
   }
@@ -134,40 +156,40 @@ __device__ __forceinline__ double block_max(double v, double* scratch) {
 }
 
 // Terms of one objective, pre-rotated by f: T0f = f*T0, T1f = f*T1.
-template <int N, bool INREG>
+template <int N, bool INREG, typename G>
 struct SpecTerms {
-  cplx t0[INREG ? N * N : 1], t1[INREG ? N * N : 1];
-  const cplx* s0;
-  const cplx* s1;
+  G t0[INREG ? N * N : 1], t1[INREG ? N * N : 1];
+  const G* s0;
+  const G* s1;
   int stride;
   template <int FSEL>
-  __device__ __forceinline__ void load(const cplx* g0, const cplx* g1, cplx* smem, int BT,
+  __device__ __forceinline__ void load(const cplx* g0, const cplx* g1, void* smem, int BT,
                                        int tid) {
     if (INREG) {
 #pragma unroll
       for (int e = 0; e < N * N; ++e) {
-        t0[e] = apply_f<FSEL>(g0[e]);
-        t1[e] = apply_f<FSEL>(g1[e]);
+        t0[e] = g_load<FSEL>(g0[e], G());
+        t1[e] = g_load<FSEL>(g1[e], G());
       }
     } else {
       stride = BT;
-      cplx* p0 = smem + tid;
-      cplx* p1 = smem + (size_t)N * N * BT + tid;
+      G* p0 = reinterpret_cast<G*>(smem) + tid;
+      G* p1 = reinterpret_cast<G*>(smem) + (size_t)N * N * BT + tid;
       for (int e = 0; e < N * N; ++e) {
-        p0[(size_t)e * BT] = apply_f<FSEL>(g0[e]);
-        p1[(size_t)e * BT] = apply_f<FSEL>(g1[e]);
+        p0[(size_t)e * BT] = g_load<FSEL>(g0[e], G());
+        p1[(size_t)e * BT] = g_load<FSEL>(g1[e], G());
       }
       s0 = p0;
       s1 = p1;
     }
   }
   // At = h*T0f + (h*eps)*T1f
-  __device__ __forceinline__ void assemble(double h, double heps, cplx (&At)[N * N]) const {
+  __device__ __forceinline__ void assemble(double h, double heps, G (&At)[N * N]) const {
 #pragma unroll
     for (int e = 0; e < N * N; ++e) {
-      const cplx a = INREG ? t0[e] : s0[(size_t)e * stride];
-      const cplx b = INREG ? t1[e] : s1[(size_t)e * stride];
-      At[e] = make_double2(fma(heps, b.x, h * a.x), fma(heps, b.y, h * a.y));
+      const G a = INREG ? t0[e] : s0[(size_t)e * stride];
+      const G b = INREG ? t1[e] : s1[(size_t)e * stride];
+      At[e] = g_axpy(h, a, heps, b);
     }
   }
 };
@@ -179,9 +201,9 @@ struct SpecTerms {
 // NVEC = 1: one state per objective.  NVEC = N: the N basis vectors are
 // propagated together (pass 1 of the time-parallel sweep: the result is the
 // propagator of the segment).  blockIdx.y selects the segment.
-template <int N, bool INREG, int NVEC>
+template <int N, bool INREG, int NVEC, typename G>
 struct PropCtx {
-  SpecTerms<N, INREG> T;
+  SpecTerms<N, INREG, G> T;
   cplx y[NVEC][N];
   const double* sdt;
   const double* sp;
@@ -197,14 +219,14 @@ struct PropCtx {
 };
 
 // Run consecutive steps j (moving by c.dir) while their planned degree is MT.
-template <int N, bool INREG, int NVEC, int MT>
-__device__ __forceinline__ int prop_run(PropCtx<N, INREG, NVEC>& c, int j, int jend) {
+template <int N, bool INREG, int NVEC, typename G, int MT>
+__device__ __forceinline__ int prop_run(PropCtx<N, INREG, NVEC, G>& c, int j, int jend) {
   constexpr int NN = N * N;
   while (j != jend && c.splan[j] == MT) {
     const int n = c.base + j;
     const double dtn = c.sdt[j];
     const double eps = c.driven ? (c.staged ? c.sp[j] : c.pulse[n]) : c.c1_fixed;
-    cplx At[NN];
+    G At[NN];
     int s = 1, m = MT;
     if (MT > 0) {
       c.T.assemble(dtn, dtn * eps, At);
@@ -218,9 +240,9 @@ __device__ __forceinline__ int prop_run(PropCtx<N, INREG, NVEC>& c, int j, int j
     for (int v = 0; v < NVEC; ++v) {
       cplx out[N];
       if (MT > 0)
-        expmv_fixed<N, (MT > 0 ? MT : 1)>(At, c.y[v], out);
+        expmv_fixed<N, (MT > 0 ? MT : 1), G>(At, c.y[v], out);
       else
-        expmv_generic<N>(At, c.y[v], out, s, m);
+        expmv_generic<N, G>(At, c.y[v], out, s, m);
 #pragma unroll
       for (int i = 0; i < N; ++i) c.y[v][i] = out[i];
     }
@@ -235,7 +257,7 @@ __device__ __forceinline__ int prop_run(PropCtx<N, INREG, NVEC>& c, int j, int j
   return j;
 }
 
-template <int N, int FSEL, int NVEC>
+template <int N, int FSEL, int NVEC, typename G>
 __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NN = N * N;
@@ -249,9 +271,9 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
   double* sp = sdt + KQ_NTC;
   unsigned char* splan = reinterpret_cast<unsigned char*>(sp + KQ_NTC);
   double* scratch = reinterpret_cast<double*>(splan + KQ_NTC);
-  PropCtx<N, INREG, NVEC> c;
+  PropCtx<N, INREG, NVEC, G> c;
   c.T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
-                          reinterpret_cast<cplx*>(scratch + 32), BT, tid);
+                          scratch + 32, BT, tid);
   c.opn0 = a.op_norm[k * 2 + 0];
   c.opn1 = a.op_norm[k * 2 + 1];
   const int l = a.term2pulse[k * 2 + 1];
@@ -331,15 +353,15 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
     const int jend = a.backward ? -1 : len;
     while (j != jend) {
       switch (splan[j]) {
-        case 1: j = prop_run<N, INREG, NVEC, 1>(c, j, jend); break;
-        case 2: j = prop_run<N, INREG, NVEC, 2>(c, j, jend); break;
-        case 3: j = prop_run<N, INREG, NVEC, 3>(c, j, jend); break;
-        case 4: j = prop_run<N, INREG, NVEC, 4>(c, j, jend); break;
-        case 5: j = prop_run<N, INREG, NVEC, 5>(c, j, jend); break;
-        case 6: j = prop_run<N, INREG, NVEC, 6>(c, j, jend); break;
-        case 7: j = prop_run<N, INREG, NVEC, 7>(c, j, jend); break;
-        case 8: j = prop_run<N, INREG, NVEC, 8>(c, j, jend); break;
-        default: j = prop_run<N, INREG, NVEC, 0>(c, j, jend); break;
+        case 1: j = prop_run<N, INREG, NVEC, G, 1>(c, j, jend); break;
+        case 2: j = prop_run<N, INREG, NVEC, G, 2>(c, j, jend); break;
+        case 3: j = prop_run<N, INREG, NVEC, G, 3>(c, j, jend); break;
+        case 4: j = prop_run<N, INREG, NVEC, G, 4>(c, j, jend); break;
+        case 5: j = prop_run<N, INREG, NVEC, G, 5>(c, j, jend); break;
+        case 6: j = prop_run<N, INREG, NVEC, G, 6>(c, j, jend); break;
+        case 7: j = prop_run<N, INREG, NVEC, G, 7>(c, j, jend); break;
+        case 8: j = prop_run<N, INREG, NVEC, G, 8>(c, j, jend); break;
+        default: j = prop_run<N, INREG, NVEC, G, 0>(c, j, jend); break;
       }
     }
   }
@@ -392,9 +414,9 @@ __global__ void k_seg_chain(const KqSweepArgs a, int nseg) {
 // Fused update + forward sweep (optimize.py:449-500), M = 2, L = 1.
 // shared: [red 2*32 | tot 2 | pad][mbar KQ_RING][sdt|sg|ssl|ssig|sbound KQ_NTC each]
 //         [splan KQ_NTC bytes][chi ring KQ_RING * BT*N][Phi0 ring (SECOND)][terms (N = 4)]
-template <int N, bool INREG, bool SECOND>
+template <int N, bool INREG, bool SECOND, typename G>
 struct FwCtx {
-  SpecTerms<N, INREG> T;
+  SpecTerms<N, INREG, G> T;
   cplx phi[N], chi[N], eta[N], dphi[N], mu[N * N];
   double cnorm, opn0, opn1, c1_fixed, ga, O0, O1, Oc;
   bool driven, valid, writer, multi, failed;
@@ -409,8 +431,8 @@ struct FwCtx {
   int k0;
 };
 
-template <int N, bool INREG, bool SECOND>
-__device__ __forceinline__ void fw_make_eta(FwCtx<N, INREG, SECOND>& c) {
+template <int N, bool INREG, bool SECOND, typename G>
+__device__ __forceinline__ void fw_make_eta(FwCtx<N, INREG, SECOND, G>& c) {
 #pragma unroll
   for (int cc = 0; cc < N; ++cc) {
     cplx acc = c_zero();
@@ -420,8 +442,8 @@ __device__ __forceinline__ void fw_make_eta(FwCtx<N, INREG, SECOND>& c) {
   }
 }
 
-template <int N, bool INREG, bool SECOND>
-__device__ __forceinline__ void fw_issue_row(const KqSweepArgs& a, FwCtx<N, INREG, SECOND>& c,
+template <int N, bool INREG, bool SECOND, typename G>
+__device__ __forceinline__ void fw_issue_row(const KqSweepArgs& a, FwCtx<N, INREG, SECOND, G>& c,
                                              int r) {
   const int st = r % KQ_RING;
   mbar_expect_tx(&c.mbar[st], SECOND ? 2 * c.row_bytes : c.row_bytes);
@@ -433,8 +455,8 @@ __device__ __forceinline__ void fw_issue_row(const KqSweepArgs& a, FwCtx<N, INRE
 }
 
 // Run consecutive steps while their planned Taylor degree is MT (0 = generic).
-template <int N, bool INREG, bool SECOND, int MT>
-__device__ __forceinline__ int fw_run(const KqSweepArgs& a, FwCtx<N, INREG, SECOND>& c, int j,
+template <int N, bool INREG, bool SECOND, typename G, int MT>
+__device__ __forceinline__ int fw_run(const KqSweepArgs& a, FwCtx<N, INREG, SECOND, G>& c, int j,
                                       int len) {
   constexpr int NN = N * N;
   while (j < len && c.splan[j] == MT) {
@@ -527,20 +549,21 @@ __device__ __forceinline__ int fw_run(const KqSweepArgs& a, FwCtx<N, INREG, SECO
       c.ga = __dadd_rn(c.ga, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), dt_cur));
     }
     // ---- forward step under the updated pulse -------------------------------
-    cplx At[NN], out[N];
+    G At[NN];
+    cplx out[N];
     // the plan was made from the guess pulse with CTA-wide norm bounds; the
     // updated pulse (CTA-uniform) may push the bound out of its binade (rare)
     const double x_new = dt_cur * (fma(fabs(eps_new), c.O1, c.O0) + c.Oc);
     if (MT > 0 && x_new <= c.sbound[j]) {
       c.T.assemble(dt_cur, dt_cur * eps, At);
-      expmv_fixed<N, (MT > 0 ? MT : 1)>(At, c.phi, out);
+      expmv_fixed<N, (MT > 0 ? MT : 1), G>(At, c.phi, out);
     } else {
       int s, m;
       double bound;
       plan_bound(x_new, s, m, bound);
       const double h = dt_cur / (double)s;
       c.T.assemble(h, h * eps, At);
-      expmv_generic<N>(At, c.phi, out, s, m);
+      expmv_generic<N, G>(At, c.phi, out, s, m);
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) c.phi[i] = out[i];
@@ -565,14 +588,14 @@ __device__ __forceinline__ int fw_run(const KqSweepArgs& a, FwCtx<N, INREG, SECO
   return j;
 }
 
-template <int N, int FSEL, bool SECOND, int BTMAX>
+template <int N, int FSEL, bool SECOND, int BTMAX, typename G>
 __global__ void __launch_bounds__(BTMAX, 1) k_fwupd_spec(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NN = N * N;
   constexpr bool INREG = (N <= 3);
   const int BT = blockDim.x, tid = threadIdx.x;
   const int K = a.K, NT = a.NT;
-  FwCtx<N, INREG, SECOND> c;
+  FwCtx<N, INREG, SECOND, G> c;
   c.K = K;
   c.lane = tid & 31;
   c.warp = tid >> 5;
@@ -668,15 +691,15 @@ __global__ void __launch_bounds__(BTMAX, 1) k_fwupd_spec(const KqSweepArgs a) {
     int j = 0;
     while (j < len) {
       switch (splan[j]) {
-        case 1: j = fw_run<N, INREG, SECOND, 1>(a, c, j, len); break;
-        case 2: j = fw_run<N, INREG, SECOND, 2>(a, c, j, len); break;
-        case 3: j = fw_run<N, INREG, SECOND, 3>(a, c, j, len); break;
-        case 4: j = fw_run<N, INREG, SECOND, 4>(a, c, j, len); break;
-        case 5: j = fw_run<N, INREG, SECOND, 5>(a, c, j, len); break;
-        case 6: j = fw_run<N, INREG, SECOND, 6>(a, c, j, len); break;
-        case 7: j = fw_run<N, INREG, SECOND, 7>(a, c, j, len); break;
-        case 8: j = fw_run<N, INREG, SECOND, 8>(a, c, j, len); break;
-        default: j = fw_run<N, INREG, SECOND, 0>(a, c, j, len); break;
+        case 1: j = fw_run<N, INREG, SECOND, G, 1>(a, c, j, len); break;
+        case 2: j = fw_run<N, INREG, SECOND, G, 2>(a, c, j, len); break;
+        case 3: j = fw_run<N, INREG, SECOND, G, 3>(a, c, j, len); break;
+        case 4: j = fw_run<N, INREG, SECOND, G, 4>(a, c, j, len); break;
+        case 5: j = fw_run<N, INREG, SECOND, G, 5>(a, c, j, len); break;
+        case 6: j = fw_run<N, INREG, SECOND, G, 6>(a, c, j, len); break;
+        case 7: j = fw_run<N, INREG, SECOND, G, 7>(a, c, j, len); break;
+        case 8: j = fw_run<N, INREG, SECOND, G, 8>(a, c, j, len); break;
+        default: j = fw_run<N, INREG, SECOND, G, 0>(a, c, j, len); break;
       }
     }
   }

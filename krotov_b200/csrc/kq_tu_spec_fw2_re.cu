@@ -1,0 +1,23 @@
+// Specialised fused update/forward sweep, N = 2, generator element type double
+// (kq_spec.cuh): instantiations.
+#include "kq_host.cuh"
+#include "kq_spec.cuh"
+
+KQ_DEFINE_TABLES_UPLOAD(kq_tables_upload_spec_fw2_re)
+
+int kq_launch_fwupd_spec2_re(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                          cudaStream_t st) {
+  void* params[] = {(void*)&a};
+  const bool coop = pl.grid > 1;
+  if (pl.block > 256) {
+    if (fsel == 0) {
+      return second ? launch(k_fwupd_spec<2, 0, true, 1024, double>, pl, coop, st, params)
+                    : launch(k_fwupd_spec<2, 0, false, 1024, double>, pl, coop, st, params);
+    }
+  }
+  if (fsel == 0) {
+    return second ? launch(k_fwupd_spec<2, 0, true, 256, double>, pl, coop, st, params)
+                  : launch(k_fwupd_spec<2, 0, false, 256, double>, pl, coop, st, params);
+  }
+  return kq_fail(KQ_ERR_ARG, "real-generator kernels are Hilbert-space only");
+}

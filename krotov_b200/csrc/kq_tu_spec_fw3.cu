@@ -1,4 +1,5 @@
-// Specialised fused update/forward sweep, N = 3 (kq_spec.cuh): instantiations.
+// Specialised fused update/forward sweep, N = 3, generator element type cplx
+// (kq_spec.cuh): instantiations.
 #include "kq_host.cuh"
 #include "kq_spec.cuh"
 
@@ -9,9 +10,9 @@ int kq_launch_fwupd_spec3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool
   void* params[] = {(void*)&a};
   const bool coop = pl.grid > 1;
   if (fsel == 0) {
-    return second ? launch(k_fwupd_spec<3, 0, true, 256>, pl, coop, st, params)
-                  : launch(k_fwupd_spec<3, 0, false, 256>, pl, coop, st, params);
+    return second ? launch(k_fwupd_spec<3, 0, true, 256, cplx>, pl, coop, st, params)
+                  : launch(k_fwupd_spec<3, 0, false, 256, cplx>, pl, coop, st, params);
   }
-  return second ? launch(k_fwupd_spec<3, 2, true, 256>, pl, coop, st, params)
-                : launch(k_fwupd_spec<3, 2, false, 256>, pl, coop, st, params);
+  return second ? launch(k_fwupd_spec<3, 2, true, 256, cplx>, pl, coop, st, params)
+                : launch(k_fwupd_spec<3, 2, false, 256, cplx>, pl, coop, st, params);
 }

@@ -74,7 +74,8 @@ class SweepEngine:
             ops=self.t_ops.data_ptr(), ops_adj=self.t_ops_adj.data_ptr(),
             mu=self.t_mu.data_ptr(), term2pulse=self.t_t2p.data_ptr(),
             op_norm=self.t_opn.data_ptr(), dt=self.t_dt.data_ptr(),
-            shape=self.t_shape.data_ptr(), lambda_a=self.t_lambda.data_ptr())
+            shape=self.t_shape.data_ptr(), lambda_a=self.t_lambda.data_ptr(),
+            real_ops=1 if cp.real_ops else 0, reserved=0)
         self._p = ctypes.byref(self.problem)
         nbytes = self.lib.kq_workspace_bytes(self._p)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
