@@ -129,6 +129,70 @@ __device__ __forceinline__ void expmv_generic(const G (&At)[N * N], const cplx (
   }
 }
 
+// ---- closed form for N = 2 with a real generator matrix --------------------
+// exp(i R) = e^{i t} [ C(z) I + i S(z) R' ],  t = tr(R)/2, R' = R - t I,
+// z = -det R' (R'^2 = z I), C(z) = sum_j (-z)^j/(2j)!, S(z) = sum_j (-z)^j/(2j+1)!.
+// The series are the even/odd parts of the same Taylor series the generic path
+// sums, truncated one order later (2P >= m+3, because |z| <= 2 ||R||_1^2), so the
+// accuracy is at least that of the generic path;
+// the cost drops from m complex matvecs to two real Horner recurrences.
+__host__ __device__ constexpr double kq_inv_fact(int n) {
+  double f = 1.0;
+  for (int i = 2; i <= n; ++i) f *= (double)i;
+  return 1.0 / f;
+}
+template <int P>
+__device__ __forceinline__ void expmv2_real(const double (&R)[4], const cplx (&v)[2],
+                                            cplx (&y)[2]) {
+  const double a = R[0], c = R[1], b = R[2], d = R[3];   // column-major [[a, b], [c, d]]
+  const double t = 0.5 * (a + d), dl = 0.5 * (a - d);
+  const double z = fma(dl, dl, b * c);
+  double C = kq_inv_fact(2 * (P - 1)), S = kq_inv_fact(2 * (P - 1) + 1);
+#pragma unroll
+  for (int j = P - 2; j >= 0; --j) {
+    C = fma(-z, C, kq_inv_fact(2 * j));
+    S = fma(-z, S, kq_inv_fact(2 * j + 1));
+  }
+  // w = R' v
+  const cplx w0 = make_double2(fma(dl, v[0].x, b * v[1].x), fma(dl, v[0].y, b * v[1].y));
+  const cplx w1 = make_double2(fma(-dl, v[1].x, c * v[0].x), fma(-dl, v[1].y, c * v[0].y));
+  // u = C v + i S w
+  cplx u0 = make_double2(fma(-S, w0.y, C * v[0].x), fma(S, w0.x, C * v[0].y));
+  cplx u1 = make_double2(fma(-S, w1.y, C * v[1].x), fma(S, w1.x, C * v[1].y));
+  if (t != 0.0) {   // traceless generators (two-level systems) skip the phase
+    double st, ct;
+    sincos(t, &st, &ct);
+    u0 = make_double2(fma(-st, u0.y, ct * u0.x), fma(st, u0.x, ct * u0.y));
+    u1 = make_double2(fma(-st, u1.y, ct * u1.x), fma(st, u1.x, ct * u1.y));
+  }
+  y[0] = u0;
+  y[1] = u1;
+}
+
+// One propagation step with a compile-time Taylor degree M: the closed form for
+// (N = 2, real generator), the unrolled Horner recurrence otherwise.
+template <int N, int M, typename G>
+__device__ __forceinline__ void step_fixed(const G (&At)[N * N], const cplx (&v)[N],
+                                           cplx (&y)[N]) {
+  expmv_fixed<N, M, G>(At, v, y);
+}
+template <>
+__device__ __forceinline__ void step_fixed<2, 1, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<3>(At, v, y); }
+template <>
+__device__ __forceinline__ void step_fixed<2, 2, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<3>(At, v, y); }
+template <>
+__device__ __forceinline__ void step_fixed<2, 3, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<3>(At, v, y); }
+template <>
+__device__ __forceinline__ void step_fixed<2, 4, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<4>(At, v, y); }
+template <>
+__device__ __forceinline__ void step_fixed<2, 5, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<4>(At, v, y); }
+template <>
+__device__ __forceinline__ void step_fixed<2, 6, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<5>(At, v, y); }
+template <>
+__device__ __forceinline__ void step_fixed<2, 7, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<5>(At, v, y); }
+template <>
+__device__ __forceinline__ void step_fixed<2, 8, double>(const double (&At)[4], const cplx (&v)[2], cplx (&y)[2]) { expmv2_real<6>(At, v, y); }
+
 #define KQ_MFIX 8   // Taylor degrees 1..KQ_MFIX have fully unrolled step bodies
 
 // Plan for a norm bound x: (s, m) and the largest x for which it stays valid.
@@ -240,7 +304,7 @@ __device__ __forceinline__ int prop_run(PropCtx<N, INREG, NVEC, G>& c, int j, in
     for (int v = 0; v < NVEC; ++v) {
       cplx out[N];
       if (MT > 0)
-        expmv_fixed<N, (MT > 0 ? MT : 1), G>(At, c.y[v], out);
+        step_fixed<N, (MT > 0 ? MT : 1), G>(At, c.y[v], out);
       else
         expmv_generic<N, G>(At, c.y[v], out, s, m);
 #pragma unroll
@@ -556,7 +620,7 @@ __device__ __forceinline__ int fw_run(const KqSweepArgs& a, FwCtx<N, INREG, SECO
     const double x_new = dt_cur * (fma(fabs(eps_new), c.O1, c.O0) + c.Oc);
     if (MT > 0 && x_new <= c.sbound[j]) {
       c.T.assemble(dt_cur, dt_cur * eps, At);
-      expmv_fixed<N, (MT > 0 ? MT : 1), G>(At, c.phi, out);
+      step_fixed<N, (MT > 0 ? MT : 1), G>(At, c.phi, out);
     } else {
       int s, m;
       double bound;
