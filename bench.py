@@ -163,6 +163,41 @@ def time_oracle(wl, iters, k_sample=None):
     return per_iter, ks
 
 
+def time_c_oracle(wl, iters=3):
+    """Iterations/s of the multi-threaded C restatement of the path
+    (oracle/krotov_oracle_c.c, OpenMP over objectives, own Pade expm) on the
+    full workload: best of 1 thread and all host threads."""
+    os.environ.setdefault('OMP_WAIT_POLICY', 'ACTIVE')
+    os.environ.setdefault('GOMP_SPINCOUNT', '100000000')
+    os.environ.setdefault('OMP_PROC_BIND', 'true')
+    from oracle import krotov_oracle as orc
+    from oracle import krotov_oracle_c as coc
+    low = wl.lowered()
+    ncpu = min(coc.max_threads(), os.cpu_count() or 1)
+    best = None
+    for threads in sorted({1, ncpu}):
+        co = coc.COracle(low, nthreads=threads)
+        pulses = np.array(low['pulses'])
+        phiT = co.forward(pulses)
+        tau = np.einsum('kn,kn->k', co.targets.conj(), phiT)
+        times = []
+        for _ in range(iters):
+            chis = orc.chis_re(list(phiT), list(co.targets), list(tau), None)
+            t0 = time.perf_counter()
+            rec = co.iteration(pulses, chis)
+            times.append(time.perf_counter() - t0)
+            pulses, phiT, tau = rec['optimized_pulses'], \
+                rec['fw_states_T'], rec['tau_vals']
+        val = 1.0 / float(np.min(times))
+        if best is None or val > best[0]:
+            best = (val, threads)
+    return {"value": best[0], "unit": UNIT, "cores": best[1], "kind": "port",
+            "host_cpus": os.cpu_count(),
+            "sample": "%d Krotov iterations of the full workload, C/OpenMP "
+                      "restatement (oracle/krotov_oracle_c.c), best of 1 and "
+                      "%d threads" % (iters, ncpu)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -192,6 +227,10 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
+    try:   # extra information: an optimised multi-threaded C port
+        line["cpu_baseline_c"] = time_c_oracle(wl)
+    except Exception as exc:  # pragma: no cover
+        line["cpu_baseline_c"] = {"unavailable": repr(exc)}
     print(json.dumps(line))
 
 
@@ -375,6 +414,13 @@ def run_ours(args):
                          "objectives at nt=%d, time scaled by %d/%d"
                          % (ks, K, NT + 1, K, ks)}
 
+    cpu_c = None
+    if cpu is not None and WORKLOAD['workload'] == 'C4_tls_ensemble':
+        try:
+            cpu_c = time_c_oracle(wl)
+        except Exception as exc:  # pragma: no cover
+            cpu_c = {"unavailable": repr(exc)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT,
@@ -388,6 +434,7 @@ def run_ours(args):
                                "%d GPUs, GPUShards mode '%s'" % (world, mode))),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
+            "cpu_baseline_c": cpu_c,
             "wall_seconds_timed_region": wall,
         }
         print(json.dumps(line))

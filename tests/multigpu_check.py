@@ -26,6 +26,8 @@ def main():
                              (37, 120, 're', 'gather'),
                              (128, 300, 'sm', 'gather'),
                              (5, 80, 'ss', 'gather')):
+        if K < world:
+            continue
         wl = krotov.workloads.tls_ensemble(K=K, nt=nt)
         chi_fn = getattr(krotov.functionals, 'chis_' + chi)
         taus = []

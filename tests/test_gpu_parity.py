@@ -370,3 +370,62 @@ def test_sharded_two_gpus_matches_single_gpu(krotov):
            os.path.join(root, 'tests', 'multigpu_check.py')]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def _tls_variant(krotov, H0, H1, K=5, nt=150, T=5.0):
+    """K two-level objectives with generator terms H0*(1+0.05k), H1."""
+    from functools import partial
+    guess = lambda t, args: 0.3 * krotov.shapes.flattop(  # noqa: E731
+        t, t_start=0, t_stop=T, t_rise=0.5, func='blackman')
+    S = partial(krotov.shapes.flattop, t_start=0, t_stop=T, t_rise=0.5,
+                func='sinsq')
+    psi0 = np.array([[1], [0]], dtype=complex)
+    psi1 = np.array([[0], [1]], dtype=complex)
+    objs = [krotov.Objective(initial_state=psi0, target=psi1,
+                             H=[H0 * (1 + 0.05 * k), [H1, guess]])
+            for k in range(K)]
+    return objs, {guess: dict(lambda_a=2.0, update_shape=S)}, \
+        np.linspace(0, T, nt)
+
+
+@pytest.mark.parametrize('case', ['real_traceless', 'real_with_trace',
+                                  'complex_drive', 'non_hermitian'])
+def test_two_level_kernel_variants_vs_oracle(krotov, case):
+    """The N=2 kernels have a closed-form path for real generators (with and
+    without trace: the phase e^{it}) and a Taylor path for complex ones;
+    both against the oracle, with time-parallel sweeps on and off."""
+    from oracle import krotov_oracle as orc
+    sx = np.array([[0, 1], [1, 0]], dtype=complex)
+    sy = np.array([[0, -1j], [1j, 0]], dtype=complex)
+    sz = np.array([[1, 0], [0, -1]], dtype=complex)
+    H0, H1 = {
+        'real_traceless': (-0.5 * sz, sx),
+        'real_with_trace': (np.diag([0.3, 1.7]).astype(complex) + 0.1 * sx,
+                            sx + 0.2 * np.diag([1.0, 0.0])),
+        'complex_drive': (-0.5 * sz, sy),
+        'non_hermitian': (-0.5 * sz - 0.05j * np.diag([0.0, 1.0]), sx),
+    }[case]
+    objs, opts, tlist = _tls_variant(krotov, H0, H1)
+    lib = krotov._lib.load()
+    results = []
+    for tp in (1, 0):
+        assert lib.kq_set_option(b"time_parallel", tp) == 0
+        results.append(krotov.optimize_pulses(
+            objs, opts, tlist, propagator=krotov.propagators.expm,
+            chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+            store_all_pulses=True))
+    lib.kq_set_option(b"time_parallel", 1)
+    from krotov_b200.compiler import initialize_controls
+    (controls, _, pulses, mapping, lam, shp) = initialize_controls(
+        objs, opts, tlist)
+    terms = [[(np.asarray(o.H[0]), -1), (np.asarray(o.H[1][0]), 0)]
+             for o in objs]
+    rec = orc.optimize(
+        terms, [o.initial_state.ravel() for o in objs],
+        [o.target.ravel() for o in objs], pulses, shp, lam, tlist,
+        orc.chis_re, iter_stop=2)
+    for res in results:
+        for it in (1, 2):
+            assert rel(res.all_pulses[it],
+                       rec[it]['optimized_pulses']) < PULSE_RTOL, case
+    assert rel(results[0].all_pulses[2], results[1].all_pulses[2]) < 1e-13
