@@ -260,6 +260,9 @@ def run_ours(args):
 
     from krotov_b200.parallelization import (GPUShards, ShardComm,
                                              shard_bounds)
+    if args.picard is not None:
+        krotov._lib.check(krotov._lib.load().kq_set_option(
+            b"picard", args.picard))
     wl = build_workload()
     objectives = wl.objectives(krotov.Objective)
     (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(
@@ -334,6 +337,7 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     if eng.status() != 0:
         raise RuntimeError("exchange failure in sweep kernel")
+    fb_epoch, pic_iters = eng.sweep_diagnostics()
     total_ms = float(np.sum(t_iter))
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=eng.device)
@@ -389,6 +393,8 @@ def run_ours(args):
         "kernel": dominant, "kernel_ms": dom_ms,
         "algorithmic_bytes_per_launch": alg_bytes,
         "fw_sweep_ms": fw_ms, "bw_sweep_ms": bw_ms,
+        "picard_iterations_last_sweep": pic_iters,
+        "sequential_fallback_used": bool(fb_epoch == eng.epoch),
         "ns_per_time_step_fw": fw_ms * 1e6 / NT,
         "ns_per_time_step_bw": bw_ms * 1e6 / NT,
         "note": "sequential chain of nt-1 dependent steps; working set "
@@ -457,6 +463,9 @@ def main():
     ap.add_argument('--shard-mode', default='auto',
                     choices=['auto', 'exchange', 'gather'],
                     help='multi-GPU distribution of the fused sweep')
+    ap.add_argument('--picard', type=int, default=None, choices=[0, 1, 2],
+                    help='time-parallel fused sweep: 0 off (sequential '
+                         'kernel), 1 on (library default)')
     ap.add_argument('--workload', default='C4',
                     help='C4 (contract workload) or C1/C2/C3/C5/C4sat for '
                          'additional measurements')

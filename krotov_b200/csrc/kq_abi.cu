@@ -58,6 +58,10 @@ struct Scratch {
 };
 Scratch g_scratch[kMaxDevices];
 bool g_disable_segments = false;   // kq_set_option("time_parallel", 0)
+int g_picard = 1;                  // kq_set_option("picard", 0|1|2): off / auto / forced
+int g_picard_maxit = 64;           // kq_set_option("picard_maxit", n)
+constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
+constexpr int kPicMaxItCap = 1000;
 
 int get_scratch(int dev, size_t bytes, void** out) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -89,6 +93,11 @@ void build_tables(KqTables& T) {
   }
   T.inv[0] = 0.0;
   for (int j = 1; j <= KQ_TAYLOR_MAXM; ++j) T.inv[j] = 1.0 / (double)j;
+  double f = 1.0;
+  for (int n = 0; n < KQ_INVFACT_N; ++n) {
+    if (n > 1) f *= (double)n;
+    T.invfact[n] = 1.0 / f;
+  }
 }
 
 int device_init(int* dev_out) {
@@ -107,7 +116,8 @@ int device_init(int* dev_out) {
         kq_tables_upload_spec_prop_re, kq_tables_upload_spec_fw2_re,
         kq_tables_upload_spec_fw3_re, kq_tables_upload_spec_fw4_re,
         kq_tables_upload_warp0,    kq_tables_upload_warp8,    kq_tables_upload_warp16,
-        kq_tables_upload_warp32};
+        kq_tables_upload_warp32,   kq_tables_upload_picard2,  kq_tables_upload_picard3,
+        kq_tables_upload_picard4};
     for (auto up : uploads) {
       const int rc = up(&T);
       if (rc) return rc;
@@ -219,6 +229,38 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
   pl.grid = (warps_needed + wpb - 1) / wpb;
   pl.smem = fixed + per_warp * wpb;
   return KQ_OK;
+}
+
+// Geometry of the time-parallel fused sweep (kq_picard.cuh): Q objectives per
+// CTA, TC chunks of W steps per objective.  Returns false if the problem is
+// outside what that family handles (the sequential kernels take over).
+struct PicPlan {
+  int Q, TC, W, grid, block, stride;
+  size_t smem;
+};
+size_t pic_stride(const kq_problem* p) { return (size_t)round_up(p->NT, 64); }
+bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
+  const int K = p->K, N = p->N, NT = p->NT, NN = N * N;
+  if (N < 2 || N > 4 || p->M != 2 || p->L != 1) return false;
+  const int gmax = std::min(sms, kPicMaxBlocks);
+  const int Q = (K + gmax - 1) / gmax;
+  if (Q > 8) return false;
+  int TC = (256 / Q) / 32 * 32;
+  if (TC > round_up(NT, 32)) TC = round_up(NT, 32);
+  const int W = (NT + TC - 1) / TC;
+  const size_t NTP = (size_t)TC * W;
+  const size_t smem = 128 * sizeof(double) + NTP * sizeof(double) + (size_t)Q * NTP * sizeof(double) +
+                      (size_t)Q * NTP * N * sizeof(cplx) + (size_t)Q * 8 * NN * sizeof(cplx) +
+                      (size_t)Q * 2 * NN * sizeof(cplx);
+  if (smem > kSmemBudget) return false;
+  pp.Q = Q;
+  pp.TC = TC;
+  pp.W = W;
+  pp.grid = (K + Q - 1) / Q;
+  pp.block = Q * TC;
+  pp.stride = (int)pic_stride(p);
+  pp.smem = smem;
+  return true;
 }
 
 KqSweepArgs base_args(const kq_problem* p) {
@@ -400,6 +442,16 @@ int kq_set_option(const char* name, int value) {
     g_disable_segments = (value == 0);
     return KQ_OK;
   }
+  if (name && std::strcmp(name, "picard") == 0) {
+    if (value < 0 || value > 2) return fail(KQ_ERR_ARG, "picard must be 0, 1 or 2");
+    g_picard = value;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "picard_maxit") == 0) {
+    if (value < 1 || value > kPicMaxItCap) return fail(KQ_ERR_ARG, "picard_maxit out of range");
+    g_picard_maxit = value;
+    return KQ_OK;
+  }
   return fail(KQ_ERR_ARG, "unknown option '%s'", name ? name : "(null)");
 }
 
@@ -456,8 +508,11 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* st
   return KQ_OK;
 }
 
-size_t kq_workspace_bytes(const kq_problem*) {
-  return kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
+size_t kq_workspace_bytes(const kq_problem* p) {
+  size_t bytes = kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
+  if (p && p->NT > 0)   // slots of the time-parallel fused sweep: part | eps | ga
+    bytes += ((size_t)(kPicMaxBlocks + 1) * pic_stride(p) + kPicMaxBlocks) * sizeof(KqSlot);
+  return bytes;
 }
 
 int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
@@ -553,6 +608,41 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   }
   const int fsel = p->is_super ? 2 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  a.epoch = epoch;
+  // time-parallel fused sweep (kq_picard.cuh), with the sequential kernel
+  // queued behind it as a conditional fall-back
+  PicPlan pp;
+  if (g_picard && pl.family == 0 && pl.spec && a.world == 1 && g_dev[dev].coop &&
+      picard_plan(p, g_dev[dev].sms, pp)) {
+    const uint32_t ce = epoch ? epoch : 1u;
+    KqSweepArgs b = a;
+    b.epoch = ce;
+    b.pic_Q = pp.Q;
+    b.pic_TC = pp.TC;
+    b.pic_W = pp.W;
+    b.pic_stride = pp.stride;
+    b.pic_maxit = std::min(g_picard_maxit, p->NT + 1);
+    b.pic_rtol = 2e-14;
+    b.tag_base = epoch * (uint32_t)(kPicMaxItCap + 2);
+    char* base = static_cast<char*>(workspace) + kStatusBytes +
+                 (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
+    b.pic_part = reinterpret_cast<KqSlot*>(base);
+    b.pic_eps = b.pic_part + (size_t)kPicMaxBlocks * pp.stride;
+    b.pic_ga = b.pic_eps + pp.stride;
+    Plan ppl;
+    std::memset(&ppl, 0, sizeof ppl);
+    ppl.grid = pp.grid;
+    ppl.block = pp.block;
+    ppl.smem = pp.smem;
+    const bool real = p->real_ops && !p->is_super;
+    switch (p->N) {
+      case 2: rc = kq_launch_fwupd_picard2(b, ppl, fsel, second, real, st); break;
+      case 3: rc = kq_launch_fwupd_picard3(b, ppl, fsel, second, real, st); break;
+      default: rc = kq_launch_fwupd_picard4(b, ppl, fsel, second, real, st); break;
+    }
+    if (rc) return rc;
+    a.cond_epoch = ce;   // the sequential kernel below runs only on request
+  }
   if (pl.family == 0) {
     if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
     if (p->real_ops && !p->is_super) {

@@ -27,10 +27,12 @@ typedef double2 cplx;
 #define KQ_RING 4    // depth of the TMA ring for state rows (kq_spec.cuh)
 #define KQ_TAYLOR_BINS 64
 #define KQ_TAYLOR_MAXM 32
+#define KQ_INVFACT_N 40
 
 struct KqTables {
   int m_of_bin[KQ_TAYLOR_BINS];     // Taylor degree for xs in (2^-(i+1), 2^-i]
   double inv[KQ_TAYLOR_MAXM + 1];   // 1/j
+  double invfact[KQ_INVFACT_N];     // 1/n!  (closed-form N = 2 step, kq_picard.cuh)
 };
 
 // Every translation unit has its own copy of the tables, uploaded once per

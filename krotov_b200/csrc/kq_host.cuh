@@ -77,6 +77,9 @@ int kq_tables_upload_warp0(const KqTables* T);
 int kq_tables_upload_warp8(const KqTables* T);
 int kq_tables_upload_warp16(const KqTables* T);
 int kq_tables_upload_warp32(const KqTables* T);
+int kq_tables_upload_picard2(const KqTables* T);
+int kq_tables_upload_picard3(const KqTables* T);
+int kq_tables_upload_picard4(const KqTables* T);
 
 int kq_launch_prop_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
 int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
@@ -97,6 +100,12 @@ int kq_launch_fwupd_spec3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool
                           cudaStream_t st);
 int kq_launch_fwupd_spec4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                           cudaStream_t st);
+int kq_launch_fwupd_picard2(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                            bool real, cudaStream_t st);
+int kq_launch_fwupd_picard3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                            bool real, cudaStream_t st);
+int kq_launch_fwupd_picard4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+                            bool real, cudaStream_t st);
 int kq_launch_warp0(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
                     cudaStream_t st);
 int kq_launch_warp8(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,

@@ -52,6 +52,16 @@ struct KqSweepArgs {
   int seg_len, seg_pass;
   cplx* seg_P;
   cplx* seg_B;
+  // time-parallel fused sweep (kq_picard.cuh): CTA = pic_Q objectives x pic_TC
+  // time chunks of pic_W steps; cross-CTA exchange through tagged slots
+  int pic_Q, pic_TC, pic_W, pic_maxit, pic_stride;
+  double pic_rtol;
+  KqSlot* pic_part;   // [gridDim.x][pic_stride] per-CTA partial sums over its objectives
+  KqSlot* pic_eps;    // [pic_stride] updated pulse
+  KqSlot* pic_ga;     // [gridDim.x] per-CTA share of the g_a integral
+  // sequential kernels launched as the fall-back of the time-parallel sweep run
+  // only if status[1] == cond_epoch (0 = unconditional)
+  uint32_t cond_epoch, epoch;
 };
 
 __device__ __forceinline__ void kq_store(const KqSweepArgs& a, size_t idx, cplx v) {

@@ -659,6 +659,8 @@ __global__ void __launch_bounds__(BTMAX, 1) k_fwupd_spec(const KqSweepArgs a) {
   constexpr bool INREG = (N <= 3);
   const int BT = blockDim.x, tid = threadIdx.x;
   const int K = a.K, NT = a.NT;
+  // fall-back of the time-parallel sweep: run only if it asked for it
+  if (a.cond_epoch && *reinterpret_cast<volatile int*>(a.status + 1) != (int)a.cond_epoch) return;
   FwCtx<N, INREG, SECOND, G> c;
   c.K = K;
   c.lane = tid & 31;

@@ -228,3 +228,12 @@ class SweepEngine:
         """Exchange status word (0 = ok); synchronises."""
         self.d2h_bytes += 4
         return int(self.workspace[:4].view(self.torch.int32).item())
+
+    def sweep_diagnostics(self):
+        """(fallback_epoch, picard_iterations) of the last fused sweep:
+        status words 1 and 2 of the workspace (kq_picard.cuh); synchronises.
+        ``fallback_epoch == self.epoch`` means the time-parallel sweep did not
+        converge and the sequential kernel produced the result."""
+        w = self.workspace[:12].view(self.torch.int32).cpu()
+        self.d2h_bytes += 12
+        return int(w[1]), int(w[2])

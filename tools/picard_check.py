@@ -1,0 +1,84 @@
+"""GPU check of the time-parallel (Picard) fused sweep against the sequential
+kernel: same pulses to rounding, iteration counts, kernel times."""
+import sys, os, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import krotov_b200 as krotov
+from krotov_b200.compiler import compile_problem, initialize_controls
+from krotov_b200.engine import SweepEngine
+
+lib = krotov._lib.load()
+
+
+def rel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+def engine_run(wl, picard, iters=3, second=False):
+    lib.kq_set_option(b"picard", picard)
+    objectives = wl.objectives(krotov.Objective)
+    (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(
+        objectives, wl.pulse_options, wl.tlist)
+    cp = compile_problem(objectives, controls, mapping, wl.tlist)
+    eng = SweepEngine(cp, shp, lam)
+    guess_t = eng.pulses_to_device(guess_pulses)
+    opt_t = guess_t.clone()
+    Phi0 = eng.new_state_store() if second else None
+    Phi1 = eng.new_state_store() if second else None
+    phiT = eng.propagate_forward(guess_t, store=Phi0)
+    tau_t = eng.overlaps(eng.t_targets, phiT)
+    sigma_t = None
+    if second:
+        sigma_t = torch.full((cp.NT,), -0.05, dtype=torch.float64, device=eng.device)
+    out = []
+    stream = torch.cuda.current_stream()
+    for it in range(iters):
+        eng.chi_builtin(wl.chi if wl.chi in ('re', 'ss', 'sm', 'hs') else 're', phiT, tau_t, K_total=cp.K)
+        eng.sweep_backward(guess_t)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        phiT = eng.sweep_forward_update(guess_t, opt_t, phiT=phiT, sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
+        e1.record(stream)
+        tau_t = eng.overlaps(eng.t_targets, phiT)
+        torch.cuda.synchronize()
+        fb, pit = eng.sweep_diagnostics()
+        out.append(dict(pulses=opt_t.cpu().numpy().copy(), phiT=phiT.cpu().numpy().copy(),
+                        ga=eng.g_a.cpu().numpy().copy(), tau=tau_t.cpu().numpy().copy(),
+                        ms=e0.elapsed_time(e1), fallback=(fb == eng.epoch), pit=pit,
+                        Phi1=None if Phi1 is None else Phi1.cpu().numpy().copy(),
+                        status=eng.status()))
+        guess_t, opt_t = opt_t, guess_t
+        if second:
+            Phi0, Phi1 = Phi1, Phi0
+    return out
+
+
+def compare(name, wl, second=False, iters=3):
+    seq = engine_run(wl, 0, iters, second)
+    pic = engine_run(wl, 2, iters, second)
+    for it in range(iters):
+        a, b = pic[it], seq[it]
+        line = ("%-22s it%d  pulses %.2e  phiT %.2e  ga %.2e  tau %.2e  | picard its %3d fallback %d "
+                "status %d | fw ms: picard %.4f  seq %.4f" % (
+                    name, it + 1, rel(a['pulses'], b['pulses']),
+                    np.max(np.abs(a['phiT'] - b['phiT'])), rel(a['ga'], b['ga']),
+                    np.max(np.abs(a['tau'] - b['tau'])), a['pit'], a['fallback'], a['status'],
+                    a['ms'], b['ms']))
+        if second:
+            line += "  Phi1 %.2e" % np.max(np.abs(a['Phi1'] - b['Phi1']))
+        print(line, flush=True)
+
+
+if __name__ == '__main__':
+    W = krotov.workloads
+    compare('C4 K=8 nt=100', W.tls_ensemble(K=8, nt=100))
+    compare('C4 K=128 nt=1000', W.tls_ensemble(K=128, nt=1000), iters=5)
+    compare('C1', W.tls_state_to_state())
+    compare('C2', W.transmon_xgate())
+    compare('C3 first', W.two_qubit_gate())
+    compare('C3 second', W.two_qubit_gate(), second=True)
+    compare('C4 K=300 nt=1000', W.tls_ensemble(K=300, nt=1000))
+    compare('C4 K=128 nt=5000', W.tls_ensemble(K=128, nt=5000))
+    lib.kq_set_option(b"picard", 1)
