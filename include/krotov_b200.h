@@ -105,7 +105,12 @@ enum { KQ_CHI_RE = 0, KQ_CHI_SS = 1, KQ_CHI_SM = 2, KQ_CHI_HS = 3 };
 int kq_version(void);
 const char* kq_last_error(void);
 
-/* Library options (process-wide).  "time_parallel" (default 1): propagation
+/* Library options (process-wide).  "picard" (default 1): the fused sweep of
+ * kq_sweep_forward_update uses the time-parallel fixed-point kernels where the
+ * problem allows (0: always the sequential kernels); "picard_maxit" (default
+ * 64): rounds before the time-parallel sweep gives up; "picard_timing": per
+ * phase cycle counts in workspace status words 16..25.
+ * "time_parallel" (default 1): propagation
  * sweeps under known pulses (kq_propagate_forward, kq_sweep_backward*) are cut
  * into time segments that run concurrently (segment propagators -> boundary
  * states -> states); 0 selects the purely sequential sweep. */
@@ -173,6 +178,34 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses,
                             const kq_c128* Phi0, kq_c128* Phi1, double* g_a,
                             const kq_comm* comm, void* workspace,
                             uint32_t epoch, void* stream);
+
+/* One complete Krotov iteration (optimize.py:393-508) in ONE launch of the
+ * time-parallel kernel family (csrc/kq_picard.cuh): boundary condition
+ * (chi_kind = KQ_CHI_* evaluated from targets/weights/tau_in/phiT_in, or -1 with
+ * the normalised chiT [K][N] + chi_norms [K] of a host chi_constructor),
+ * backward sweep under guess_pulses (X receives all backward states if not
+ * NULL), pulse update + forward sweep (the sequential chain is replaced by a
+ * causal fixed-point iteration that is parallel in time), tau_out[k] =
+ * <target_k|phi_k(T)> (if targets and tau_out are given), phiT_out, g_a.
+ * chi_out / chi_norms_out (may be NULL) receive the normalised boundary states.
+ * sigma/Phi0/Phi1 as in kq_sweep_forward_update.  tau_in/phiT_in must not alias
+ * tau_out/phiT_out.  Returns KQ_ERR_UNSUPPORTED when the problem is outside the
+ * family (N in 2..4, two generator terms, one pulse, single GPU, state stores
+ * fit shared memory): use the four-call sequence then.  If the fixed-point
+ * iteration does not converge ("picard_maxit" option) the outputs are left
+ * untouched, workspace status word 1 is set to `epoch` and word 3 to the first
+ * such epoch; word 2 holds the number of fixed-point rounds of the last
+ * converged call. */
+int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
+                        const kq_c128* targets, const double* weights,
+                        const kq_c128* chiT, const double* chi_norms,
+                        const kq_c128* tau_in, const kq_c128* phiT_in,
+                        const double* guess_pulses, double* opt_pulses,
+                        const kq_c128* phi0, kq_c128* phiT_out,
+                        kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
+                        double* chi_norms_out, const double* sigma,
+                        const kq_c128* Phi0, kq_c128* Phi1, double* g_a,
+                        void* workspace, uint32_t epoch, void* stream);
 
 /* Boundary condition chi_k(T) for the built-in functionals, followed by the
  * normalisation of optimize.py:407-410 (L2 / Frobenius norm):

@@ -59,6 +59,7 @@ struct Scratch {
 Scratch g_scratch[kMaxDevices];
 bool g_disable_segments = false;   // kq_set_option("time_parallel", 0)
 int g_picard = 1;                  // kq_set_option("picard", 0|1|2): off / auto / forced
+int g_picard_timing = 0;
 int g_picard_maxit = 64;           // kq_set_option("picard_maxit", n)
 constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
 constexpr int kPicMaxItCap = 1000;
@@ -235,7 +236,7 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
 // CTA, TC chunks of W steps per objective.  Returns false if the problem is
 // outside what that family handles (the sequential kernels take over).
 struct PicPlan {
-  int Q, TC, W, grid, block, stride;
+  int Q, TC, W, lw, Wc, grid, block, stride;
   size_t smem;
 };
 size_t pic_stride(const kq_problem* p) { return (size_t)round_up(p->NT, 64); }
@@ -245,22 +246,64 @@ bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   const int gmax = std::min(sms, kPicMaxBlocks);
   const int Q = (K + gmax - 1) / gmax;
   if (Q > 8) return false;
-  int TC = (256 / Q) / 32 * 32;
-  if (TC > round_up(NT, 32)) TC = round_up(NT, 32);
-  const int W = (NT + TC - 1) / TC;
+  const int tcmax = (256 / Q) / 32 * 32;
+  // chunk length: the smallest power of two that covers the grid with <= tcmax
+  // chunks; then as few chunks as needed
+  int lw = 0;
+  while (((NT + (1 << lw) - 1) >> lw) > tcmax) ++lw;
+  const int W = 1 << lw;
+  const int TC = round_up((NT + W - 1) / W, 32);
   const size_t NTP = (size_t)TC * W;
-  const size_t smem = 128 * sizeof(double) + NTP * sizeof(double) + (size_t)Q * NTP * sizeof(double) +
-                      (size_t)Q * NTP * N * sizeof(cplx) + (size_t)Q * 8 * NN * sizeof(cplx) +
-                      (size_t)Q * 2 * NN * sizeof(cplx);
+  const int grid = (K + Q - 1) / Q;
+  const int Wc = round_up((NT + grid - 1) / grid, 2);
+  const size_t smem = 256 * sizeof(double) + NTP * sizeof(double) + (size_t)Q * NTP * sizeof(double) +
+                      (size_t)3 * Wc * sizeof(double) + (size_t)Q * NTP * N * sizeof(cplx) +
+                      (size_t)Q * 8 * NN * sizeof(cplx) + (size_t)Q * 4 * NN * sizeof(cplx);
   if (smem > kSmemBudget) return false;
   pp.Q = Q;
   pp.TC = TC;
   pp.W = W;
-  pp.grid = (K + Q - 1) / Q;
+  pp.lw = lw;
+  pp.Wc = Wc;
+  pp.grid = grid;
   pp.block = Q * TC;
   pp.stride = (int)pic_stride(p);
   pp.smem = smem;
   return true;
+}
+
+// Fill the time-parallel family's launch arguments and launch it.
+int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* workspace,
+                  uint32_t epoch, bool second, cudaStream_t st) {
+  b.epoch = epoch ? epoch : 1u;
+  b.pic_Q = pp.Q;
+  b.pic_TC = pp.TC;
+  b.pic_W = pp.W;
+  b.pic_lw = pp.lw;
+  b.pic_Wc = pp.Wc;
+  b.pic_stride = pp.stride;
+  b.pic_maxit = std::min(g_picard_maxit, p->NT + 1);
+  b.pic_rtol = 2e-14;
+  b.pic_timing = g_picard_timing;
+  b.tag_base = epoch * (uint32_t)(kPicMaxItCap + 2);
+  b.status = reinterpret_cast<int*>(workspace);
+  char* base = static_cast<char*>(workspace) + kStatusBytes +
+               (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
+  b.pic_part = reinterpret_cast<KqSlot*>(base);
+  b.pic_eps = b.pic_part + (size_t)kPicMaxBlocks * pp.stride;
+  b.pic_ga = b.pic_eps + pp.stride;
+  Plan ppl;
+  std::memset(&ppl, 0, sizeof ppl);
+  ppl.grid = pp.grid;
+  ppl.block = pp.block;
+  ppl.smem = pp.smem;
+  const int fsel = p->is_super ? 2 : 0;
+  const bool real = p->real_ops && !p->is_super;
+  switch (p->N) {
+    case 2: return kq_launch_picard2(b, ppl, fsel, second, real, st);
+    case 3: return kq_launch_picard3(b, ppl, fsel, second, real, st);
+    default: return kq_launch_picard4(b, ppl, fsel, second, real, st);
+  }
 }
 
 KqSweepArgs base_args(const kq_problem* p) {
@@ -435,7 +478,7 @@ __global__ void k_chi_boundary(int K, int N, int kind, int K_total, const cplx* 
 
 extern "C" {
 
-int kq_version(void) { return 102; }
+int kq_version(void) { return 103; }
 
 int kq_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "time_parallel") == 0) {
@@ -445,6 +488,10 @@ int kq_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "picard") == 0) {
     if (value < 0 || value > 2) return fail(KQ_ERR_ARG, "picard must be 0, 1 or 2");
     g_picard = value;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "picard_timing") == 0) {
+    g_picard_timing = value ? 1 : 0;
     return KQ_OK;
   }
   if (name && std::strcmp(name, "picard_maxit") == 0) {
@@ -614,34 +661,11 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   PicPlan pp;
   if (g_picard && pl.family == 0 && pl.spec && a.world == 1 && g_dev[dev].coop &&
       picard_plan(p, g_dev[dev].sms, pp)) {
-    const uint32_t ce = epoch ? epoch : 1u;
     KqSweepArgs b = a;
-    b.epoch = ce;
-    b.pic_Q = pp.Q;
-    b.pic_TC = pp.TC;
-    b.pic_W = pp.W;
-    b.pic_stride = pp.stride;
-    b.pic_maxit = std::min(g_picard_maxit, p->NT + 1);
-    b.pic_rtol = 2e-14;
-    b.tag_base = epoch * (uint32_t)(kPicMaxItCap + 2);
-    char* base = static_cast<char*>(workspace) + kStatusBytes +
-                 (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
-    b.pic_part = reinterpret_cast<KqSlot*>(base);
-    b.pic_eps = b.pic_part + (size_t)kPicMaxBlocks * pp.stride;
-    b.pic_ga = b.pic_eps + pp.stride;
-    Plan ppl;
-    std::memset(&ppl, 0, sizeof ppl);
-    ppl.grid = pp.grid;
-    ppl.block = pp.block;
-    ppl.smem = pp.smem;
-    const bool real = p->real_ops && !p->is_super;
-    switch (p->N) {
-      case 2: rc = kq_launch_fwupd_picard2(b, ppl, fsel, second, real, st); break;
-      case 3: rc = kq_launch_fwupd_picard3(b, ppl, fsel, second, real, st); break;
-      default: rc = kq_launch_fwupd_picard4(b, ppl, fsel, second, real, st); break;
-    }
+    b.pic_bw = 0;
+    rc = launch_picard(p, b, pp, workspace, epoch, second, st);
     if (rc) return rc;
-    a.cond_epoch = ce;   // the sequential kernel below runs only on request
+    a.cond_epoch = epoch ? epoch : 1u;   // the sequential kernel below runs only on request
   }
   if (pl.family == 0) {
     if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
@@ -659,6 +683,62 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
     }
   }
   return launch_warp(a, pl, fsel, second, true, st);
+}
+
+int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
+                        const kq_c128* targets, const double* weights, const kq_c128* chiT,
+                        const double* chi_norms, const kq_c128* tau_in, const kq_c128* phiT_in,
+                        const double* guess_pulses, double* opt_pulses, const kq_c128* phi0,
+                        kq_c128* phiT_out, kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
+                        double* chi_norms_out, const double* sigma, const kq_c128* Phi0,
+                        kq_c128* Phi1, double* g_a, void* workspace, uint32_t epoch,
+                        void* stream) {
+  int rc = check_problem(p);
+  if (rc) return rc;
+  if (!guess_pulses || !opt_pulses || !phi0 || !g_a || !workspace)
+    return fail(KQ_ERR_ARG, "NULL argument to kq_krotov_iteration");
+  if (!p->mu || !p->shape || !p->lambda_a) return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
+  if (chi_kind < -1 || chi_kind > KQ_CHI_HS) return fail(KQ_ERR_ARG, "unknown chi kind %d", chi_kind);
+  if (chi_kind < 0 && (!chiT || !chi_norms)) return fail(KQ_ERR_ARG, "chiT/chi_norms are NULL");
+  if (chi_kind >= 0 && !targets) return fail(KQ_ERR_ARG, "built-in chi needs targets");
+  if ((chi_kind == KQ_CHI_SS || chi_kind == KQ_CHI_SM) && !tau_in)
+    return fail(KQ_ERR_ARG, "chis_ss/chis_sm need tau_in");
+  if (chi_kind == KQ_CHI_HS && !phiT_in) return fail(KQ_ERR_ARG, "chis_hs needs phiT_in");
+  if (chi_kind >= 0 && K_total != p->K)
+    return fail(KQ_ERR_UNSUPPORTED, "kq_krotov_iteration is single-GPU (K_total must equal K)");
+  const bool second = sigma != nullptr;
+  if (second && !Phi0) return fail(KQ_ERR_ARG, "second order needs Phi0");
+  int dev;
+  rc = device_init(&dev);
+  if (rc) return rc;
+  PicPlan pp;
+  if (!g_picard || !g_dev[dev].coop || !picard_plan(p, g_dev[dev].sms, pp))
+    return fail(KQ_ERR_UNSUPPORTED, "problem is outside the time-parallel kernel family");
+  KqSweepArgs a = base_args(p);
+  a.ops = reinterpret_cast<const cplx*>(p->ops);
+  a.ops_adj = reinterpret_cast<const cplx*>(p->ops_adj);
+  a.pulses = guess_pulses;
+  a.opt_pulses = opt_pulses;
+  a.state0 = reinterpret_cast<const cplx*>(phi0);
+  a.stateT = reinterpret_cast<cplx*>(phiT_out);
+  a.store = second ? reinterpret_cast<cplx*>(Phi1) : nullptr;
+  a.chi_norms = chi_norms;
+  a.sigma = sigma;
+  a.Phi0 = reinterpret_cast<const cplx*>(Phi0);
+  a.g_a = g_a;
+  a.pic_bw = 1;
+  a.chi_kind = chi_kind;
+  a.K_total = K_total;
+  a.chiT = reinterpret_cast<const cplx*>(chiT);
+  a.targets = reinterpret_cast<const cplx*>(targets);
+  a.weights = weights;
+  a.tau_in = reinterpret_cast<const cplx*>(tau_in);
+  a.tau_out = reinterpret_cast<cplx*>(tau_out);
+  a.phiT_in = reinterpret_cast<const cplx*>(phiT_in);
+  a.Xout = reinterpret_cast<cplx*>(X);
+  a.chi_out = reinterpret_cast<cplx*>(chi_out);
+  a.chi_norms_out = chi_norms_out;
+  return launch_picard(p, a, pp, workspace, epoch, second, static_cast<cudaStream_t>(stream));
 }
 
 int kq_chi_boundary(const kq_problem* p, int kind, int32_t K_total, const kq_c128* phiT,

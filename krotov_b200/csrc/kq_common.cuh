@@ -131,6 +131,34 @@ __device__ __forceinline__ bool slot_try_load(const KqSlot* p, uint32_t tag, dou
   }
   return false;
 }
+// Wait for NB slots at once: all loads of a polling round are in flight together
+// (one L2 round trip per round instead of one per slot).  Inactive entries must
+// still point to readable memory.
+template <int NB>
+__device__ __forceinline__ void slot_wait_batch(const KqSlot* const (&p)[NB],
+                                                const bool (&act)[NB], uint32_t tag,
+                                                double (&v)[NB], bool& failed) {
+#pragma unroll
+  for (int u = 0; u < NB; ++u) v[u] = 0.0;
+  if (failed) return;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    uint32_t lo[NB], t0[NB], hi[NB], t1[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u)
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u])
+                   : "l"(p[u]));
+    bool all = true;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const bool ok = !act[u] || (t0[u] == tag && t1[u] == tag);
+      all = all && ok;
+      if (act[u]) v[u] = __hiloint2double((int)hi[u], (int)lo[u]);
+    }
+    if (all) return;
+  }
+  failed = true;
+}
 // Spin until the slot carries `tag`; gives up (sets *failed) after ~2^24 polls
 // so that a lost peer cannot hang the device.
 __device__ __forceinline__ double slot_wait(const KqSlot* p, uint32_t tag, bool& failed) {

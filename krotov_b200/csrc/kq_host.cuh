@@ -100,11 +100,11 @@ int kq_launch_fwupd_spec3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool
                           cudaStream_t st);
 int kq_launch_fwupd_spec4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                           cudaStream_t st);
-int kq_launch_fwupd_picard2(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+int kq_launch_picard2(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                             bool real, cudaStream_t st);
-int kq_launch_fwupd_picard3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+int kq_launch_picard3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                             bool real, cudaStream_t st);
-int kq_launch_fwupd_picard4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
+int kq_launch_picard4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                             bool real, cudaStream_t st);
 int kq_launch_warp0(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
                     cudaStream_t st);

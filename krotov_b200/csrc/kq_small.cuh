@@ -62,6 +62,22 @@ struct KqSweepArgs {
   // sequential kernels launched as the fall-back of the time-parallel sweep run
   // only if status[1] == cond_epoch (0 = unconditional)
   uint32_t cond_epoch, epoch;
+  int pic_timing;     // 1: CTA 0 writes per-phase cycle counts to status[16..]
+  // fused Krotov iteration (k_krotov_picard): chi boundary and backward sweep
+  // inside the kernel
+  int pic_lw, pic_Wc;        // log2(pic_W); time steps reduced per CTA (even)
+  int pic_bw;                // 1: backward sweep in the kernel (chi from chi_kind / chiT), 0: chi from X
+  int chi_kind, K_total;     // KQ_CHI_* or -1 (normalised chiT + chi_norms given)
+  const cplx* ops_adj;
+  const cplx* chiT;
+  const cplx* targets;
+  const double* weights;
+  const cplx* tau_in;
+  cplx* tau_out;
+  const cplx* phiT_in;
+  cplx* Xout;                // [NT+1][K][N] or null
+  cplx* chi_out;             // [K][N] or null
+  double* chi_norms_out;     // [K] or null
 };
 
 __device__ __forceinline__ void kq_store(const KqSweepArgs& a, size_t idx, cplx v) {

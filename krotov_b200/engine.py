@@ -183,6 +183,38 @@ class SweepEngine:
         self.launches += 1
         return phiT
 
+    def krotov_iteration(self, chi_kind, guess_t, opt_t, phiT_in, tau_in,
+                         phiT_out, tau_out, store_X=False, sigma_t=None,
+                         Phi0=None, Phi1=None):
+        """One whole Krotov iteration (optimize.py:393-508) in one launch of
+        the time-parallel kernel family: chi boundary (`chi_kind` 're', 'ss',
+        'sm', 'hs', or None for the states already in :attr:`chi` /
+        :attr:`chi_norms`), backward sweep, update + forward sweep, tau.
+        Raises :class:`KqError` (KQ_ERR_UNSUPPORTED) if the problem is outside
+        that family."""
+        self.epoch += 1
+        kind = -1 if chi_kind is None else CHI_KINDS[chi_kind]
+        check(self.lib.kq_krotov_iteration(
+            self._p, kind, self.cp.K, _ptr(self.t_targets),
+            _ptr(self.t_weights),
+            _ptr(self.chi if kind < 0 else None),
+            _ptr(self.chi_norms if kind < 0 else None),
+            _ptr(tau_in), _ptr(phiT_in), _ptr(guess_t), _ptr(opt_t),
+            _ptr(self.t_psi0), _ptr(phiT_out), _ptr(tau_out),
+            _ptr(self.X if store_X else None),
+            _ptr(None if kind < 0 else self.chi),
+            _ptr(None if kind < 0 else self.chi_norms),
+            _ptr(sigma_t), _ptr(Phi0), _ptr(Phi1), _ptr(self.g_a),
+            _ptr(self.workspace), ctypes.c_uint32(self.epoch & 0xFFFFFFFF),
+            self._stream()))
+        self.launches += 1
+
+    def fused_supported(self):
+        """True if :meth:`krotov_iteration` handles this problem."""
+        cp = self.cp
+        return (self.comm is None and self.gather is None and cp.M == 2
+                and cp.L == 1 and 2 <= cp.N <= 4)
+
     def overlaps(self, a, b, out=None):
         """tau_k = <a_k|b_k> (optimize.py:316-322, 503-508)."""
         if out is None:
@@ -234,6 +266,12 @@ class SweepEngine:
         status words 1 and 2 of the workspace (kq_picard.cuh); synchronises.
         ``fallback_epoch == self.epoch`` means the time-parallel sweep did not
         converge and the sequential kernel produced the result."""
-        w = self.workspace[:12].view(self.torch.int32).cpu()
-        self.d2h_bytes += 12
+        w = self.workspace[:16].view(self.torch.int32).cpu()
+        self.d2h_bytes += 16
         return int(w[1]), int(w[2])
+
+    def first_failed_epoch(self):
+        """Epoch of the first fused iteration that did not converge (0 =
+        none); synchronises."""
+        self.d2h_bytes += 4
+        return int(self.workspace[12:16].view(self.torch.int32).item())

@@ -16,7 +16,7 @@ def rel(a, b):
     return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
 
 
-def engine_run(wl, picard, iters=3, second=False):
+def engine_run(wl, picard, iters=3, second=False, fused=False):
     lib.kq_set_option(b"picard", picard)
     objectives = wl.objectives(krotov.Objective)
     (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(
@@ -34,20 +34,32 @@ def engine_run(wl, picard, iters=3, second=False):
         sigma_t = torch.full((cp.NT,), -0.05, dtype=torch.float64, device=eng.device)
     out = []
     stream = torch.cuda.current_stream()
+    chi = wl.chi if wl.chi in ('re', 'ss', 'sm', 'hs') else 're'
+    phiT2, tau2 = eng.new_states(), torch.empty_like(tau_t)
     for it in range(iters):
-        eng.chi_builtin(wl.chi if wl.chi in ('re', 'ss', 'sm', 'hs') else 're', phiT, tau_t, K_total=cp.K)
-        eng.sweep_backward(guess_t)
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        phiT = eng.sweep_forward_update(guess_t, opt_t, phiT=phiT, sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
-        e1.record(stream)
-        tau_t = eng.overlaps(eng.t_targets, phiT)
+        if fused:
+            e0.record(stream)
+            eng.krotov_iteration(chi, guess_t, opt_t, phiT, tau_t, phiT2, tau2, store_X=True,
+                                 sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
+            e1.record(stream)
+            phiT, phiT2 = phiT2, phiT
+            tau_t, tau2 = tau2, tau_t
+        else:
+            eng.chi_builtin(chi, phiT, tau_t, K_total=cp.K)
+            eng.sweep_backward(guess_t)
+            e0.record(stream)
+            phiT = eng.sweep_forward_update(guess_t, opt_t, phiT=phiT, sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
+            e1.record(stream)
+            tau_t = eng.overlaps(eng.t_targets, phiT)
         torch.cuda.synchronize()
         fb, pit = eng.sweep_diagnostics()
+        cyc = eng.workspace[64:104].view(torch.int32).cpu().numpy().copy()
         out.append(dict(pulses=opt_t.cpu().numpy().copy(), phiT=phiT.cpu().numpy().copy(),
                         ga=eng.g_a.cpu().numpy().copy(), tau=tau_t.cpu().numpy().copy(),
-                        ms=e0.elapsed_time(e1), fallback=(fb == eng.epoch), pit=pit,
+                        ms=e0.elapsed_time(e1), cycles=cyc, fallback=(fb == eng.epoch), pit=pit,
                         Phi1=None if Phi1 is None else Phi1.cpu().numpy().copy(),
+                        X=eng.X.cpu().numpy().copy(), chi=eng.chi.cpu().numpy().copy(),
                         status=eng.status()))
         guess_t, opt_t = opt_t, guess_t
         if second:
@@ -58,21 +70,45 @@ def engine_run(wl, picard, iters=3, second=False):
 def compare(name, wl, second=False, iters=3):
     seq = engine_run(wl, 0, iters, second)
     pic = engine_run(wl, 2, iters, second)
-    for it in range(iters):
-        a, b = pic[it], seq[it]
-        line = ("%-22s it%d  pulses %.2e  phiT %.2e  ga %.2e  tau %.2e  | picard its %3d fallback %d "
-                "status %d | fw ms: picard %.4f  seq %.4f" % (
-                    name, it + 1, rel(a['pulses'], b['pulses']),
-                    np.max(np.abs(a['phiT'] - b['phiT'])), rel(a['ga'], b['ga']),
-                    np.max(np.abs(a['tau'] - b['tau'])), a['pit'], a['fallback'], a['status'],
-                    a['ms'], b['ms']))
-        if second:
-            line += "  Phi1 %.2e" % np.max(np.abs(a['Phi1'] - b['Phi1']))
-        print(line, flush=True)
+    try:
+        fus = engine_run(wl, 2, iters, second, fused=True)
+    except Exception as exc:
+        print(name, 'fused path unavailable:', exc)
+        fus = None
+    for label, run in (('picard', pic), ('fused ', fus)):
+        if run is None:
+            continue
+        for it in range(iters):
+            a, b = run[it], seq[it]
+            line = ("%-18s %s it%d  pulses %.2e  phiT %.2e  ga %.2e  tau %.2e X %.2e chi %.2e | its %3d fb %d "
+                    "st %d | ms: %.4f  seq-fw %.4f" % (
+                        name, label, it + 1, rel(a['pulses'], b['pulses']),
+                        np.max(np.abs(a['phiT'] - b['phiT'])), rel(a['ga'], b['ga']),
+                        np.max(np.abs(a['tau'] - b['tau'])), np.max(np.abs(a['X'] - b['X'])),
+                        np.max(np.abs(a['chi'] - b['chi'])), a['pit'], a['fallback'], a['status'],
+                        a['ms'], b['ms']))
+            if second:
+                line += "  Phi1 %.2e" % np.max(np.abs(a['Phi1'] - b['Phi1']))
+            print(line, flush=True)
+
+
+def timing(name, wl, iters=3, fused=True):
+    lib.kq_set_option(b"picard_timing", 1)
+    out = engine_run(wl, 1, iters, fused=fused)
+    lib.kq_set_option(b"picard_timing", 0)
+    return out
 
 
 if __name__ == '__main__':
     W = krotov.workloads
+    if len(sys.argv) > 1 and sys.argv[1] == 'timing':
+        for r in timing('C4', W.tls_ensemble(K=128, nt=1000), 4):
+            cyc = r['cycles']
+            its = max(r['pit'], 1)
+            names = ['prologue', 'bw', 'passA+scan', 'passB', 'stage1', 'stage2', 'stage3', 'blockmax', 'outputs', 'final']
+            print('kernel %.1f us, %d its; cycles (per iter for 2..7): ' % (r['ms'] * 1e3, its) + ', '.join(
+                '%s %d' % (n, c // (its if 2 <= i <= 7 else 1)) for i, (n, c) in enumerate(zip(names, cyc))))
+        sys.exit(0)
     compare('C4 K=8 nt=100', W.tls_ensemble(K=8, nt=100))
     compare('C4 K=128 nt=1000', W.tls_ensemble(K=128, nt=1000), iters=5)
     compare('C1', W.tls_state_to_state())
