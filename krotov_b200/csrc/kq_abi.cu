@@ -256,9 +256,9 @@ bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   const size_t NTP = (size_t)TC * W;
   const int grid = (K + Q - 1) / Q;
   const int Wc = round_up((NT + grid - 1) / grid, 2);
-  const size_t smem = 256 * sizeof(double) + NTP * sizeof(double) + (size_t)Q * NTP * sizeof(double) +
+  const size_t smem = 256 * sizeof(double) + 2 * NTP * sizeof(double) + (size_t)Q * NTP * sizeof(double) +
                       (size_t)3 * Wc * sizeof(double) + (size_t)Q * NTP * N * sizeof(cplx) +
-                      (size_t)Q * 8 * NN * sizeof(cplx) + (size_t)Q * 4 * NN * sizeof(cplx);
+                      (size_t)2 * Q * 8 * NN * sizeof(cplx) + (size_t)Q * 4 * NN * sizeof(cplx);
   if (smem > kSmemBudget) return false;
   pp.Q = Q;
   pp.TC = TC;
@@ -291,7 +291,7 @@ int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* w
                (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
   b.pic_part = reinterpret_cast<KqSlot*>(base);
   b.pic_eps = b.pic_part + (size_t)kPicMaxBlocks * pp.stride;
-  b.pic_ga = b.pic_eps + pp.stride;
+  b.pic_ga = b.pic_eps + (size_t)kPicMaxBlocks * pp.stride;
   Plan ppl;
   std::memset(&ppl, 0, sizeof ppl);
   ppl.grid = pp.grid;
@@ -558,7 +558,7 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* st
 size_t kq_workspace_bytes(const kq_problem* p) {
   size_t bytes = kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
   if (p && p->NT > 0)   // slots of the time-parallel fused sweep: part | eps | ga
-    bytes += ((size_t)(kPicMaxBlocks + 1) * pic_stride(p) + kPicMaxBlocks) * sizeof(KqSlot);
+    bytes += ((size_t)2 * kPicMaxBlocks * pic_stride(p) + kPicMaxBlocks) * sizeof(KqSlot);
   return bytes;
 }
 

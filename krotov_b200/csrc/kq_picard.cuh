@@ -1,8 +1,9 @@
-// Time-parallel fused pulse update + forward sweep (optimize.py:449-500 of the
-// reference) for the specialised problem shape (N <= 4, one drift + one control
-// term, one pulse).
+// Time-parallel Krotov iteration (optimize.py:393-508 of the reference) for the
+// specialised problem shape (N <= 4, one drift + one control term, one pulse):
+// chi boundary -> backward sweep -> pulse update + forward sweep -> tau in ONE
+// kernel launch, with no sequential pass over the time grid.
 //
-// The sequential sweep is a chain of nt-1 dependent steps:
+// The reference's update sweep is a chain of nt-1 dependent steps,
 //     eps[n] = guess[n] + (S[n]/lambda) Im sum_k <chi_k[n]| mu |phi_k[n]>,
 //     phi_k[n+1] = U_k(eps[n]) phi_k[n].
 // Because phi_k[n] depends on eps[0..n-1] only, the updated pulse is the unique
@@ -10,37 +11,46 @@
 // propagates all objectives under eps and evaluates the overlaps at every time
 // step.  One evaluation of F is fully parallel in time; the Picard iteration
 // eps_{j+1} = guess + (S/lambda) F(eps_j) converges like (C T)^j / j!  (Volterra
-// structure; C4: 9 iterations to 1e-15) and is exact after at most nt-1
+// structure; C4: 9-12 iterations to 1e-15) and is exact after at most nt-1
 // iterations whatever the coupling.  Iterating to |eps_{j+1} - eps_j| <= rtol
 // max|eps| reproduces the sequential result to rounding.
 //
-// Mapping: CTA = Q objectives x TC time chunks of W steps (thread = one chunk of
-// one objective).  One evaluation of F:
-//   pass A  every thread propagates the N basis vectors through its chunk
-//           (chunk propagator M_t, registers);
-//   scan    Kogge-Stone inclusive scan of M_t over the lanes (N x N complex
-//           products, SHFL), warp totals through shared memory -> state at the
-//           start of every chunk;
-//   pass B  every thread propagates that state through its chunk and evaluates
-//           Im <mu^dag chi ||chi|| | phi> at each step (mu^dag chi prepared once
-//           per launch in shared memory);
-//   sum     over the objectives: inside the CTA in shared memory, across CTAs
-//           through flag-tagged 16-byte slots in global memory (kq_common.cuh):
-//           every CTA publishes its partial sums for all time steps, CTA c
-//           reduces time slice c in a fixed order and publishes the updated
-//           pulse values, every CTA reads the whole updated pulse.  Two
-//           one-way L2 hops per iteration, no grid barrier, deterministic.
-// A final evaluation under the converged pulse stores phi(T) (and all forward
-// states for second order).  If the iteration does not converge in pic_maxit
-// rounds the kernel requests the sequential kernel through status[1].
+// Mapping: CTA = Q objectives x TC time chunks of W = 2^lw steps (thread = one
+// chunk of one objective).  A propagation over the whole grid under a known
+// pulse (backward sweep; one evaluation of F) is
+//   pass A  every thread multiplies the step propagators of its chunk (the N
+//           basis vectors go through the chunk: chunk propagator M_t, registers);
+//   scan    Kogge-Stone scan of M_t over the lanes (N x N complex products,
+//           SHFL), warp totals through shared memory -> state at the chunk
+//           boundary of every thread;
+//   pass B  every thread propagates that state through its chunk and, in the
+//           update sweep, evaluates Im <mu^dag chi ||chi|| | phi> at each step
+//           (mu^dag chi comes from the backward sweep and stays in shared
+//           memory; backward states go to HBM only when the caller wants them).
+// The sum over the objectives runs inside the CTA in shared memory and across
+// CTAs through flag-tagged 16-byte slots in global memory (kq_common.cuh):
+// every CTA publishes its partial sums for all time steps, CTA c reduces time
+// slice c in a fixed order and publishes the updated pulse values, every CTA
+// reads the whole updated pulse.  Two one-way L2 hops per Picard iteration, no
+// grid barrier, deterministic.
+// If the iteration does not converge in pic_maxit rounds the kernel leaves its
+// outputs untouched and reports through status[1] / status[3]; the caller then
+// uses the sequential kernels (kq_spec.cuh).
 #pragma once
 #include "kq_spec.cuh"
 
 #define KQ_PIC_WPO 8      // warps per objective at most (TC <= 256)
 #define KQ_PIC_BT 256     // threads per CTA the kernels are compiled for
+#define KQ_PIC_XCAP 64.0  // largest scaled step norm dt*||A|| the family accepts
+#define KQ_PIC_NTICK 16
+constexpr int kPicBlocksMax = 148;   // CTAs at most (one per SM)
 
 __device__ __forceinline__ cplx shfl_up_c(cplx v, int d) {
   return make_double2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ cplx shfl_down_c(cplx v, int d) {
+  return make_double2(__shfl_down_sync(0xffffffffu, v.x, d),
+                      __shfl_down_sync(0xffffffffu, v.y, d));
 }
 
 // C = A * B (column-major N x N)
@@ -81,121 +91,155 @@ __device__ __forceinline__ void mat_vec(const cplx* A, const cplx (&x)[N], cplx 
 }
 
 // ---- one propagation step, prepared once and applied to several vectors ------
+// h = dt/s, heps = h*eps; (s, m) = CTA-uniform scaling count and Taylor degree.
 template <int N, bool INREG, typename G>
 struct StepOp {
   G At[N * N];
-  int s, m;
-  __device__ __forceinline__ void prepare(const SpecTerms<N, INREG, G>& T, double dt, double eps,
-                                          int s_, int m_) {
-    s = s_;
-    m = m_;
-    const double h = (s_ == 1) ? dt : dt / (double)s_;
-    T.assemble(h, h * eps, At);
-  }
-  __device__ __forceinline__ void apply(cplx (&y)[N]) const {
-    cplx out[N];
-    expmv_generic<N, G>(At, y, out, s, m);
+  template <int WB>
+  static __device__ __forceinline__ void prepare_batch(const SpecTerms<N, INREG, G>& T,
+                                                       const double (&h)[WB],
+                                                       const double (&heps)[WB], int m,
+                                                       StepOp (&ops)[WB]) {
+    (void)m;
 #pragma unroll
-    for (int i = 0; i < N; ++i) y[i] = out[i];
+    for (int w = 0; w < WB; ++w) T.assemble(h[w], heps[w], ops[w].At);
+  }
+  // NV vectors stored one after the other in Y
+  template <int NV>
+  __device__ __forceinline__ void apply(cplx (&Y)[NV * N], int s, int m) const {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      cplx in[N], out[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) in[i] = Y[v * N + i];
+      expmv_generic<N, G>(At, in, out, s, m);
+#pragma unroll
+      for (int i = 0; i < N; ++i) Y[v * N + i] = out[i];
+    }
   }
 };
 
-template <int P>
-__device__ __forceinline__ void pic_poly(double z, double& C, double& S) {
-  C = kq_inv_fact(2 * (P - 1));
-  S = kq_inv_fact(2 * (P - 1) + 1);
-#pragma unroll
-  for (int j = P - 2; j >= 0; --j) {
-    C = fma(-z, C, kq_inv_fact(2 * j));
-    S = fma(-z, S, kq_inv_fact(2 * j + 1));
-  }
+// sin and cos of the trace phase; out of line so that the (large) argument
+// reduction code exists once per kernel.
+static __device__ __noinline__ double2 pic_phase(double t) {
+  double st, ct;
+  sincos(t, &st, &ct);
+  return make_double2(st, ct);
 }
 
-// N = 2 with a real generator: closed form (see expmv2_real in kq_spec.cuh);
-// the polynomials C(z), S(z) are evaluated once per step and shared by all
-// vectors the step is applied to.
+// N = 2 with a real generator: closed form (see expmv2_real in kq_spec.cuh),
+// exp(iR) = e^{it} [C(z) I + i S(z) R'],  t = tr R / 2, R' = R - t I, z = -det R';
+// kept as C, S*dl, S*b, S*c and the phase, shared by all vectors the step is
+// applied to.  The polynomials C(z), S(z) of all steps of a batch are evaluated
+// in one Horner loop (independent chains fill the FP64 pipe, no branches).
 template <bool INREG>
 struct StepOp<2, INREG, double> {
-  double C, S, dl, b, c, st, ct;
-  int s;
-  bool phase;
-  __device__ __forceinline__ void prepare(const SpecTerms<2, INREG, double>& T, double dt,
-                                          double eps, int s_, int m_) {
-    s = s_;
-    const double h = (s_ == 1) ? dt : dt / (double)s_;
-    double R[4];
-    T.assemble(h, h * eps, R);
-    const double a = R[0], d = R[3];
-    c = R[1];
-    b = R[2];
-    const double t = 0.5 * (a + d);
-    dl = 0.5 * (a - d);
-    const double z = fma(dl, dl, b * c);
-    const int P = max(3, (m_ + 4) >> 1);   // 2P >= m + 3
-    switch (P) {
-      case 3: pic_poly<3>(z, C, S); break;
-      case 4: pic_poly<4>(z, C, S); break;
-      case 5: pic_poly<5>(z, C, S); break;
-      case 6: pic_poly<6>(z, C, S); break;
-      default: {
-        C = c_kq_tables.invfact[2 * (P - 1)];
-        S = c_kq_tables.invfact[2 * (P - 1) + 1];
-        for (int j = P - 2; j >= 0; --j) {
-          C = fma(-z, C, c_kq_tables.invfact[2 * j]);
-          S = fma(-z, S, c_kq_tables.invfact[2 * j + 1]);
-        }
+  double C, Sd, Sb, Sc, st, ct;
+  template <int WB>
+  static __device__ __forceinline__ void prepare_batch(const SpecTerms<2, INREG, double>& T,
+                                                       const double (&h)[WB],
+                                                       const double (&heps)[WB], int m,
+                                                       StepOp (&ops)[WB]) {
+    double z[WB], dl[WB], b[WB], c[WB], t[WB], Cv[WB], Sv[WB];
+#pragma unroll
+    for (int w = 0; w < WB; ++w) {
+      double R[4];
+      T.assemble(h[w], heps[w], R);
+      t[w] = 0.5 * (R[0] + R[3]);
+      dl[w] = 0.5 * (R[0] - R[3]);
+      c[w] = R[1];
+      b[w] = R[2];
+      z[w] = fma(dl[w], dl[w], b[w] * c[w]);
+    }
+    const int P = max(2, (m + 4) >> 1);   // 2P >= m + 3
+    const double c_top = c_kq_tables.invfact[2 * (P - 1)];
+    const double s_top = c_kq_tables.invfact[2 * (P - 1) + 1];
+#pragma unroll
+    for (int w = 0; w < WB; ++w) {
+      Cv[w] = c_top;
+      Sv[w] = s_top;
+    }
+#pragma unroll 1
+    for (int j = P - 2; j >= 0; --j) {
+      const double cj = c_kq_tables.invfact[2 * j], sj = c_kq_tables.invfact[2 * j + 1];
+#pragma unroll
+      for (int w = 0; w < WB; ++w) {
+        Cv[w] = fma(-z[w], Cv[w], cj);
+        Sv[w] = fma(-z[w], Sv[w], sj);
       }
     }
-    phase = (t != 0.0);
-    st = 0.0;
-    ct = 1.0;
-    if (phase) sincos(t, &st, &ct);
+#pragma unroll
+    for (int w = 0; w < WB; ++w) {
+      ops[w].C = Cv[w];
+      ops[w].Sd = Sv[w] * dl[w];
+      ops[w].Sb = Sv[w] * b[w];
+      ops[w].Sc = Sv[w] * c[w];
+      ops[w].st = 0.0;
+      ops[w].ct = 1.0;
+      if (t[w] != 0.0) {   // traceless generators skip the phase
+        const double2 sc = pic_phase(t[w]);
+        ops[w].st = sc.x;
+        ops[w].ct = sc.y;
+      }
+    }
   }
-  __device__ __forceinline__ void apply(cplx (&y)[2]) const {
-    for (int rep = 0; rep < s; ++rep) {
-      const cplx v0 = y[0], v1 = y[1];
-      const cplx w0 = make_double2(fma(dl, v0.x, b * v1.x), fma(dl, v0.y, b * v1.y));
-      const cplx w1 = make_double2(fma(-dl, v1.x, c * v0.x), fma(-dl, v1.y, c * v0.y));
-      cplx u0 = make_double2(fma(-S, w0.y, C * v0.x), fma(S, w0.x, C * v0.y));
-      cplx u1 = make_double2(fma(-S, w1.y, C * v1.x), fma(S, w1.x, C * v1.y));
+  template <int NV>
+  __device__ __forceinline__ void apply(cplx (&Y)[NV * 2], int s, int m) const {
+    (void)m;
+    once<NV>(Y);
+    if (s > 1) {   // rare: scaled steps
+#pragma unroll 1
+      for (int rep = 1; rep < s; ++rep) once<NV>(Y);
+    }
+  }
+  template <int NV>
+  __device__ __forceinline__ void once(cplx (&Y)[NV * 2]) const {
+    const bool phase = (st != 0.0) || (ct != 1.0);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const cplx v0 = Y[2 * v], v1 = Y[2 * v + 1];
+      // u = C v + i (S R') v
+      cplx u0 = make_double2(fma(-Sd, v0.y, fma(-Sb, v1.y, C * v0.x)),
+                             fma(Sd, v0.x, fma(Sb, v1.x, C * v0.y)));
+      cplx u1 = make_double2(fma(Sd, v1.y, fma(-Sc, v0.y, C * v1.x)),
+                             fma(-Sd, v1.x, fma(Sc, v0.x, C * v1.y)));
       if (phase) {
         u0 = make_double2(fma(-st, u0.y, ct * u0.x), fma(st, u0.x, ct * u0.y));
         u1 = make_double2(fma(-st, u1.y, ct * u1.x), fma(st, u1.x, ct * u1.y));
       }
-      y[0] = u0;
-      y[1] = u1;
+      Y[2 * v] = u0;
+      Y[2 * v + 1] = u1;
     }
   }
 };
 
-// CTA-wide maxima of four non-negative doubles (all threads call).
-// scratch: [4][32] doubles.  Two barriers.
-__device__ __forceinline__ void block_max4(double& v0, double& v1, double& v2, double& v3,
-                                           double* scratch) {
-  v0 = warp_allreduce_max(v0);
-  v1 = warp_allreduce_max(v1);
-  v2 = warp_allreduce_max(v2);
-  v3 = warp_allreduce_max(v3);
+// Warp maximum of non-negative doubles (or +inf as a "bad" marker): their bit
+// patterns are ordered like unsigned integers, so two integer REDUX do it.
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
+}
+
+// CTA-wide maxima of two non-negative doubles; `buf` = 64 doubles that are not
+// reused before the next barrier of the caller (one barrier inside).
+__device__ __forceinline__ void block_max2(double& v0, double& v1, double* buf) {
+  v0 = warp_max_nonneg(v0);
+  v1 = warp_max_nonneg(v1);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
   if (lane == 0) {
-    scratch[warp] = v0;
-    scratch[32 + warp] = v1;
-    scratch[64 + warp] = v2;
-    scratch[96 + warp] = v3;
+    buf[warp] = v0;
+    buf[32 + warp] = v1;
   }
   __syncthreads();
-  double r0 = scratch[0], r1 = scratch[32], r2 = scratch[64], r3 = scratch[96];
+  double r0 = buf[0], r1 = buf[32];
   for (int w = 1; w < nw; ++w) {
-    r0 = fmax(r0, scratch[w]);
-    r1 = fmax(r1, scratch[32 + w]);
-    r2 = fmax(r2, scratch[64 + w]);
-    r3 = fmax(r3, scratch[96 + w]);
+    r0 = fmax(r0, buf[w]);
+    r1 = fmax(r1, buf[32 + w]);
   }
-  __syncthreads();
   v0 = r0;
   v1 = r1;
-  v2 = r2;
-  v3 = r3;
 }
 
 // CTA-wide sum in a fixed order (warp butterfly, then the warps in order).
@@ -211,307 +255,613 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return r;
 }
 
-// Shared state of one thread of the time-parallel kernels.
-template <int N, bool INREG, typename G>
-struct PicCtx {
-  SpecTerms<N, INREG, G> T;
-  cplx start[N];     // state of this objective at the start of the sweep
-  int q, t, lane, wq, k, W, TC, NT;
-  bool driven;
-  double c1_fixed;
-  const double* dt;
-  const double* seps;   // [W][TC] transposed pulse values of the current iterate
-  cplx* wtot;           // [Q][KQ_PIC_WPO][N*N] warp totals
+struct PicGeom {
+  int q, t, lane, wq, WPO, W, lw, TC, NT;
 };
 
-// Pass A + scan: state at the start of this thread's chunk under the pulse in
-// c.seps.  Contains one __syncthreads (all threads of the CTA must call).
-template <int N, bool INREG, typename G>
-__device__ __forceinline__ void pic_chunk_start(const PicCtx<N, INREG, G>& c, int s, int m,
-                                                cplx (&b)[N]) {
+// Pass A: product of the step propagators of this thread's chunk,
+// M = U_last ... U_first (REV: U_first ... U_last, the backward sweep's order of
+// application).  Steps beyond the grid have dt = 0 (identity).  With WT > 0 the
+// chunk length is the compile-time constant WT: all operators are prepared
+// together and kept in `ops`.
+template <int N, bool INREG, typename G, int WT, bool REV>
+__device__ __forceinline__ void pic_pass_a(const SpecTerms<N, INREG, G>& T, const PicGeom& g,
+                                           const double* seps, const double* dtg, bool driven,
+                                           double c1_fixed, int s, int m, double inv_s,
+                                           cplx (&M)[N * N],
+                                           StepOp<N, INREG, G> (&ops)[WT > 0 ? WT : 1]) {
   constexpr int NN = N * N;
-  cplx M[NN];
 #pragma unroll
   for (int e = 0; e < NN; ++e) M[e] = c_make((e % N) == (e / N) ? 1.0 : 0.0, 0.0);
-  for (int w = 0; w < c.W; ++w) {
-    const int n = c.t * c.W + w;
-    if (n < c.NT) {
-      const double eps = c.driven ? c.seps[w * c.TC + c.t] : c.c1_fixed;
-      StepOp<N, INREG, G> op;
-      op.prepare(c.T, c.dt[n], eps, s, m);
+  if constexpr (WT > 0) {
+    constexpr int WB = WT > 0 ? WT : 1;
+    double h[WB], heps[WB];
 #pragma unroll
-      for (int v = 0; v < N; ++v) {
-        cplx y[N];
+    for (int w = 0; w < WB; ++w) {
+      const int n = g.t * WB + w;
+      h[w] = ((n < g.NT) ? dtg[n] : 0.0) * inv_s;
+      heps[w] = h[w] * (driven ? seps[w * g.TC + g.t] : c1_fixed);
+    }
+    StepOp<N, INREG, G>::template prepare_batch<WB>(T, h, heps, m, ops);
 #pragma unroll
-        for (int i = 0; i < N; ++i) y[i] = M[v * N + i];
-        op.apply(y);
-#pragma unroll
-        for (int i = 0; i < N; ++i) M[v * N + i] = y[i];
+    for (int ww = 0; ww < WB; ++ww) {
+      const int w = REV ? WB - 1 - ww : ww;
+      ops[w].template apply<N>(M, s, m);
+    }
+  } else {
+    for (int ww = 0; ww < g.W; ++ww) {
+      const int w = REV ? g.W - 1 - ww : ww;
+      const int n = (g.t << g.lw) + w;
+      if (n < g.NT) {
+        double h[1], heps[1];
+        h[0] = dtg[n] * inv_s;
+        heps[0] = h[0] * (driven ? seps[w * g.TC + g.t] : c1_fixed);
+        StepOp<N, INREG, G> op1[1];
+        StepOp<N, INREG, G>::template prepare_batch<1>(T, h, heps, m, op1);
+        op1[0].template apply<N>(M, s, m);
       }
     }
   }
-  // inclusive scan over the lanes: M <- M_lane * ... * M_0
+}
+
+// Scan of the chunk propagators over the lanes (first half of the scan): after
+// it M is the product over this lane and all earlier (REV: later) lanes.
+template <int N, bool REV>
+__device__ __forceinline__ void pic_scan_lanes(cplx (&M)[N * N], int lane) {
+  constexpr int NN = N * N;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     cplx O[NN];
 #pragma unroll
-    for (int e = 0; e < NN; ++e) O[e] = shfl_up_c(M[e], off);
-    if (c.lane >= off) {
+    for (int e = 0; e < NN; ++e) O[e] = REV ? shfl_down_c(M[e], off) : shfl_up_c(M[e], off);
+    if (REV ? (lane + off < 32) : (lane >= off)) {
       cplx Cm[NN];
       mat_mul<N>(M, O, Cm);
 #pragma unroll
       for (int e = 0; e < NN; ++e) M[e] = Cm[e];
     }
   }
-  cplx* wt = c.wtot + (size_t)c.q * KQ_PIC_WPO * NN;
-  if (c.lane == 31) {
-#pragma unroll
-    for (int e = 0; e < NN; ++e) wt[c.wq * NN + e] = M[e];
-  }
-  __syncthreads();
+}
+
+// Second half: warp totals through shared memory (`wt`, this objective's
+// [WPO][N*N] block, written before the barrier the caller places between the
+// halves), then b = state at the boundary where this thread's chunk starts
+// (forward: before its first step; REV: after its last step).
+template <int N, bool REV>
+__device__ __forceinline__ void pic_scan_finish(const cplx (&M)[N * N], const cplx (&start)[N],
+                                                const PicGeom& g, const cplx* wt, cplx (&b)[N]) {
+  constexpr int NN = N * N;
   cplx v[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) v[i] = c.start[i];
-  for (int w = 0; w < c.wq; ++w) {
-    cplx o[N];
-    mat_vec<N>(wt + w * NN, v, o);
+  for (int i = 0; i < N; ++i) v[i] = start[i];
+  if (REV) {
+#pragma unroll 1
+    for (int w = g.WPO - 1; w > g.wq; --w) {
+      cplx o[N];
+      mat_vec<N>(wt + w * NN, v, o);
 #pragma unroll
-    for (int i = 0; i < N; ++i) v[i] = o[i];
+      for (int i = 0; i < N; ++i) v[i] = o[i];
+    }
+  } else {
+#pragma unroll 1
+    for (int w = 0; w < g.wq; ++w) {
+      cplx o[N];
+      mat_vec<N>(wt + w * NN, v, o);
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = o[i];
+    }
   }
   cplx e_[N];
   mat_vec<N>(M, v, e_);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const cplx up = shfl_up_c(e_[i], 1);
-    b[i] = (c.lane == 0) ? v[i] : up;
+    const cplx nb = REV ? shfl_down_c(e_[i], 1) : shfl_up_c(e_[i], 1);
+    b[i] = (g.lane == (REV ? 31 : 0)) ? v[i] : nb;
   }
 }
 
-// Taylor plan for the whole CTA from the largest scaled norm of any step.
-__device__ __forceinline__ void pic_plan(double xmax, int& s, int& m) {
+// CTA-uniform scaling count and Taylor degree for a norm bound x <= KQ_PIC_XCAP.
+__device__ __forceinline__ void pic_plan(double x, int& s, int& m, double& inv_s) {
   double bound;
-  plan_bound(xmax, s, m, bound);
+  plan_bound(fmin(x, KQ_PIC_XCAP), s, m, bound);
+  inv_s = (s == 1) ? 1.0 : 1.0 / (double)s;
 }
 
-// shared: [scratch 128][seps NTP][dsm Q*NTP][eta Q*NTP*N cplx][wtot Q*WPO*NN cplx][terms]
-template <int N, int FSEL, bool SECOND, typename G>
-__global__ void __launch_bounds__(KQ_PIC_BT, 1) k_fwupd_picard(const KqSweepArgs a) {
+// shared: [scratch 256][seps NTP][dsm Q*NTP][own 3*Wc][eta Q*NTP*N cplx]
+//         (seps is double-buffered: 2*NTP) [wtot 2*Q*WPO*NN cplx][terms Q*4*NN (N = 4)]
+template <int N, int FSEL, bool SECOND, typename G, int WT>
+__global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NN = N * N;
   constexpr bool INREG = (N <= 3);
+  constexpr int FSEL_BW = (FSEL == 0) ? 1 : 2;
+  constexpr int WA = WT > 0 ? WT : 1;
+  // step operators prepared in pass A are reused by pass B when they are small
+  constexpr bool KEEP = (WT > 0) && (WT * sizeof(StepOp<N, INREG, G>) <= 320);
   const int tid = threadIdx.x, BT = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = BT >> 5;
-  const int Q = a.pic_Q, TC = a.pic_TC, W = a.pic_W, NT = a.NT, K = a.K;
+  const int Q = a.pic_Q, TC = a.pic_TC, W = a.pic_W, lw = a.pic_lw, NT = a.NT, K = a.K;
   const int NTP = TC * W;
   const int nblk = gridDim.x;
   const bool single = (nblk == 1);
+  const int Wl = (WT > 0) ? WT : W;      // chunk length (compile-time when WT > 0)
+  const int Wc = a.pic_Wc;               // time slice reduced by each CTA
+  const int n_lo = blockIdx.x * Wc;
 
-  double* scratch = reinterpret_cast<double*>(smem_raw);   // [128]
-  double* seps = scratch + 128;                             // [NTP]  index w*TC + t
-  double* dsm = seps + NTP;                                 // [Q][NTP]
-  cplx* eta = reinterpret_cast<cplx*>(dsm + (size_t)Q * NTP);   // [Q][W][N][TC]
-  cplx* wtot = eta + (size_t)Q * NTP * N;                   // [Q][WPO][NN]
-  G* sterms = reinterpret_cast<G*>(wtot + (size_t)Q * KQ_PIC_WPO * NN);   // [Q][2][NN] (N = 4)
+  double* scratch = reinterpret_cast<double*>(smem_raw);   // [256]
+  double* seps0 = scratch + 256;                            // [2][NTP] by round parity, index w*TC + t
+  double* dsm = seps0 + 2 * NTP;                            // [Q][NTP]
+  const double* seps = seps0 + NTP;                         // round 1 = the guess pulse
+  double* own_sl = dsm + (size_t)Q * NTP;                   // [Wc] S/lambda of the owned slice
+  double* own_g = own_sl + Wc;                              // [Wc] guess pulse
+  double* own_dt = own_g + Wc;                              // [Wc] dt
+  cplx* eta = reinterpret_cast<cplx*>(own_dt + Wc);         // [Q][W][N][TC]
+  cplx* wtot = eta + (size_t)Q * NTP * N;                   // [2][Q][WPO][NN] (by round parity)
+  G* sterms = reinterpret_cast<G*>(wtot + (size_t)2 * Q * KQ_PIC_WPO * NN);   // [Q][4][NN] (N = 4)
 
-  PicCtx<N, INREG, G> c;
-  c.q = tid / TC;
-  c.t = tid - c.q * TC;
-  c.lane = lane;
-  c.wq = c.t >> 5;
-  c.W = W;
-  c.TC = TC;
-  c.NT = NT;
-  c.dt = a.dt;
-  c.seps = seps;
-  c.wtot = wtot;
-  int k = blockIdx.x * Q + c.q;
+  PicGeom g;
+  g.q = tid / TC;
+  g.t = tid - g.q * TC;
+  g.lane = lane;
+  g.wq = g.t >> 5;
+  g.WPO = TC >> 5;
+  g.W = W;
+  g.lw = lw;
+  g.TC = TC;
+  g.NT = NT;
+  int k = blockIdx.x * Q + g.q;
   const bool valid = k < K;
   if (!valid) k = K - 1;
-  c.k = k;
-  if (INREG) {
-    c.T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
-                            nullptr, BT, tid);
-  } else {
-    if (c.t < NN) {
-      sterms[(c.q * 2 + 0) * NN + c.t] = g_load<FSEL>(a.ops[((size_t)k * 2 + 0) * NN + c.t], G());
-      sterms[(c.q * 2 + 1) * NN + c.t] = g_load<FSEL>(a.ops[((size_t)k * 2 + 1) * NN + c.t], G());
-    }
-    c.T.s0 = sterms + (size_t)c.q * 2 * NN;
-    c.T.s1 = c.T.s0 + NN;
-    c.T.stride = 1;
+  cplx* wt = wtot + (size_t)g.q * KQ_PIC_WPO * NN;
+
+  // optional per-phase cycle counts (thread 0 of CTA 0): kq_set_option("picard_timing", 1)
+  const bool timing = a.pic_timing && tid == 0 && blockIdx.x == 0;
+  long long tacc[KQ_PIC_NTICK], tprev = 0;
+#pragma unroll
+  for (int i = 0; i < KQ_PIC_NTICK; ++i) tacc[i] = 0;
+#define KQ_TICK(i)                      \
+  if (timing) {                         \
+    const long long now_ = clock64();   \
+    tacc[i] += now_ - tprev;            \
+    tprev = now_;                       \
   }
+  if (timing) tprev = clock64();
+
   const double opn0 = a.op_norm[k * 2 + 0], opn1 = a.op_norm[k * 2 + 1];
-  c.driven = a.term2pulse[k * 2 + 1] == 0;
-  c.c1_fixed = (a.term2pulse[k * 2 + 1] == -1) ? 1.0 : 0.0;
+  const bool driven = a.term2pulse[k * 2 + 1] == 0;
+  const double c1_fixed = (a.term2pulse[k * 2 + 1] == -1) ? 1.0 : 0.0;
   const double lam = a.lambda_a[0];
   cplx mu[NN];
 #pragma unroll
   for (int e = 0; e < NN; ++e) mu[e] = a.mu[(size_t)k * NN + e];
-  const double cnorm = valid ? a.chi_norms[k] : 0.0;
-#pragma unroll
-  for (int i = 0; i < N; ++i) c.start[i] = a.state0[(size_t)k * N + i];
 
-  // eta[n] = mu^dag chi[n] ||chi||  for the steps of this chunk
-  for (int w = 0; w < W; ++w) {
-    const int n = c.t * W + w;
-    cplx chi[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i)
-      chi[i] = (n < NT) ? a.X[((size_t)n * K + k) * N + i] : c_zero();
-#pragma unroll
-    for (int cc = 0; cc < N; ++cc) {
-      cplx acc = c_zero();
-#pragma unroll
-      for (int r = 0; r < N; ++r) acc = c_fma_conj(mu[cc * N + r], chi[r], acc);
-      eta[(((size_t)c.q * W + w) * N + cc) * TC + c.t] =
-          make_double2(acc.x * cnorm, acc.y * cnorm);
+  if (!INREG) {
+    if (g.t < NN) {
+      const size_t o0 = ((size_t)k * 2 + 0) * NN + g.t, o1 = ((size_t)k * 2 + 1) * NN + g.t;
+      sterms[(g.q * 4 + 0) * NN + g.t] = g_load<FSEL>(a.ops[o0], G());
+      sterms[(g.q * 4 + 1) * NN + g.t] = g_load<FSEL>(a.ops[o1], G());
+      if (a.pic_bw) {
+        sterms[(g.q * 4 + 2) * NN + g.t] = g_load<FSEL_BW>(a.ops_adj[o0], G());
+        sterms[(g.q * 4 + 3) * NN + g.t] = g_load<FSEL_BW>(a.ops_adj[o1], G());
+      }
     }
   }
-  // CTA-wide operator norm bounds and the first iterate (the guess pulse)
-  double O0 = opn0, O1 = c.driven ? opn1 : 0.0, Oc = c.driven ? 0.0 : c.c1_fixed * opn1;
-  double dummy = 0.0;
-  block_max4(O0, O1, Oc, dummy, scratch);
-  double xm = 0.0, em = 0.0, dm = 0.0, bad = 0.0;
+
+  // first iterate (the guess pulse), the owned slice's scalars, norm bounds
+  double gmax = 0.0, dtmax = 0.0;
   for (int n = tid; n < NTP; n += BT) {
     const double e = (n < NT) ? a.pulses[n] : 0.0;
-    seps[(n % W) * TC + n / W] = e;
-    if (n < NT) xm = fmax(xm, a.dt[n] * (fma(fabs(e), O1, O0) + Oc));
+    seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
+    seps0[(n & (W - 1)) * TC + (n >> lw)] = 0.0;
+    if (n < NT) {
+      gmax = fmax(gmax, fabs(e));
+      dtmax = fmax(dtmax, fabs(a.dt[n]));
+    }
   }
-  block_max4(xm, em, dm, bad, scratch);   // also orders the smem writes above
+  for (int i = tid; i < Wc; i += BT) {
+    const int n = n_lo + i;
+    const bool in = n < NT;
+    own_sl[i] = in ? a.shape[n] / lam : 0.0;   // S/lambda as in optimize.py:474
+    own_g[i] = in ? a.pulses[n] : 0.0;
+    own_dt[i] = in ? a.dt[n] : 0.0;
+  }
+  block_max2(gmax, dtmax, scratch);          // barrier: also orders the writes above
+  double O0 = opn0, O1 = driven ? opn1 : 0.0;
+  block_max2(O0, O1, scratch + 64);
+  double Oc = driven ? 0.0 : c1_fixed * opn1, unused = 0.0;
+  block_max2(Oc, unused, scratch + 128);
 
-  const int Wc = (NT + nblk - 1) / nblk;   // time slice reduced by each CTA
-  const int n_lo = blockIdx.x * Wc;
+  // ---- boundary condition chi_k(T), normalised (optimize.py:404-410) ---------
+  cplx chiT[N];
+  double cnorm;
+  if (a.pic_bw) {
+    if (a.chi_kind < 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) chiT[i] = a.chiT[(size_t)k * N + i];
+      cnorm = a.chi_norms[k];
+    } else {
+      const double wgt = a.weights ? a.weights[k] : 1.0;
+      const double Kt = (double)a.K_total;
+      cplx cf;
+      if (a.chi_kind == KQ_CHI_RE || a.chi_kind == KQ_CHI_HS) {
+        cf = c_make(wgt * (1.0 / (2.0 * Kt)), 0.0);
+      } else if (a.chi_kind == KQ_CHI_SS) {
+        const cplx tk = a.tau_in[k];
+        cf = c_make(tk.x / Kt * wgt, tk.y / Kt * wgt);
+      } else {   // KQ_CHI_SM: sum_j w_j tau_j over all objectives, fixed order
+        double sx = 0.0, sy = 0.0;
+        for (int j = tid; j < K; j += BT) {
+          const double wj = a.weights ? a.weights[j] : 1.0;
+          const cplx tj = a.tau_in[j];
+          sx = fma(wj, tj.x, sx);
+          sy = fma(wj, tj.y, sy);
+        }
+        sx = block_sum(sx, scratch + 192);
+        sy = block_sum(sy, scratch + 192);
+        const double f = (1.0 / (Kt * Kt)) * wgt;
+        cf = c_make(f * sx, f * sy);
+      }
+      double nrm2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        cplx tg = a.targets[(size_t)k * N + i];
+        if (a.chi_kind == KQ_CHI_HS) tg = c_sub(tg, a.phiT_in[(size_t)k * N + i]);
+        const cplx v = c_make(cf.x * tg.x - cf.y * tg.y, cf.x * tg.y + cf.y * tg.x);
+        chiT[i] = v;
+        nrm2 = fma(v.x, v.x, nrm2);
+        nrm2 = fma(v.y, v.y, nrm2);
+      }
+      cnorm = sqrt(nrm2);
+#pragma unroll
+      for (int i = 0; i < N; ++i) chiT[i] = c_make(chiT[i].x / cnorm, chiT[i].y / cnorm);
+    }
+    if (g.t == 0 && valid) {
+      if (a.chi_out) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) a.chi_out[(size_t)k * N + i] = chiT[i];
+      }
+      if (a.chi_norms_out) a.chi_norms_out[k] = cnorm;
+    }
+  } else {
+    cnorm = a.chi_norms[k];
+#pragma unroll
+    for (int i = 0; i < N; ++i) chiT[i] = c_zero();
+  }
+  if (!valid) cnorm = 0.0;
+  KQ_TICK(0)
+
+  // ---- backward sweep (optimize.py:849-886) -> eta[n] = mu^dag chi[n] ||chi|| --
+  if (a.pic_bw) {
+    SpecTerms<N, INREG, G> Tb;
+    if (INREG) {
+      Tb.template load<FSEL_BW>(a.ops_adj + ((size_t)k * 2 + 0) * NN,
+                                a.ops_adj + ((size_t)k * 2 + 1) * NN, nullptr, BT, tid);
+    } else {
+      Tb.s0 = sterms + (size_t)(g.q * 4 + 2) * NN;
+      Tb.s1 = Tb.s0 + NN;
+      Tb.stride = 1;
+    }
+    int s, m;
+    double inv_s;
+    pic_plan(dtmax * (fma(gmax, O1, O0) + Oc), s, m, inv_s);
+    cplx M[NN], y[N];
+    StepOp<N, INREG, G> ops[WA];
+    pic_pass_a<N, INREG, G, WT, true>(Tb, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
+    pic_scan_lanes<N, true>(M, lane);
+    if (lane == 0) {
+#pragma unroll
+      for (int e = 0; e < NN; ++e) wt[g.wq * NN + e] = M[e];
+    }
+    __syncthreads();
+    pic_scan_finish<N, true>(M, chiT, g, wt, y);
+    if (a.Xout && valid && g.t == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) a.Xout[((size_t)NT * K + k) * N + i] = chiT[i];
+    }
+#pragma unroll
+    for (int ww = 0; ww < Wl; ++ww) {
+      const int w = Wl - 1 - ww;
+      const int n = g.t * Wl + w;
+      if (n < NT) {
+        if (KEEP) {
+          ops[WT > 0 ? w : 0].template apply<1>(y, s, m);
+        } else {
+          double h[1], heps[1];
+          h[0] = a.dt[n] * inv_s;
+          heps[0] = h[0] * (driven ? seps[w * TC + g.t] : c1_fixed);
+          StepOp<N, INREG, G> op1[1];
+          StepOp<N, INREG, G>::template prepare_batch<1>(Tb, h, heps, m, op1);
+          op1[0].template apply<1>(y, s, m);
+        }
+        if (a.Xout && valid) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) a.Xout[((size_t)n * K + k) * N + i] = y[i];
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < N; ++cc) {
+        cplx acc = c_zero();
+#pragma unroll
+        for (int r = 0; r < N; ++r) acc = c_fma_conj(mu[cc * N + r], y[r], acc);
+        eta[(((size_t)g.q * W + w) * N + cc) * TC + g.t] =
+            (n < NT) ? make_double2(acc.x * cnorm, acc.y * cnorm) : c_zero();
+      }
+    }
+  } else {
+    for (int w = 0; w < W; ++w) {
+      const int n = (g.t << lw) + w;
+      cplx chi[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        chi[i] = (n < NT) ? a.X[((size_t)n * K + k) * N + i] : c_zero();
+#pragma unroll
+      for (int cc = 0; cc < N; ++cc) {
+        cplx acc = c_zero();
+#pragma unroll
+        for (int r = 0; r < N; ++r) acc = c_fma_conj(mu[cc * N + r], chi[r], acc);
+        eta[(((size_t)g.q * W + w) * N + cc) * TC + g.t] =
+            make_double2(acc.x * cnorm, acc.y * cnorm);
+      }
+    }
+  }
+  __syncthreads();   // wtot is reused by the forward scans
+  KQ_TICK(1)
+
+  // ---- pulse update + forward sweep (optimize.py:449-500): Picard iteration ---
+  // Round `it` evaluates F under the iterate eps_it (eps_1 = guess pulse):
+  //   [fetch this thread's entries of eps_it] -> pass A -> scan (its barrier also
+  //   carries the CTA-wide max |eps_it - eps_{it-1}|, max |eps_it|) -> pass B ->
+  //   partial sums to the owners -> owners publish eps_{it+1}.
+  // Converged when eps_it = eps_{it-1} to rtol: the evaluation just done then
+  // gives phi(T) under the final pulse.
+  SpecTerms<N, INREG, G> T;
+  if (INREG) {
+    T.template load<FSEL>(a.ops + ((size_t)k * 2 + 0) * NN, a.ops + ((size_t)k * 2 + 1) * NN,
+                          nullptr, BT, tid);
+  } else {
+    T.s0 = sterms + (size_t)(g.q * 4 + 0) * NN;
+    T.s1 = T.s0 + NN;
+    T.stride = 1;
+  }
+  cplx phi0[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) phi0[i] = a.state0[(size_t)k * N + i];
+  const int t_last = (NT - 1) >> lw;       // thread whose chunk ends the sweep
+  const uint32_t tag0 = a.tag_base;
+  const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+  const bool direct = (Q == 1) && !single;   // pass B publishes its partial sums itself
   bool failed = false, converged = false;
   double ga_acc = 0.0;   // single: this thread's share; multi: lane 0 of each warp
+  double em = gmax;      // max |eps| of the previous iterate (plans the next evaluation)
+  double dm = kInf, en = gmax;   // this thread's share of max |eps_it - eps_{it-1}|, max |eps_it|
+  cplx y[N];
   int it = 0;
   while (true) {
     ++it;
+    // ---- the new iterate (multi-CTA: from the owners), coalesced over the CTA ----
+    // the pulse is double-buffered by round parity: a warp may fetch eps_it while
+    // another one still reads eps_{it-1} in its pass B
+    double* sw = seps0 + (size_t)(it & 1) * NTP;
+    const double* sr = seps0 + (size_t)((it - 1) & 1) * NTP;
+    if (!single && it > 1) {
+      const uint32_t tagp = tag0 + (uint32_t)(it - 1);
+      dm = 0.0;
+      en = 0.0;
+      for (int nb = tid; nb < NT; nb += 4 * BT) {
+        const KqSlot* ptr[4];
+        bool act[4];
+        double ev[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = nb + u * BT;
+          act[u] = n < NT;
+          ptr[u] = &a.pic_eps[(size_t)blockIdx.x * a.pic_stride + (act[u] ? n : 0)];
+        }
+        slot_wait_batch<4>(ptr, act, tagp, ev, failed);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = nb + u * BT;
+          if (act[u]) {
+            const int idx = (n & (W - 1)) * TC + (n >> lw);
+            double e_new = ev[u];
+            if (e_new == kInf) en = kInf;   // an owner's exchange timed out
+            if (!(dtmax * (fma(fabs(e_new), O1, O0) + Oc) <= KQ_PIC_XCAP)) {
+              e_new = a.pulses[n];   // runaway iterate: restart this entry
+              dm = kInf;
+            }
+            dm = fmax(dm, fabs(e_new - sr[idx]));
+            en = fmax(en, fabs(e_new));
+            sw[idx] = e_new;
+          }
+        }
+      }
+      if (failed) en = kInf;   // exchange timed out
+      __syncthreads();
+    }
+    seps = sw;
+    KQ_TICK(14)
+    // the evaluation is planned for |eps| <= 2 max|eps_{it-1}| (verified after the scan)
+    const double em_bound = 2.0 * em;
     int s, m;
-    pic_plan(xm, s, m);
-    cplx y[N];
-    pic_chunk_start<N, INREG, G>(c, s, m, y);
-    // ---- pass B: overlaps at every step of the chunk -------------------------
-    for (int w = 0; w < W; ++w) {
-      const int n = c.t * W + w;
-      double d = 0.0;
-      if (n < NT) {
+    double inv_s;
+    pic_plan(dtmax * (fma(em_bound, O1, O0) + Oc), s, m, inv_s);
+    bool stop;
+    {
+      // warp totals are double-buffered: a warp may start the next round while
+      // another one still reads this round's totals
+      cplx* wt = wtot + ((size_t)(it & 1) * Q + g.q) * KQ_PIC_WPO * NN;
+      cplx M[NN];
+      StepOp<N, INREG, G> ops[WA];
+      pic_pass_a<N, INREG, G, WT, false>(T, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
+      KQ_TICK(2)
+      pic_scan_lanes<N, false>(M, lane);
+      if (lane == 31) {
+#pragma unroll
+        for (int e = 0; e < NN; ++e) wt[g.wq * NN + e] = M[e];
+      }
+      double* rbuf = scratch + (it & 1) * 64;
+      {
+        const double wd = warp_max_nonneg(dm), we = warp_max_nonneg(en);
+        if (lane == 0) {
+          rbuf[warp] = wd;
+          rbuf[32 + warp] = we;
+        }
+      }
+      KQ_TICK(10)
+      __syncthreads();
+      KQ_TICK(11)
+      double dmax = rbuf[0], emax = rbuf[32];
+      for (int w = 1; w < nwarps; ++w) {
+        dmax = fmax(dmax, rbuf[w]);
+        emax = fmax(emax, rbuf[32 + w]);
+      }
+      pic_scan_finish<N, false>(M, phi0, g, wt, y);
+      KQ_TICK(12)
+      // CTA-uniform (and grid-uniform: every CTA sees the same pulse) decisions
+      const bool exch_fail = !(emax < kInf);
+      const bool resolved = emax <= em_bound;        // the plan covered this iterate
+      converged = !exch_fail && resolved && (dmax <= a.pic_rtol * emax);
+      stop = converged || exch_fail || it >= a.pic_maxit;
+      if (exch_fail) em = kInf; else em = emax;
+      const uint32_t tag = tag0 + (uint32_t)it;
+      // ---- pass B: overlaps at every step of the chunk ------------------------
+#pragma unroll
+      for (int w = 0; w < Wl; ++w) {
+        const int n = g.t * Wl + w;
         double e0 = 0.0, e1 = 0.0;
 #pragma unroll
         for (int cc = 0; cc < N; ++cc) {
-          const cplx et = eta[(((size_t)c.q * W + w) * N + cc) * TC + c.t];
+          const cplx et = eta[(((size_t)g.q * W + w) * N + cc) * TC + g.t];
           if (cc & 1)
             e1 += c_im_conj_mul(et, y[cc]);
           else
             e0 += c_im_conj_mul(et, y[cc]);
         }
-        d = e0 + e1;
-        if (SECOND) {
-          if (n > 0 && valid) {
-            double v2 = 0.0;
+        double d = e0 + e1;   // eta = 0 beyond the grid
+        if (n < NT) {
+          if (SECOND) {
+            if (n > 0 && valid) {
+              double v2 = 0.0;
 #pragma unroll
-            for (int r = 0; r < N; ++r) {
-              cplx wv = c_zero();
+              for (int r = 0; r < N; ++r) {
+                cplx wv = c_zero();
 #pragma unroll
-              for (int cc = 0; cc < N; ++cc) wv = c_fma(mu[cc * N + r], y[cc], wv);
-              const cplx dphi = c_sub(y[r], a.Phi0[((size_t)n * K + k) * N + r]);
-              v2 += c_im_conj_mul(dphi, wv);
+                for (int cc = 0; cc < N; ++cc) wv = c_fma(mu[cc * N + r], y[cc], wv);
+                const cplx dphi = c_sub(y[r], a.Phi0[((size_t)n * K + k) * N + r]);
+                v2 += c_im_conj_mul(dphi, wv);
+              }
+              d = fma(0.5 * a.sigma[n], v2, d);
             }
-            d = fma(0.5 * a.sigma[n], v2, d);
+          }
+          if (SECOND && stop && converged && a.store && valid) {
+            // second order keeps all forward states of the final evaluation
+#pragma unroll
+            for (int i = 0; i < N; ++i) a.store[((size_t)n * K + k) * N + i] = y[i];
+          }
+          if (direct && !stop) slot_store(&a.pic_part[(size_t)n * nblk + blockIdx.x], d, tag);
+          if (KEEP) {
+            ops[WT > 0 ? w : 0].template apply<1>(y, s, m);
+          } else {
+            double h[1], heps[1];
+            h[0] = a.dt[n] * inv_s;
+            heps[0] = h[0] * (driven ? seps[w * TC + g.t] : c1_fixed);
+            StepOp<N, INREG, G> op1[1];
+            StepOp<N, INREG, G>::template prepare_batch<1>(T, h, heps, m, op1);
+            op1[0].template apply<1>(y, s, m);
           }
         }
-        const double eps = c.driven ? seps[w * TC + c.t] : c.c1_fixed;
-        StepOp<N, INREG, G> op;
-        op.prepare(c.T, a.dt[n], eps, s, m);
-        op.apply(y);
+        if (!direct) dsm[(size_t)g.q * NTP + w * TC + g.t] = d;
       }
-      dsm[(size_t)c.q * NTP + w * TC + c.t] = d;
     }
-    __syncthreads();
+    KQ_TICK(3)
+    if (stop) break;
     // ---- sum over the objectives, pulse update --------------------------------
-    xm = 0.0;
-    em = 0.0;
-    dm = 0.0;
     ga_acc = 0.0;
     if (single) {
+      __syncthreads();
+      dm = 0.0;
+      en = 0.0;
       for (int n = tid; n < NT; n += BT) {
-        const int idx = (n % W) * TC + n / W;
+        const int idx = (n & (W - 1)) * TC + (n >> lw);
         double d1 = dsm[idx];
         for (int qq = 1; qq < Q; ++qq) d1 += dsm[(size_t)qq * NTP + idx];
-        const double sl = a.shape[n] / lam;
-        const double dtn = a.dt[n];
-        const double e_new = __dadd_rn(a.pulses[n], __dmul_rn(sl, d1));
+        const double sl = own_sl[n], dtn = own_dt[n];
+        double e_new = __dadd_rn(own_g[n], __dmul_rn(sl, d1));
         ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), dtn));
+        if (!(dtmax * (fma(fabs(e_new), O1, O0) + Oc) <= KQ_PIC_XCAP)) {
+          e_new = own_g[n];   // runaway iterate: restart this entry, not converged
+          dm = kInf;
+        }
         dm = fmax(dm, fabs(e_new - seps[idx]));
-        em = fmax(em, fabs(e_new));
-        xm = fmax(xm, dtn * (fma(fabs(e_new), O1, O0) + Oc));
-        if (!(fabs(e_new) < 1.0e150)) bad = 1.0;
-        seps[idx] = e_new;
+        en = fmax(en, fabs(e_new));
+        seps0[(size_t)((it + 1) & 1) * NTP + idx] = e_new;
       }
+      __syncthreads();
     } else {
-      const uint32_t tag = a.tag_base + (uint32_t)it;
-      const size_t stride = (size_t)a.pic_stride;
-      // stage 1: this CTA's partial sums for every time step
-      for (int n = tid; n < NT; n += BT) {
-        const int idx = (n % W) * TC + n / W;
-        double d1 = dsm[idx];
-        for (int qq = 1; qq < Q; ++qq) d1 += dsm[(size_t)qq * NTP + idx];
-        slot_store(&a.pic_part[(size_t)blockIdx.x * stride + n], d1, tag);
+      const uint32_t tag = tag0 + (uint32_t)it;
+      if (!direct) {
+        // stage 1: this CTA's partial sums for every time step
+        __syncthreads();
+        for (int n = tid; n < NT; n += BT) {
+          const int idx = (n & (W - 1)) * TC + (n >> lw);
+          double d1 = dsm[idx];
+          for (int qq = 1; qq < Q; ++qq) d1 += dsm[(size_t)qq * NTP + idx];
+          slot_store(&a.pic_part[(size_t)n * nblk + blockIdx.x], d1, tag);
+        }
       }
+      KQ_TICK(4)
       // stage 2: reduce time slice [n_lo, n_lo + Wc) over all CTAs (fixed order)
       for (int ni = warp; ni < Wc; ni += nwarps) {
         const int n = n_lo + ni;
         if (n < NT) {
-          double acc = 0.0;
-          for (int cb = lane; cb < nblk; cb += 32)
-            acc += slot_wait(&a.pic_part[(size_t)cb * stride + n], tag, failed);
-          acc = warp_allreduce_sum(acc);
-          if (lane == 0) {
-            const double sl = a.shape[n] / lam;
-            const double e_new = __dadd_rn(a.pulses[n], __dmul_rn(sl, acc));
-            ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), a.dt[n]));
-            slot_store(&a.pic_eps[n], e_new, tag);
+          constexpr int NB = (kPicBlocksMax + 31) / 32;
+          const KqSlot* ptr[NB];
+          bool act[NB];
+          double pv[NB];
+#pragma unroll
+          for (int u = 0; u < NB; ++u) {
+            const int cb = lane + 32 * u;
+            act[u] = cb < nblk;
+            ptr[u] = &a.pic_part[(size_t)n * nblk + (act[u] ? cb : 0)];
           }
+          slot_wait_batch<NB>(ptr, act, tag, pv, failed);
+          double acc = 0.0;
+#pragma unroll
+          for (int u = 0; u < NB; ++u) acc += pv[u];
+          acc = warp_allreduce_sum(acc);
+          const double sl = own_sl[ni];
+          // a failed wait publishes +inf: every CTA then stops in the next round
+          const double e_new = failed ? kInf : __dadd_rn(own_g[ni], __dmul_rn(sl, acc));
+          if (lane == 0)
+            ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), own_dt[ni]));
+          // push the new value into every CTA's own mailbox (no line is polled by
+          // more than one CTA)
+          for (int cb = lane; cb < nblk; cb += 32)
+            slot_store(&a.pic_eps[(size_t)cb * a.pic_stride + n], e_new, tag);
         }
       }
-      // stage 3: the whole updated pulse
-      for (int n = tid; n < NT; n += BT) {
-        const int idx = (n % W) * TC + n / W;
-        const double e_new = slot_wait(&a.pic_eps[n], tag, failed);
-        dm = fmax(dm, fabs(e_new - seps[idx]));
-        em = fmax(em, fabs(e_new));
-        xm = fmax(xm, a.dt[n] * (fma(fabs(e_new), O1, O0) + Oc));
-        if (!(fabs(e_new) < 1.0e150)) bad = 1.0;
-        seps[idx] = e_new;
-      }
-      if (failed) bad = 2.0;
+      KQ_TICK(5)
     }
-    block_max4(xm, em, dm, bad, scratch);
-    if (bad > 0.0) break;
-    if (dm <= a.pic_rtol * em) {
-      converged = true;
-      break;
-    }
-    if (it >= a.pic_maxit) break;
   }
 
   if (!converged) {
-    // ask for the sequential kernel (launched right after this one)
     if (blockIdx.x == 0 && tid == 0) {
       a.status[1] = (int)a.epoch;
-      if (bad > 1.5) atomicExch(a.status, (int)-4);
+      atomicCAS(a.status + 3, 0, (int)a.epoch);   // first epoch that did not converge
+      if (!(em < kInf)) atomicExch(a.status, (int)-4);
     }
     return;
   }
   // ---- outputs ----------------------------------------------------------------
   if (blockIdx.x == 0) {
-    for (int n = tid; n < NT; n += BT) a.opt_pulses[n] = seps[(n % W) * TC + n / W];
+    for (int n = tid; n < NT; n += BT) a.opt_pulses[n] = seps[(n & (W - 1)) * TC + (n >> lw)];
   }
   if (single) {
-    const double ga = block_sum(ga_acc, scratch);
+    const double ga = block_sum(ga_acc, scratch + 192);
     if (tid == 0) a.g_a[0] = ga;
   } else {
-    const uint32_t tagf = a.tag_base + (uint32_t)a.pic_maxit + 1u;
-    double ga = block_sum((lane == 0) ? ga_acc : 0.0, scratch);
+    const uint32_t tagf = tag0 + (uint32_t)a.pic_maxit + 1u;
+    double ga = block_sum((lane == 0) ? ga_acc : 0.0, scratch + 192);
     if (tid == 0) slot_store(&a.pic_ga[blockIdx.x], ga, tagf);
     if (blockIdx.x == 0 && warp == 0) {
       double acc = 0.0;
@@ -524,33 +874,28 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_fwupd_picard(const KqSweepArgs
     }
   }
   if (tid == 0 && blockIdx.x == 0) a.status[2] = it;   // Picard iterations used (diagnostics)
-  // final evaluation under the converged pulse: phi(T), forward states
-  {
-    int s, m;
-    pic_plan(xm, s, m);
-    cplx y[N];
-    pic_chunk_start<N, INREG, G>(c, s, m, y);
-    const bool store = SECOND && a.store && valid;
-    if (store && c.t == 0) {
+  KQ_TICK(8)
+  // second order: the final pass B stored rows 0..NT-1 of the forward states;
+  // row NT is the end of the last chunk
+  if (SECOND && a.store && valid && g.t == t_last) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) a.store[(size_t)k * N + i] = y[i];
+    for (int i = 0; i < N; ++i) a.store[((size_t)NT * K + k) * N + i] = y[i];
+  }
+  if (g.t == t_last && valid) {
+    if (a.stateT) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = y[i];
     }
-    for (int w = 0; w < W; ++w) {
-      const int n = c.t * W + w;
-      if (n < NT) {
-        const double eps = c.driven ? seps[w * TC + c.t] : c.c1_fixed;
-        StepOp<N, INREG, G> op;
-        op.prepare(c.T, a.dt[n], eps, s, m);
-        op.apply(y);
-        if (store) {
+    if (a.tau_out && a.targets) {
+      cplx acc = c_zero();
 #pragma unroll
-          for (int i = 0; i < N; ++i) a.store[((size_t)(n + 1) * K + k) * N + i] = y[i];
-        }
-        if (n == NT - 1 && a.stateT && valid) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) a.stateT[(size_t)k * N + i] = y[i];
-        }
-      }
+      for (int i = 0; i < N; ++i) acc = c_fma_conj(a.targets[(size_t)k * N + i], y[i], acc);
+      a.tau_out[k] = acc;
     }
   }
+  KQ_TICK(9)
+  if (timing) {
+    for (int i = 0; i < KQ_PIC_NTICK; ++i) a.status[16 + i] = (int)tacc[i];
+  }
+#undef KQ_TICK
 }

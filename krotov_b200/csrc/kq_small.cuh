@@ -57,7 +57,7 @@ struct KqSweepArgs {
   int pic_Q, pic_TC, pic_W, pic_maxit, pic_stride;
   double pic_rtol;
   KqSlot* pic_part;   // [gridDim.x][pic_stride] per-CTA partial sums over its objectives
-  KqSlot* pic_eps;    // [pic_stride] updated pulse
+  KqSlot* pic_eps;    // [gridDim.x][pic_stride] updated pulse, one mailbox per CTA
   KqSlot* pic_ga;     // [gridDim.x] per-CTA share of the g_a integral
   // sequential kernels launched as the fall-back of the time-parallel sweep run
   // only if status[1] == cond_epoch (0 = unconditional)

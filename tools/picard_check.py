@@ -54,7 +54,7 @@ def engine_run(wl, picard, iters=3, second=False, fused=False):
             tau_t = eng.overlaps(eng.t_targets, phiT)
         torch.cuda.synchronize()
         fb, pit = eng.sweep_diagnostics()
-        cyc = eng.workspace[64:104].view(torch.int32).cpu().numpy().copy()
+        cyc = eng.workspace[64:128].view(torch.int32).cpu().numpy().copy()
         out.append(dict(pulses=opt_t.cpu().numpy().copy(), phiT=phiT.cpu().numpy().copy(),
                         ga=eng.g_a.cpu().numpy().copy(), tau=tau_t.cpu().numpy().copy(),
                         ms=e0.elapsed_time(e1), cycles=cyc, fallback=(fb == eng.epoch), pit=pit,
@@ -105,9 +105,10 @@ if __name__ == '__main__':
         for r in timing('C4', W.tls_ensemble(K=128, nt=1000), 4):
             cyc = r['cycles']
             its = max(r['pit'], 1)
-            names = ['prologue', 'bw', 'passA+scan', 'passB', 'stage1', 'stage2', 'stage3', 'blockmax', 'outputs', 'final']
-            print('kernel %.1f us, %d its; cycles (per iter for 2..7): ' % (r['ms'] * 1e3, its) + ', '.join(
-                '%s %d' % (n, c // (its if 2 <= i <= 7 else 1)) for i, (n, c) in enumerate(zip(names, cyc))))
+            names = ['prologue', 'bw', 'passA', 'passB', 'stage1', 'stage2', 'stage3', 'blockmax', 'outputs', 'final',
+                     'scan-shfl', 'scan-bar', 'scan-finish', 'passB-bar', 'fetch', '-']
+            print('kernel %.1f us, %d its; cycles (per iter except prologue/bw/outputs/final): ' % (r['ms'] * 1e3, its) + ', '.join(
+                '%s %d' % (n, c // (1 if i in (0, 1, 8, 9) else its)) for i, (n, c) in enumerate(zip(names, cyc)) if n != '-'))
         sys.exit(0)
     compare('C4 K=8 nt=100', W.tls_ensemble(K=8, nt=100))
     compare('C4 K=128 nt=1000', W.tls_ensemble(K=128, nt=1000), iters=5)
