@@ -215,6 +215,10 @@ class SweepEngine:
         return (self.comm is None and self.gather is None and cp.M == 2
                 and cp.L == 1 and 2 <= cp.N <= 4)
 
+    def clear_fused_failure(self):
+        """Reset the 'first failed epoch' status word."""
+        self.workspace[12:16].zero_()
+
     def overlaps(self, a, b, out=None):
         """tau_k = <a_k|b_k> (optimize.py:316-322, 503-508)."""
         if out is None:

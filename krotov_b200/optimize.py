@@ -21,6 +21,7 @@ import numpy as np
 from . import functionals as _functionals
 from .compiler import compile_problem, initialize_controls
 from .conversions import control_onto_interval, pulse_onto_tlist
+from ._lib import KqError
 from .engine import SweepEngine
 from .info_hooks import chain
 from .mu import derivative_wrt_pulse
@@ -215,7 +216,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     parallel_map=None, store_all_pulses=False,
                     continue_from=None,
                     skip_initial_forward_propagation=False, norm=None,
-                    overlap=None, limit_thread_pool=None, device=None):
+                    overlap=None, limit_thread_pool=None, device=None,
+                    engine_mode=None):
     """Use Krotov's method to optimize towards the given `objectives`.
 
     Arguments have the meaning documented for the reference
@@ -241,6 +243,10 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     * `storage`, `limit_thread_pool`: accepted and ignored (state stores live
       in HBM; objectives are batched on the GPU).
     * `device`: CUDA device (default: current torch device).
+    * `engine_mode`: None (default) picks the fastest kernels: the fused
+      time-parallel iteration kernel (``kq_krotov_iteration``, one launch per
+      Krotov iteration) where the problem allows, else the sweep kernels;
+      ``'sweeps'`` forces the four-launch sweep sequence.
 
     Returns:
         Result
@@ -304,6 +310,12 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     chi_kind = _BUILTIN_CHI.get(chi_constructor)
     if chi_kind is not None and cp.targets is None:
         chi_kind = None  # built-ins need state targets; let the host raise
+    if engine_mode not in (None, 'sweeps'):
+        raise ValueError("engine_mode must be None or 'sweeps'")
+    # one-launch-per-iteration kernel family (csrc/kq_picard.cuh); falls back
+    # to the sweep kernels when the library declines or does not converge
+    use_fused = (engine_mode is None and shard is None
+                 and gather_comm is None and eng.fused_supported())
     L, NT, K = cp.L, cp.NT, K_total
     has_targets = cp.targets is not None
     templates = [obj.initial_state for obj in objectives]
@@ -435,6 +447,12 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             guess_t.copy_(new_guess)
     deferred = []   # (iteration, tau_t, pulses_t or None, ev0, ev1) fast path
     finished_by_break = False
+    # phi(T) and tau are double-buffered: the iteration reads the previous
+    # ones (chis_ss/sm/hs) while it writes the new ones
+    spare = {'phiT': eng.new_states(),
+             'tau': torch.empty(cp.K, dtype=torch.complex128,
+                                device=eng.device)}
+    any_fused = False
 
     # ---- main loop (optimize.py:393-577) ----------------------------------
     for krotov_iteration in range(iter_start + 1, iter_stop + 1):
@@ -448,10 +466,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
 
         # boundary condition chi(T), normalised (optimize.py:404-410)
         chi_states = chi_norms = None
-        if chi_kind is not None:
-            eng.chi_builtin(chi_kind, phiT, tau_t, K_total=K_total,
-                            shard=shard)
-        else:
+        if chi_kind is None:
             chis = chi_constructor(fw_states_T=fw_states_T,
                                    objectives=objectives, tau_vals=tau_vals)
             chi_norms = list(eng.chi_from_host(
@@ -461,23 +476,68 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         if isinstance(fw_states_T, _LazyFinalStates):
             fw_states_T.freeze(needed=False)
 
-        # backward propagation under the guess pulses (optimize.py:413-425)
-        eng.sweep_backward(guess_t)
-
-        # forward propagation and pulse update (optimize.py:427-500)
+        # forward propagation and pulse update need sigma at the midpoints
         sigma_t = None
         if second_order:
             sig = np.array([
                 float(sigma(tlist[n] + 0.5 * (tlist[n + 1] - tlist[n])))
                 for n in range(NT)])
             sigma_t = eng.upload(sig, torch.float64)
-        phiT = eng.sweep_forward_update(
-            guess_t, opt_t, phiT=phiT, sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
-        tau_t = eng.overlaps(eng.t_targets, phiT) if has_targets else None
+
+        def sweep_iteration():
+            """backward propagation under the guess pulses
+            (optimize.py:413-425), forward propagation and pulse update
+            (:427-500), tau (:503-508): one kernel launch each"""
+            if chi_kind is not None:
+                eng.chi_builtin(chi_kind, phiT, tau_t, K_total=K_total,
+                                shard=shard)
+            eng.sweep_backward(guess_t)
+            new_phiT = eng.sweep_forward_update(
+                guess_t, opt_t, phiT=spare_phiT, sigma_t=sigma_t, Phi0=Phi0,
+                Phi1=Phi1)
+            new_tau = eng.overlaps(eng.t_targets, new_phiT, out=spare_tau) \
+                if has_targets else None
+            return new_phiT, new_tau
+
+        spare_phiT = spare['phiT']
+        spare_tau = spare['tau'] if has_targets else None
+        ran_fused = False
+        if use_fused:
+            try:
+                # chi boundary, both sweeps and tau in ONE launch
+                eng.krotov_iteration(
+                    chi_kind, guess_t, opt_t, phiT, tau_t, spare_phiT,
+                    spare_tau, store_X=info_hook is not None,
+                    sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
+                ran_fused = True
+            except KqError as exc:
+                if 'error -3' not in str(exc):
+                    raise
+                use_fused = False      # outside the fused kernel family
+        if ran_fused and host_loop:
+            fb_epoch, _ = eng.sweep_diagnostics()      # synchronises
+            if fb_epoch == (eng.epoch & 0xFFFFFFFF):
+                # the fixed-point iteration did not converge: outputs are
+                # untouched; repeat with the sweep kernels and stay there
+                ran_fused = use_fused = False
+                eng.clear_fused_failure()
+        if ran_fused:
+            new_phiT, new_tau = spare_phiT, spare_tau
+        else:
+            if chi_kind is None:
+                pass    # chi was uploaded by chi_from_host above
+            new_phiT, new_tau = sweep_iteration()
+        spare['phiT'] = phiT if phiT is not None else eng.new_states()
+        if has_targets:
+            spare['tau'] = tau_t if tau_t is not None else torch.empty(
+                cp.K, dtype=torch.complex128, device=eng.device)
+        phiT, tau_t = new_phiT, new_tau
+        any_fused = any_fused or ran_fused
 
         if not host_loop:
             ev1.record(torch.cuda.current_stream(eng.device))
-            deferred.append((krotov_iteration, tau_t,
+            deferred.append((krotov_iteration,
+                             None if tau_t is None else tau_t.clone(),
                              opt_t.clone() if store_all_pulses else None,
                              ev0, ev1))
             # prepare next iteration (optimize.py:564): guess <- optimized
@@ -579,6 +639,28 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         if st != 0:
             raise RuntimeError("sweep kernel reported exchange failure %d"
                                % st)
+        if any_fused and eng.first_failed_epoch() != 0:
+            # a fused iteration did not converge somewhere along the way; no
+            # hook has seen anything yet, so simply redo the run with the
+            # sweep kernels
+            logger.info("time-parallel iteration did not converge; "
+                        "repeating with the sweep kernels")
+            if shard is not None:
+                shard.close()
+            if gather_comm is not None:
+                gather_comm.close()
+            return optimize_pulses(
+                objectives, pulse_options, tlist, propagator=propagator,
+                chi_constructor=chi_constructor, mu=mu, sigma=sigma,
+                iter_start=iter_start, iter_stop=iter_stop,
+                check_convergence=check_convergence, info_hook=info_hook,
+                storage=storage, parallel_map=parallel_map,
+                store_all_pulses=store_all_pulses,
+                continue_from=continue_from,
+                skip_initial_forward_propagation=(
+                    skip_initial_forward_propagation), norm=norm,
+                overlap=overlap, limit_thread_pool=limit_thread_pool,
+                device=device, engine_mode='sweeps')
         for (it, tau_i, pulses_i, e0, e1) in deferred:
             secs = e0.elapsed_time(e1) * 1e-3
             result.iters.append(it)
