@@ -50,58 +50,78 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+    """SM clock / throttle-reason sampling during the timed region.  NVML is
+    polled from a thread every ~2 ms (the timed region of the fused kernel is
+    only a few milliseconds long, too short for `nvidia-smi -lms`); falls back
+    to one nvidia-smi query if NVML is unavailable."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,"
-             "clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, 'hw_slowdown'), (0x40, 'hw_thermal_slowdown'),
+               (0x20, 'sw_thermal_slowdown'), (0x4, 'sw_power_cap'))
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.thread = index, [], None
+        self.stop_flag = threading.Event()
+        self.nvml = self.handle = None
+        self.sm_max = None
+
+    def _sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        self.rows.append((float(sm), int(mask)))
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index),
-                 '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(
+                self.handle, pynvml.NVML_CLOCK_SM))
+            self._sample()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self._sample()
+                    except Exception:
+                        break
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-                 'sw_power_cap']
-        for r in self.rows:
+        if self.nvml is not None:
+            self.stop_flag.set()
+            if self.thread is not None:
+                self.thread.join(timeout=2)
             try:
-                sm.append(float(r[1]))
-                smax.append(float(r[2]))
-                for name, val in zip(names, r[5:9]):
-                    if val.lower().startswith('active'):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self._sample()
+            except Exception:
+                pass
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({name for _, mask in self.rows
+                              for bit, name in self.REASONS if mask & bit})
+            return {"sm_mhz": float(np.median(sm)) if sm else None,
+                    "sm_max_mhz": self.sm_max, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
+        try:
+            out = subprocess.run(
+                ['nvidia-smi', '-i', str(self.index),
+                 '--query-gpu=clocks.sm,clocks.max.sm',
+                 '--format=csv,noheader,nounits'],
+                capture_output=True, text=True, timeout=10).stdout
+            sm, smax = [float(x) for x in out.strip().split(',')]
+            return {"sm_mhz": sm, "sm_max_mhz": smax, "reasons": [],
+                    "samples": 1, "source": "nvidia-smi (after the run)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+                    "samples": 0}
 
 
 def build_workload():

@@ -236,10 +236,11 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
 // CTA, TC chunks of W steps per objective.  Returns false if the problem is
 // outside what that family handles (the sequential kernels take over).
 struct PicPlan {
-  int Q, TC, W, lw, Wc, grid, block, stride;
+  int Q, TC, W, lw, Wc, lwc, grid, block, stride;
   size_t smem;
 };
-size_t pic_stride(const kq_problem* p) { return (size_t)round_up(p->NT, 64); }
+// slots per mailbox / per owner region: grid * 2^lwc <= 2 NT + 18 * 148
+size_t pic_stride(const kq_problem* p) { return (size_t)2 * round_up(p->NT, 64) + 2688; }
 bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   const int K = p->K, N = p->N, NT = p->NT, NN = N * N;
   if (N < 2 || N > 4 || p->M != 2 || p->L != 1) return false;
@@ -256,8 +257,11 @@ bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   const size_t NTP = (size_t)TC * W;
   const int grid = (K + Q - 1) / Q;
   const int Wc = round_up((NT + grid - 1) / grid, 2);
+  int lwc = 3;
+  while ((1 << lwc) < Wc) ++lwc;
+  if (((size_t)grid << lwc) > pic_stride(p)) return false;
   const size_t smem = 256 * sizeof(double) + 2 * NTP * sizeof(double) + (size_t)Q * NTP * sizeof(double) +
-                      (size_t)3 * Wc * sizeof(double) + (size_t)Q * NTP * N * sizeof(cplx) +
+                      (size_t)4 * Wc * sizeof(double) + (size_t)Q * NTP * N * sizeof(cplx) +
                       (size_t)2 * Q * 8 * NN * sizeof(cplx) + (size_t)Q * 4 * NN * sizeof(cplx);
   if (smem > kSmemBudget) return false;
   pp.Q = Q;
@@ -265,6 +269,7 @@ bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   pp.W = W;
   pp.lw = lw;
   pp.Wc = Wc;
+  pp.lwc = lwc;
   pp.grid = grid;
   pp.block = Q * TC;
   pp.stride = (int)pic_stride(p);
@@ -281,6 +286,7 @@ int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* w
   b.pic_W = pp.W;
   b.pic_lw = pp.lw;
   b.pic_Wc = pp.Wc;
+  b.pic_lwc = pp.lwc;
   b.pic_stride = pp.stride;
   b.pic_maxit = std::min(g_picard_maxit, p->NT + 1);
   b.pic_rtol = 2e-14;

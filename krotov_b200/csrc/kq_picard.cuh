@@ -367,7 +367,7 @@ __device__ __forceinline__ void pic_plan(double x, int& s, int& m, double& inv_s
   inv_s = (s == 1) ? 1.0 : 1.0 / (double)s;
 }
 
-// shared: [scratch 256][seps NTP][dsm Q*NTP][own 3*Wc][eta Q*NTP*N cplx]
+// shared: [scratch 256][seps NTP][dsm Q*NTP][own 4*Wc][eta Q*NTP*N cplx]
 //         (seps is double-buffered: 2*NTP) [wtot 2*Q*WPO*NN cplx][terms Q*4*NN (N = 4)]
 template <int N, int FSEL, bool SECOND, typename G, int WT>
 __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArgs a) {
@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   const bool single = (nblk == 1);
   const int Wl = (WT > 0) ? WT : W;      // chunk length (compile-time when WT > 0)
   const int Wc = a.pic_Wc;               // time slice reduced by each CTA
+  const int lwc = a.pic_lwc, WcP = 1 << lwc;   // slice length padded to a power of two (>= 8: one 128-byte line of slots)
   const int n_lo = blockIdx.x * Wc;
 
   double* scratch = reinterpret_cast<double*>(smem_raw);   // [256]
@@ -395,7 +396,8 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   double* own_sl = dsm + (size_t)Q * NTP;                   // [Wc] S/lambda of the owned slice
   double* own_g = own_sl + Wc;                              // [Wc] guess pulse
   double* own_dt = own_g + Wc;                              // [Wc] dt
-  cplx* eta = reinterpret_cast<cplx*>(own_dt + Wc);         // [Q][W][N][TC]
+  double* own_eps = own_dt + Wc;                            // [Wc] new pulse values of the slice
+  cplx* eta = reinterpret_cast<cplx*>(own_eps + Wc);        // [Q][W][N][TC]
   cplx* wtot = eta + (size_t)Q * NTP * N;                   // [2][Q][WPO][NN] (by round parity)
   G* sterms = reinterpret_cast<G*>(wtot + (size_t)2 * Q * KQ_PIC_WPO * NN);   // [Q][4][NN] (N = 4)
 
@@ -629,9 +631,8 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   const int t_last = (NT - 1) >> lw;       // thread whose chunk ends the sweep
   const uint32_t tag0 = a.tag_base;
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-  const bool direct = (Q == 1) && !single;   // pass B publishes its partial sums itself
   bool failed = false, converged = false;
-  double ga_acc = 0.0;   // single: this thread's share; multi: lane 0 of each warp
+  double ga_acc = 0.0;   // this thread's share of the g_a integral (last update)
   double em = gmax;      // max |eps| of the previous iterate (plans the next evaluation)
   double dm = kInf, en = gmax;   // this thread's share of max |eps_it - eps_{it-1}|, max |eps_it|
   cplx y[N];
@@ -647,21 +648,26 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       const uint32_t tagp = tag0 + (uint32_t)(it - 1);
       dm = 0.0;
       en = 0.0;
-      for (int nb = tid; nb < NT; nb += 4 * BT) {
+      const KqSlot* mybox = a.pic_eps + (size_t)blockIdx.x * a.pic_stride;
+      const int nslot = nblk << lwc;
+      for (int jb = tid; jb < nslot; jb += 4 * BT) {
         const KqSlot* ptr[4];
         bool act[4];
         double ev[4];
+        int nn[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int n = nb + u * BT;
-          act[u] = n < NT;
-          ptr[u] = &a.pic_eps[(size_t)blockIdx.x * a.pic_stride + (act[u] ? n : 0)];
+          const int j = jb + u * BT;
+          const int ni = j & (WcP - 1);
+          nn[u] = (j >> lwc) * Wc + ni;
+          act[u] = (j < nslot) && (ni < Wc) && (nn[u] < NT);
+          ptr[u] = mybox + (act[u] ? j : 0);
         }
         slot_wait_batch<4>(ptr, act, tagp, ev, failed);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int n = nb + u * BT;
           if (act[u]) {
+            const int n = nn[u];
             const int idx = (n & (W - 1)) * TC + (n >> lw);
             double e_new = ev[u];
             if (e_new == kInf) en = kInf;   // an owner's exchange timed out
@@ -723,7 +729,6 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       converged = !exch_fail && resolved && (dmax <= a.pic_rtol * emax);
       stop = converged || exch_fail || it >= a.pic_maxit;
       if (exch_fail) em = kInf; else em = emax;
-      const uint32_t tag = tag0 + (uint32_t)it;
       // ---- pass B: overlaps at every step of the chunk ------------------------
 #pragma unroll
       for (int w = 0; w < Wl; ++w) {
@@ -758,7 +763,6 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
 #pragma unroll
             for (int i = 0; i < N; ++i) a.store[((size_t)n * K + k) * N + i] = y[i];
           }
-          if (direct && !stop) slot_store(&a.pic_part[(size_t)n * nblk + blockIdx.x], d, tag);
           if (KEEP) {
             ops[WT > 0 ? w : 0].template apply<1>(y, s, m);
           } else {
@@ -770,7 +774,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
             op1[0].template apply<1>(y, s, m);
           }
         }
-        if (!direct) dsm[(size_t)g.q * NTP + w * TC + g.t] = d;
+        dsm[(size_t)g.q * NTP + w * TC + g.t] = d;
       }
     }
     KQ_TICK(3)
@@ -799,46 +803,84 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       __syncthreads();
     } else {
       const uint32_t tag = tag0 + (uint32_t)it;
-      if (!direct) {
-        // stage 1: this CTA's partial sums for every time step
-        __syncthreads();
-        for (int n = tid; n < NT; n += BT) {
+      const int nslot = nblk << lwc;
+      // stage 1: this CTA's partial sums, one full 128-byte line of slots per
+      // owner (layout [owner][cta][ni])
+      __syncthreads();
+      for (int j = tid; j < nslot; j += BT) {
+        const int o = j >> lwc, ni = j & (WcP - 1), n = o * Wc + ni;
+        if (ni < Wc && n < NT) {
           const int idx = (n & (W - 1)) * TC + (n >> lw);
           double d1 = dsm[idx];
           for (int qq = 1; qq < Q; ++qq) d1 += dsm[(size_t)qq * NTP + idx];
-          slot_store(&a.pic_part[(size_t)n * nblk + blockIdx.x], d1, tag);
+          slot_store(&a.pic_part[(((size_t)o * nblk + blockIdx.x) << lwc) + ni], d1, tag);
         }
       }
       KQ_TICK(4)
-      // stage 2: reduce time slice [n_lo, n_lo + Wc) over all CTAs (fixed order)
-      for (int ni = warp; ni < Wc; ni += nwarps) {
-        const int n = n_lo + ni;
-        if (n < NT) {
-          constexpr int NB = (kPicBlocksMax + 31) / 32;
-          const KqSlot* ptr[NB];
-          bool act[NB];
-          double pv[NB];
+      // stage 2: reduce the own time slice over all CTAs in a fixed order
+      const KqSlot* mine = a.pic_part + (((size_t)blockIdx.x * nblk) << lwc);
+      if (WcP <= 16) {
+        // every thread sums the CTAs c' = (tid + u BT) / WcP for ni = tid % WcP,
+        // then lanes with equal ni, then the warps
+        double v = 0.0;
+        for (int jb = tid; jb < nslot; jb += 4 * BT) {
+          const KqSlot* ptr[4];
+          bool act[4];
+          double pv[4];
 #pragma unroll
-          for (int u = 0; u < NB; ++u) {
-            const int cb = lane + 32 * u;
-            act[u] = cb < nblk;
-            ptr[u] = &a.pic_part[(size_t)n * nblk + (act[u] ? cb : 0)];
+          for (int u = 0; u < 4; ++u) {
+            const int j = jb + u * BT;
+            const int ni = j & (WcP - 1);
+            act[u] = (j < nslot) && (ni < Wc) && (n_lo + ni < NT);
+            ptr[u] = mine + (act[u] ? j : 0);
           }
-          slot_wait_batch<NB>(ptr, act, tag, pv, failed);
-          double acc = 0.0;
+          slot_wait_batch<4>(ptr, act, tag, pv, failed);
 #pragma unroll
-          for (int u = 0; u < NB; ++u) acc += pv[u];
-          acc = warp_allreduce_sum(acc);
-          const double sl = own_sl[ni];
-          // a failed wait publishes +inf: every CTA then stops in the next round
-          const double e_new = failed ? kInf : __dadd_rn(own_g[ni], __dmul_rn(sl, acc));
-          if (lane == 0)
-            ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), own_dt[ni]));
-          // push the new value into every CTA's own mailbox (no line is polled by
-          // more than one CTA)
-          for (int cb = lane; cb < nblk; cb += 32)
-            slot_store(&a.pic_eps[(size_t)cb * a.pic_stride + n], e_new, tag);
+          for (int u = 0; u < 4; ++u) v += pv[u];
         }
+        for (int o = WcP; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        double* red = scratch + 128;   // [nwarps][16]
+        if (lane < WcP) red[warp * 16 + lane] = v;
+        __syncthreads();
+        if (tid < Wc && n_lo + tid < NT) {
+          double acc = red[tid];
+          for (int w = 1; w < nwarps; ++w) acc += red[w * 16 + tid];
+          const double sl = own_sl[tid];
+          ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), own_dt[tid]));
+          own_eps[tid] = __dadd_rn(own_g[tid], __dmul_rn(sl, acc));
+        }
+      } else {
+        for (int ni = tid; ni < Wc; ni += BT) {
+          if (n_lo + ni < NT) {
+            double acc = 0.0;
+            for (int cb = 0; cb < nblk; cb += 4) {
+              const KqSlot* ptr[4];
+              bool act[4];
+              double pv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                act[u] = cb + u < nblk;
+                ptr[u] = mine + (((size_t)(act[u] ? cb + u : 0)) << lwc) + ni;
+              }
+              slot_wait_batch<4>(ptr, act, tag, pv, failed);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) acc += pv[u];
+            }
+            const double sl = own_sl[ni];
+            ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), own_dt[ni]));
+            own_eps[ni] = __dadd_rn(own_g[ni], __dmul_rn(sl, acc));
+          }
+        }
+      }
+      // a failed wait publishes +inf: every CTA then stops in the next round
+      const bool any_failed = __syncthreads_or(failed);
+      // push the new values into every CTA's own mailbox (layout
+      // [cta][owner][ni]: full lines, no line is polled by more than one CTA)
+      for (int j = tid; j < nslot; j += BT) {
+        const int cb = j >> lwc, ni = j & (WcP - 1);
+        if (ni < Wc && n_lo + ni < NT)
+          slot_store(&a.pic_eps[(size_t)cb * a.pic_stride + ((size_t)blockIdx.x << lwc) + ni],
+                     any_failed ? kInf : own_eps[ni], tag);
       }
       KQ_TICK(5)
     }
@@ -861,7 +903,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     if (tid == 0) a.g_a[0] = ga;
   } else {
     const uint32_t tagf = tag0 + (uint32_t)a.pic_maxit + 1u;
-    double ga = block_sum((lane == 0) ? ga_acc : 0.0, scratch + 192);
+    double ga = block_sum(ga_acc, scratch + 192);
     if (tid == 0) slot_store(&a.pic_ga[blockIdx.x], ga, tagf);
     if (blockIdx.x == 0 && warp == 0) {
       double acc = 0.0;

@@ -56,8 +56,8 @@ struct KqSweepArgs {
   // time chunks of pic_W steps; cross-CTA exchange through tagged slots
   int pic_Q, pic_TC, pic_W, pic_maxit, pic_stride;
   double pic_rtol;
-  KqSlot* pic_part;   // [gridDim.x][pic_stride] per-CTA partial sums over its objectives
-  KqSlot* pic_eps;    // [gridDim.x][pic_stride] updated pulse, one mailbox per CTA
+  KqSlot* pic_part;   // [owner][cta][2^pic_lwc] per-CTA partial sums over its objectives
+  KqSlot* pic_eps;    // [cta][pic_stride]: mailbox of updated pulse values [owner][2^pic_lwc]
   KqSlot* pic_ga;     // [gridDim.x] per-CTA share of the g_a integral
   // sequential kernels launched as the fall-back of the time-parallel sweep run
   // only if status[1] == cond_epoch (0 = unconditional)
@@ -66,6 +66,7 @@ struct KqSweepArgs {
   // fused Krotov iteration (k_krotov_picard): chi boundary and backward sweep
   // inside the kernel
   int pic_lw, pic_Wc;        // log2(pic_W); time steps reduced per CTA (even)
+  int pic_lwc;               // log2 of the slice length padded to a power of two >= 8
   int pic_bw;                // 1: backward sweep in the kernel (chi from chi_kind / chiT), 0: chi from X
   int chi_kind, K_total;     // KQ_CHI_* or -1 (normalised chiT + chi_norms given)
   const cplx* ops_adj;

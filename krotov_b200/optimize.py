@@ -41,6 +41,48 @@ _BUILTIN_CHI = {
 }
 
 
+class _PackedResults:
+    """Pulses | g_a | tau | status words of one iteration in ONE device buffer
+    (two of them, alternating), so that an iteration with host hooks needs a
+    single device->host copy into pinned memory and one synchronisation."""
+
+    def __init__(self, torch, device, L, NT, K):
+        def up16(x):
+            return (x + 15) // 16 * 16
+        self.torch, self.L, self.NT, self.K = torch, L, NT, K
+        self.o_ga = up16(L * NT * 8)
+        self.o_tau = self.o_ga + up16(max(L, 1) * 8)
+        self.o_diag = self.o_tau + K * 16
+        self.nbytes = self.o_diag + 16
+        self.dev = [torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
+                    for _ in (0, 1)]
+        self.host = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
+        self.hnp = self.host.numpy()
+        self.views = [self._views(r) for r in self.dev]
+
+    def _views(self, r):
+        t, L, NT, K = self.torch, self.L, self.NT, self.K
+        return dict(
+            pulses=r[:L * NT * 8].view(t.float64).view(L, NT),
+            g_a=r[self.o_ga:self.o_ga + max(L, 1) * 8].view(t.float64),
+            tau=r[self.o_tau:self.o_tau + K * 16].view(t.complex128),
+            diag=r[self.o_diag:self.o_diag + 16])
+
+    def fetch(self, i, eng):
+        """Copy buffer `i` (after appending the engine's status words) to
+        the host; returns (pulses [L][NT], g_a [L], tau [K], status words)."""
+        self.views[i]['diag'].copy_(eng.workspace[:16])
+        self.host.copy_(self.dev[i], non_blocking=True)
+        self.torch.cuda.current_stream(eng.device).synchronize()
+        eng.d2h_bytes += self.nbytes
+        h, L, NT, K = self.hnp, self.L, self.NT, self.K
+        pulses = h[:L * NT * 8].view(np.float64).reshape(L, NT)
+        g_a = h[self.o_ga:self.o_ga + max(L, 1) * 8].view(np.float64)
+        tau = h[self.o_tau:self.o_tau + K * 16].view(np.complex128)
+        diag = h[self.o_diag:self.o_diag + 16].view(np.int32)
+        return pulses, g_a, tau, diag
+
+
 class _LazyStates:
     """Per-objective view ``store[k][n]`` of a device state store
     ``[nt, K, N]``; the tensor is downloaded once, on first access.  Valid
@@ -453,6 +495,11 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
              'tau': torch.empty(cp.K, dtype=torch.complex128,
                                 device=eng.device)}
     any_fused = False
+    # hooked iterations: everything the host needs in one pinned copy
+    packed = None
+    if host_loop and shard is None:
+        packed = _PackedResults(torch, eng.device, L, NT, cp.K)
+    ri = 0
 
     # ---- main loop (optimize.py:393-577) ----------------------------------
     for krotov_iteration in range(iter_start + 1, iter_stop + 1):
@@ -499,6 +546,12 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 if has_targets else None
             return new_phiT, new_tau
 
+        if packed is not None:
+            # this iteration's outputs live in one buffer
+            pv = packed.views[ri]
+            opt_t = pv['pulses']
+            spare['tau'] = pv['tau']
+            eng.g_a = pv['g_a']
         spare_phiT = spare['phiT']
         spare_tau = spare['tau'] if has_targets else None
         ran_fused = False
@@ -514,12 +567,18 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 if 'error -3' not in str(exc):
                     raise
                 use_fused = False      # outside the fused kernel family
+        fetched = None
         if ran_fused and host_loop:
-            fb_epoch, _ = eng.sweep_diagnostics()      # synchronises
+            if packed is not None:
+                fetched = packed.fetch(ri, eng)        # synchronises
+                fb_epoch = int(fetched[3][1])
+            else:
+                fb_epoch, _ = eng.sweep_diagnostics()  # synchronises
             if fb_epoch == (eng.epoch & 0xFFFFFFFF):
                 # the fixed-point iteration did not converge: outputs are
                 # untouched; repeat with the sweep kernels and stay there
                 ran_fused = use_fused = False
+                fetched = None
                 eng.clear_fused_failure()
         if ran_fused:
             new_phiT, new_tau = spare_phiT, spare_tau
@@ -549,10 +608,20 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         # previous one and are already on the host
         guess_pulses_host = optimized_pulses if krotov_iteration > \
             first_iteration else guess_pulses
-        optimized_pulses = pulses_to_host(opt_t)   # synchronises the stream
-        g_a_integrals[:] = eng.download(eng.g_a)[:L]
-        tau_vals = tau_to_host(tau_t)
-        st = eng.status()
+        if packed is not None:
+            if fetched is None:
+                fetched = packed.fetch(ri, eng)    # synchronises the stream
+            ri ^= 1
+            optimized_pulses = [fetched[0][l].copy() for l in range(L)]
+            g_a_integrals[:] = fetched[1][:L]
+            tau_vals = fetched[2].copy() if tau_t is not None \
+                else np.array([None] * K)
+            st = int(fetched[3][0])
+        else:
+            optimized_pulses = pulses_to_host(opt_t)   # synchronises
+            g_a_integrals[:] = eng.download(eng.g_a)[:L]
+            tau_vals = tau_to_host(tau_t)
+            st = eng.status()
         if st != 0:
             raise RuntimeError("sweep kernel reported exchange failure %d"
                                % st)
