@@ -320,6 +320,7 @@ def run_ours(args):
     # allows, else chi boundary / backward sweep / fused sweep / tau launches
     fused = (args.engine != 'sweeps' and world == 1 and eng.fused_supported())
     spare_phiT, spare_tau = eng.new_states(), torch.empty_like(tau_t)
+    hint = [False]   # after the first iteration opt_t holds the previous guess
 
     def one_iteration(ev=None):
         nonlocal guess_t, opt_t, phiT, tau_t, spare_phiT, spare_tau, fused
@@ -330,7 +331,9 @@ def run_ours(args):
             try:
                 eng.krotov_iteration(
                     None if fixed_chi is not None else wl.chi, guess_t, opt_t,
-                    phiT, tau_t, spare_phiT, spare_tau)
+                    phiT, tau_t, spare_phiT, spare_tau,
+                    prev_guess_t=opt_t if hint[0] else None)
+                hint[0] = True
             except krotov._lib.KqError:
                 fused = False
                 return one_iteration(ev)

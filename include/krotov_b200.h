@@ -188,6 +188,10 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses,
  * causal fixed-point iteration that is parallel in time), tau_out[k] =
  * <target_k|phi_k(T)> (if targets and tau_out are given), phiT_out, g_a.
  * chi_out / chi_norms_out (may be NULL) receive the normalised boundary states.
+ * prev_guess_pulses (may be NULL, may alias opt_pulses) = the guess pulses of
+ * the Krotov iteration before: the fixed-point iteration then starts from
+ * guess + (guess - prev_guess) instead of guess (a hint only: the result does
+ * not depend on it beyond rounding).
  * sigma/Phi0/Phi1 as in kq_sweep_forward_update.  tau_in/phiT_in must not alias
  * tau_out/phiT_out.  Returns KQ_ERR_UNSUPPORTED when the problem is outside the
  * family (N in 2..4, two generator terms, one pulse, single GPU, state stores
@@ -200,7 +204,8 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
                         const kq_c128* targets, const double* weights,
                         const kq_c128* chiT, const double* chi_norms,
                         const kq_c128* tau_in, const kq_c128* phiT_in,
-                        const double* guess_pulses, double* opt_pulses,
+                        const double* guess_pulses,
+                        const double* prev_guess_pulses, double* opt_pulses,
                         const kq_c128* phi0, kq_c128* phiT_out,
                         kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
                         double* chi_norms_out, const double* sigma,

@@ -694,8 +694,8 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
 int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
                         const kq_c128* targets, const double* weights, const kq_c128* chiT,
                         const double* chi_norms, const kq_c128* tau_in, const kq_c128* phiT_in,
-                        const double* guess_pulses, double* opt_pulses, const kq_c128* phi0,
-                        kq_c128* phiT_out, kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
+                        const double* guess_pulses, const double* prev_guess_pulses,
+                        double* opt_pulses, const kq_c128* phi0, kq_c128* phiT_out, kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
                         double* chi_norms_out, const double* sigma, const kq_c128* Phi0,
                         kq_c128* Phi1, double* g_a, void* workspace, uint32_t epoch,
                         void* stream) {
@@ -733,6 +733,7 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   a.Phi0 = reinterpret_cast<const cplx*>(Phi0);
   a.g_a = g_a;
   a.pic_bw = 1;
+  a.pic_hint = prev_guess_pulses;
   a.chi_kind = chi_kind;
   a.K_total = K_total;
   a.chiT = reinterpret_cast<const cplx*>(chiT);

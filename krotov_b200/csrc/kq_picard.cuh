@@ -415,6 +415,9 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   const bool valid = k < K;
   if (!valid) k = K - 1;
   cplx* wt = wtot + (size_t)g.q * KQ_PIC_WPO * NN;
+  // 32-bit shared-memory indices of this thread's entries
+  const int eta_base = g.q * W * N * TC + g.t;
+  const int dsm_base = g.q * NTP + g.t;
 
   // optional per-phase cycle counts (thread 0 of CTA 0): kq_set_option("picard_timing", 1)
   const bool timing = a.pic_timing && tid == 0 && blockIdx.x == 0;
@@ -451,6 +454,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
 
   // first iterate (the guess pulse), the owned slice's scalars, norm bounds
   double gmax = 0.0, dtmax = 0.0;
+  // round 1 evaluates the guess pulse (also the backward sweep's pulse)
   for (int n = tid; n < NTP; n += BT) {
     const double e = (n < NT) ? a.pulses[n] : 0.0;
     seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         cplx acc = c_zero();
 #pragma unroll
         for (int r = 0; r < N; ++r) acc = c_fma_conj(mu[cc * N + r], y[r], acc);
-        eta[(((size_t)g.q * W + w) * N + cc) * TC + g.t] =
+        eta[eta_base + (w * N + cc) * TC] =
             (n < NT) ? make_double2(acc.x * cnorm, acc.y * cnorm) : c_zero();
       }
     }
@@ -601,10 +605,26 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         cplx acc = c_zero();
 #pragma unroll
         for (int r = 0; r < N; ++r) acc = c_fma_conj(mu[cc * N + r], chi[r], acc);
-        eta[(((size_t)g.q * W + w) * N + cc) * TC + g.t] =
+        eta[eta_base + (w * N + cc) * TC] =
             make_double2(acc.x * cnorm, acc.y * cnorm);
       }
     }
+  }
+  // first iterate of the fixed-point iteration: the guess pulse, or -- with the
+  // guess of the iteration before -- the guess plus the previous update
+  // (successive Krotov updates are similar: saves about one round)
+  if (a.pic_hint) {
+    __syncthreads();   // the backward sweep has read the guess pulse from this buffer
+    double hmax = 0.0;
+    for (int n = tid; n < NT; n += BT) {
+      const double gn = a.pulses[n];
+      const double e = gn + (gn - a.pic_hint[n]);
+      seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
+      hmax = fmax(hmax, fabs(e));
+    }
+    double unused2 = 0.0;
+    block_max2(hmax, unused2, scratch + 128);
+    gmax = fmax(gmax, hmax);
   }
   __syncthreads();   // wtot is reused by the forward scans
   KQ_TICK(1)
@@ -634,6 +654,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   bool failed = false, converged = false;
   double ga_acc = 0.0;   // this thread's share of the g_a integral (last update)
   double em = gmax;      // max |eps| of the previous iterate (plans the next evaluation)
+  double dm_prev = kInf;         // CTA-wide max |eps_{it-1} - eps_{it-2}|
   double dm = kInf, en = gmax;   // this thread's share of max |eps_it - eps_{it-1}|, max |eps_it|
   cplx y[N];
   int it = 0;
@@ -726,7 +747,14 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       // CTA-uniform (and grid-uniform: every CTA sees the same pulse) decisions
       const bool exch_fail = !(emax < kInf);
       const bool resolved = emax <= em_bound;        // the plan covered this iterate
-      converged = !exch_fail && resolved && (dmax <= a.pic_rtol * emax);
+      // error of eps_it: the last change, or -- while the iteration contracts --
+      // its extrapolation rho/(1-rho) * change with rho = ratio of the last two
+      // changes (stops one exchange round earlier)
+      const double rho = (dm_prev < kInf && dm_prev > 0.0) ? dmax / dm_prev : 1.0;
+      const bool small = (dmax <= a.pic_rtol * emax) ||
+                         (rho < 0.25 && dmax * rho <= (1.0 - rho) * 0.2 * a.pic_rtol * emax);
+      dm_prev = dmax;
+      converged = !exch_fail && resolved && small;
       stop = converged || exch_fail || it >= a.pic_maxit;
       if (exch_fail) em = kInf; else em = emax;
       // ---- pass B: overlaps at every step of the chunk ------------------------
@@ -736,7 +764,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         double e0 = 0.0, e1 = 0.0;
 #pragma unroll
         for (int cc = 0; cc < N; ++cc) {
-          const cplx et = eta[(((size_t)g.q * W + w) * N + cc) * TC + g.t];
+          const cplx et = eta[eta_base + (w * N + cc) * TC];
           if (cc & 1)
             e1 += c_im_conj_mul(et, y[cc]);
           else
@@ -774,7 +802,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
             op1[0].template apply<1>(y, s, m);
           }
         }
-        dsm[(size_t)g.q * NTP + w * TC + g.t] = d;
+        dsm[dsm_base + w * TC] = d;
       }
     }
     KQ_TICK(3)
@@ -788,7 +816,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       for (int n = tid; n < NT; n += BT) {
         const int idx = (n & (W - 1)) * TC + (n >> lw);
         double d1 = dsm[idx];
-        for (int qq = 1; qq < Q; ++qq) d1 += dsm[(size_t)qq * NTP + idx];
+        for (int qq = 1; qq < Q; ++qq) d1 += dsm[qq * NTP + idx];
         const double sl = own_sl[n], dtn = own_dt[n];
         double e_new = __dadd_rn(own_g[n], __dmul_rn(sl, d1));
         ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), dtn));
@@ -812,7 +840,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         if (ni < Wc && n < NT) {
           const int idx = (n & (W - 1)) * TC + (n >> lw);
           double d1 = dsm[idx];
-          for (int qq = 1; qq < Q; ++qq) d1 += dsm[(size_t)qq * NTP + idx];
+          for (int qq = 1; qq < Q; ++qq) d1 += dsm[qq * NTP + idx];
           slot_store(&a.pic_part[(((size_t)o * nblk + blockIdx.x) << lwc) + ni], d1, tag);
         }
       }
@@ -901,19 +929,17 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   if (single) {
     const double ga = block_sum(ga_acc, scratch + 192);
     if (tid == 0) a.g_a[0] = ga;
-  } else {
-    const uint32_t tagf = tag0 + (uint32_t)a.pic_maxit + 1u;
-    double ga = block_sum(ga_acc, scratch + 192);
-    if (tid == 0) slot_store(&a.pic_ga[blockIdx.x], ga, tagf);
-    if (blockIdx.x == 0 && warp == 0) {
-      double acc = 0.0;
-      for (int cb = lane; cb < nblk; cb += 32) acc += slot_wait(&a.pic_ga[cb], tagf, failed);
-      acc = warp_allreduce_sum(acc);
-      if (lane == 0) {
-        a.g_a[0] = acc;
-        if (failed) atomicExch(a.status, (int)-4);
-      }
+  } else if (blockIdx.x == 0) {
+    // g_a = sum_n (S/lambda) d_n^2 dt_n with (S/lambda) d_n = eps_n - guess_n
+    // (every CTA holds the whole pulse: no exchange needed)
+    double ga = 0.0;
+    for (int n = tid; n < NT; n += BT) {
+      const double sl = a.shape[n] / lam;
+      const double df = seps[(n & (W - 1)) * TC + (n >> lw)] - a.pulses[n];
+      if (sl > 0.0) ga += (df * df) / sl * a.dt[n];
     }
+    ga = block_sum(ga, scratch + 192);
+    if (tid == 0) a.g_a[0] = ga;
   }
   if (tid == 0 && blockIdx.x == 0) a.status[2] = it;   // Picard iterations used (diagnostics)
   KQ_TICK(8)

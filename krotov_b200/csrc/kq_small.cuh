@@ -76,6 +76,7 @@ struct KqSweepArgs {
   const cplx* tau_in;
   cplx* tau_out;
   const cplx* phiT_in;
+  const double* pic_hint;    // [NT] guess pulse of the iteration before, or null
   cplx* Xout;                // [NT+1][K][N] or null
   cplx* chi_out;             // [K][N] or null
   double* chi_norms_out;     // [K] or null

@@ -185,13 +185,14 @@ class SweepEngine:
 
     def krotov_iteration(self, chi_kind, guess_t, opt_t, phiT_in, tau_in,
                          phiT_out, tau_out, store_X=False, sigma_t=None,
-                         Phi0=None, Phi1=None):
+                         Phi0=None, Phi1=None, prev_guess_t=None):
         """One whole Krotov iteration (optimize.py:393-508) in one launch of
         the time-parallel kernel family: chi boundary (`chi_kind` 're', 'ss',
         'sm', 'hs', or None for the states already in :attr:`chi` /
         :attr:`chi_norms`), backward sweep, update + forward sweep, tau.
         Raises :class:`KqError` (KQ_ERR_UNSUPPORTED) if the problem is outside
-        that family."""
+        that family.  `prev_guess_t` (may be `opt_t`): guess pulses of the
+        iteration before, a starting hint for the fixed-point iteration."""
         self.epoch += 1
         kind = -1 if chi_kind is None else CHI_KINDS[chi_kind]
         check(self.lib.kq_krotov_iteration(
@@ -199,8 +200,8 @@ class SweepEngine:
             _ptr(self.t_weights),
             _ptr(self.chi if kind < 0 else None),
             _ptr(self.chi_norms if kind < 0 else None),
-            _ptr(tau_in), _ptr(phiT_in), _ptr(guess_t), _ptr(opt_t),
-            _ptr(self.t_psi0), _ptr(phiT_out), _ptr(tau_out),
+            _ptr(tau_in), _ptr(phiT_in), _ptr(guess_t), _ptr(prev_guess_t),
+            _ptr(opt_t), _ptr(self.t_psi0), _ptr(phiT_out), _ptr(tau_out),
             _ptr(self.X if store_X else None),
             _ptr(None if kind < 0 else self.chi),
             _ptr(None if kind < 0 else self.chi_norms),

@@ -495,6 +495,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
              'tau': torch.empty(cp.K, dtype=torch.complex128,
                                 device=eng.device)}
     any_fused = False
+    n_fused = 0             # iterations done by the one-launch kernel
+    prev_guess_ref = None   # device pulses the previous iteration started from
     # hooked iterations: everything the host needs in one pinned copy
     packed = None
     if host_loop and shard is None:
@@ -554,6 +556,9 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             eng.g_a = pv['g_a']
         spare_phiT = spare['phiT']
         spare_tau = spare['tau'] if has_targets else None
+        # the buffer about to receive the optimized pulses still holds the
+        # guess of the iteration before: a starting hint for the fused kernel
+        prev_guess_t = prev_guess_ref
         ran_fused = False
         if use_fused:
             try:
@@ -561,7 +566,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 eng.krotov_iteration(
                     chi_kind, guess_t, opt_t, phiT, tau_t, spare_phiT,
                     spare_tau, store_X=info_hook is not None,
-                    sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
+                    sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1,
+                    prev_guess_t=prev_guess_t)
                 ran_fused = True
             except KqError as exc:
                 if 'error -3' not in str(exc):
@@ -592,6 +598,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 cp.K, dtype=torch.complex128, device=eng.device)
         phiT, tau_t = new_phiT, new_tau
         any_fused = any_fused or ran_fused
+        n_fused += int(ran_fused)
+        prev_guess_ref = guess_t
 
         if not host_loop:
             ev1.record(torch.cuda.current_stream(eng.device))
@@ -752,6 +760,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     result.optimized_controls = [
         pulse_onto_tlist(np.asarray(p)) for p in result.optimized_controls]
     result.gpu_launches = eng.launches
+    result.fused_iterations = n_fused
     result.h2d_bytes, result.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
     if shard is not None:
         shard.close()

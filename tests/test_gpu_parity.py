@@ -429,3 +429,106 @@ def test_two_level_kernel_variants_vs_oracle(krotov, case):
             assert rel(res.all_pulses[it],
                        rec[it]['optimized_pulses']) < PULSE_RTOL, case
     assert rel(results[0].all_pulses[2], results[1].all_pulses[2]) < 1e-13
+
+
+# ---------------------------------------------------------------------------
+# One-launch-per-iteration kernel family (csrc/kq_picard.cuh)
+
+def _engine_modes(krotov, wl, iters, **kw):
+    out = {}
+    for mode in (None, 'sweeps'):
+        out[mode] = krotov.optimize_pulses(
+            wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+            propagator=krotov.propagators.expm,
+            chi_constructor=chi_of(krotov, wl), iter_stop=iters,
+            store_all_pulses=True, engine_mode=mode, **kw)
+    return out
+
+
+@pytest.mark.parametrize('name', ['C1', 'C2', 'C3', 'C4'])
+def test_fused_iteration_matches_sweep_kernels(krotov, name):
+    """The time-parallel fused iteration (one launch: chi boundary, backward
+    scan, fixed-point update sweep, tau) against the sequential sweep kernels:
+    same pulses, tau and final states to rounding; and it is really used."""
+    wl = {'C1': lambda: krotov.workloads.tls_state_to_state(),
+          'C2': lambda: krotov.workloads.transmon_xgate(),
+          'C3': lambda: krotov.workloads.two_qubit_gate(nt=500),
+          'C4': lambda: krotov.workloads.tls_ensemble(K=128, nt=1000)}[name]()
+    res = _engine_modes(krotov, wl, 3)
+    assert res[None].fused_iterations == 3
+    assert res['sweeps'].fused_iterations == 0
+    for it in (1, 2, 3):
+        assert rel(res[None].all_pulses[it],
+                   res['sweeps'].all_pulses[it]) < 1e-12, (name, it)
+    assert np.allclose(res[None].tau_vals[-1].astype(complex),
+                       res['sweeps'].tau_vals[-1].astype(complex),
+                       rtol=0, atol=1e-12)
+    a = np.array([np.asarray(s).ravel() for s in res[None].states])
+    b = np.array([np.asarray(s).ravel() for s in res['sweeps'].states])
+    assert np.allclose(a, b, rtol=0, atol=1e-12)
+
+
+def test_fused_iteration_hooks_see_backward_states(krotov, golden):
+    """With an info_hook the fused kernel also stores the backward states and
+    fills g_a / tau like the sweep kernels (golden vectors of the reference)."""
+    g = golden('tls_fixture_qobj')
+    res, rec = run_gpu(krotov, krotov.workloads.tls_reference_fixture(), 3,
+                       keep_states=True)
+    assert res.fused_iterations == 3
+    check_against_golden(rec, g, 3)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('hooked', [False, True])
+def test_fused_iteration_non_convergence_falls_back(krotov, hooked):
+    """If the fixed-point iteration is not allowed enough rounds the kernel
+    leaves its outputs untouched and the sweep kernels take over, with
+    identical results (hooked: per iteration; unhooked: the run is redone)."""
+    from oracle import krotov_oracle as orc
+    lib = krotov._lib.load()
+    wl = krotov.workloads.tls_ensemble(K=8, nt=100)
+    low = wl.lowered()
+    rec = orc.optimize(low['terms'], low['psi0'], low['targets'],
+                       low['pulses'], low['shapes'], low['lambdas'],
+                       low['tlist'], orc.chis_re, iter_stop=2)
+    assert lib.kq_set_option(b"picard_maxit", 3) == 0
+    try:
+        seen = []
+        kw = dict(info_hook=lambda **k: seen.append(k['iteration'])) \
+            if hooked else {}
+        res = krotov.optimize_pulses(
+            wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+            propagator=krotov.propagators.expm,
+            chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+            store_all_pulses=True, **kw)
+    finally:
+        lib.kq_set_option(b"picard_maxit", 64)
+    assert res.fused_iterations == 0
+    for it in (1, 2):
+        assert rel(res.all_pulses[it],
+                   rec[it]['optimized_pulses']) < PULSE_RTOL
+    if hooked:
+        assert seen == [0, 1, 2]
+
+
+def test_fused_iteration_custom_chi_and_weights(krotov):
+    """Host chi_constructor (states uploaded, chi_kind = -1) through the
+    fused kernel, against the oracle."""
+    from oracle import krotov_oracle as orc
+    wl = krotov.workloads.tls_ensemble(K=5, nt=80)
+    low = wl.lowered()
+
+    def my_chi(fw_states_T, objectives, tau_vals):
+        return krotov.functionals.chis_re(fw_states_T, objectives, tau_vals)
+
+    res = krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm, chi_constructor=my_chi,
+        iter_stop=2, store_all_pulses=True)
+    assert res.fused_iterations == 2
+    rec = orc.optimize(low['terms'], low['psi0'], low['targets'],
+                       low['pulses'], low['shapes'], low['lambdas'],
+                       low['tlist'], orc.chis_re, iter_stop=2)
+    for it in (1, 2):
+        assert rel(res.all_pulses[it],
+                   rec[it]['optimized_pulses']) < PULSE_RTOL

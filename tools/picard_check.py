@@ -41,7 +41,7 @@ def engine_run(wl, picard, iters=3, second=False, fused=False):
         if fused:
             e0.record(stream)
             eng.krotov_iteration(chi, guess_t, opt_t, phiT, tau_t, phiT2, tau2, store_X=True,
-                                 sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1)
+                                 sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1, prev_guess_t=opt_t if it > 0 else None)
             e1.record(stream)
             phiT, phiT2 = phiT2, phiT
             tau_t, tau2 = tau2, tau_t
