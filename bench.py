@@ -291,11 +291,15 @@ def run_ours(args):
     selector = GPUShards(mode=args.shard_mode)
     n_state = len(wl.lowered()['psi0'][0])
     mode = selector.choose(K, n_state) if world > 1 else None
+    if args.engine == 'sweeps' and mode == 'replicate':
+        mode = 'gather'
     lo, hi = shard_bounds(K, world, rank) if mode == 'exchange' else (0, K)
     cp = compile_problem(objectives[lo:hi], controls, mapping[lo:hi],
                          wl.tlist)
     eng = SweepEngine(cp, shp, lam)
     shard = gather_comm = None
+    if mode == 'replicate' and not eng.fused_supported():
+        mode = 'gather'
     if mode == 'exchange':
         shard = ShardComm(dist, None, eng.device).attach(eng)
     elif mode == 'gather':
@@ -318,7 +322,8 @@ def run_ours(args):
 
     # one launch per Krotov iteration (csrc/kq_picard.cuh) where the problem
     # allows, else chi boundary / backward sweep / fused sweep / tau launches
-    fused = (args.engine != 'sweeps' and world == 1 and eng.fused_supported())
+    fused = (args.engine != 'sweeps' and (world == 1 or mode == 'replicate')
+             and eng.fused_supported())
     spare_phiT, spare_tau = eng.new_states(), torch.empty_like(tau_t)
     hint = [False]   # after the first iteration opt_t holds the previous guess
 
@@ -521,7 +526,7 @@ def main():
     ap.add_argument('--no-cpu', action='store_true',
                     help='skip the CPU baseline leg')
     ap.add_argument('--shard-mode', default='auto',
-                    choices=['auto', 'exchange', 'gather'],
+                    choices=['auto', 'exchange', 'gather', 'replicate'],
                     help='multi-GPU distribution of the fused sweep')
     ap.add_argument('--engine', default='auto', choices=['auto', 'sweeps'],
                     help="'sweeps' forces the four-launch sweep sequence")

@@ -199,7 +199,9 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses,
  * iteration does not converge ("picard_maxit" option) the outputs are left
  * untouched, workspace status word 1 is set to `epoch` and word 3 to the first
  * such epoch; word 2 holds the number of fixed-point rounds of the last
- * converged call. */
+ * converged call.  diag_out (may be NULL): 4 int32 written by the kernel,
+ * {exchange status, `epoch` if not converged else 0, rounds, 0}, so that a
+ * caller can fetch results and status with one device->host copy. */
 int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
                         const kq_c128* targets, const double* weights,
                         const kq_c128* chiT, const double* chi_norms,
@@ -210,7 +212,8 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
                         kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
                         double* chi_norms_out, const double* sigma,
                         const kq_c128* Phi0, kq_c128* Phi1, double* g_a,
-                        void* workspace, uint32_t epoch, void* stream);
+                        int32_t* diag_out, void* workspace, uint32_t epoch,
+                        void* stream);
 
 /* Boundary condition chi_k(T) for the built-in functionals, followed by the
  * normalisation of optimize.py:407-410 (L2 / Frobenius norm):

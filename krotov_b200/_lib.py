@@ -87,7 +87,7 @@ _SIGNATURES = {
         ctypes.c_void_p]),
     'kq_krotov_iteration': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.c_int, ctypes.c_int32] +
-        [ctypes.c_void_p] * 20 + [ctypes.c_uint32, ctypes.c_void_p]),
+        [ctypes.c_void_p] * 21 + [ctypes.c_uint32, ctypes.c_void_p]),
     'kq_chi_boundary': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.c_int, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,

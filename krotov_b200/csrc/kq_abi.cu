@@ -697,8 +697,8 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
                         const double* guess_pulses, const double* prev_guess_pulses,
                         double* opt_pulses, const kq_c128* phi0, kq_c128* phiT_out, kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
                         double* chi_norms_out, const double* sigma, const kq_c128* Phi0,
-                        kq_c128* Phi1, double* g_a, void* workspace, uint32_t epoch,
-                        void* stream) {
+                        kq_c128* Phi1, double* g_a, int32_t* diag_out, void* workspace,
+                        uint32_t epoch, void* stream) {
   int rc = check_problem(p);
   if (rc) return rc;
   if (!guess_pulses || !opt_pulses || !phi0 || !g_a || !workspace)
@@ -745,6 +745,7 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   a.Xout = reinterpret_cast<cplx*>(X);
   a.chi_out = reinterpret_cast<cplx*>(chi_out);
   a.chi_norms_out = chi_norms_out;
+  a.diag_out = diag_out;
   return launch_picard(p, a, pp, workspace, epoch, second, static_cast<cudaStream_t>(stream));
 }
 

@@ -5,6 +5,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include "../../include/krotov_b200.h"
 #include "kq_common.cuh"
 #include "kq_small.cuh"   // KqSweepArgs
@@ -33,19 +35,52 @@ struct KqPlan {
 
 typedef KqPlan Plan;
 
+// Launch helper.  The attribute / occupancy queries are cached per kernel
+// instantiation (they cost several microseconds per call and the fused
+// iteration kernel is launched once per Krotov iteration).
 template <typename Kern>
 int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** params) {
-  KQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  // Kern is only the function-pointer TYPE (all sweep kernels share it): the
+  // cache is keyed on the pointer value
+  struct Entry {
+    const void* fn;
+    int dev, smem, block, per_sm, sms;
+  };
+  static Entry cache[128];
+  static int n_cache = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  int dev = 0;
+  KQ_CUDA(cudaGetDevice(&dev));
+  const void* fn = (const void*)kern;
+  int c_per_sm = 0, c_sms = 0;
+  bool hit = false;
+  for (int i = 0; i < n_cache; ++i) {
+    const Entry& e = cache[i];
+    if (e.fn == fn && e.dev == dev && e.smem == (int)pl.smem && e.block == pl.block) {
+      c_per_sm = e.per_sm;
+      c_sms = e.sms;
+      hit = true;
+      break;
+    }
+  }
+  if (!hit) {
+    KQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    KQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_per_sm, kern, pl.block, pl.smem));
+    KQ_CUDA(cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev));
+    // a kernel launched with several shared-memory sizes keeps the largest
+    // opt-in attribute: drop its older entries so that a smaller size sets it again
+    int w = 0;
+    for (int i = 0; i < n_cache; ++i)
+      if (!(cache[i].fn == fn && cache[i].dev == dev)) cache[w++] = cache[i];
+    n_cache = w;
+    if (n_cache < 128) cache[n_cache++] = Entry{fn, dev, (int)pl.smem, pl.block, c_per_sm, c_sms};
+  }
   if (cooperative) {
-    int per_sm = 0;
-    KQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl.block, pl.smem));
-    int dev = 0, sms = 0;
-    KQ_CUDA(cudaGetDevice(&dev));
-    KQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if ((long long)per_sm * sms < pl.grid)
+    if ((long long)c_per_sm * c_sms < (long long)pl.grid * (pl.grid_y > 1 ? pl.grid_y : 1))
       return kq_fail(KQ_ERR_UNSUPPORTED,
                   "fused sweep needs %d co-resident CTAs but only %d fit (K too large)", pl.grid,
-                  per_sm * sms);
+                  c_per_sm * c_sms);
     KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1), dim3(pl.block),
                                         params, pl.smem, st));
   } else {

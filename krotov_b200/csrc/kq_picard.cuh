@@ -264,7 +264,7 @@ struct PicGeom {
 // application).  Steps beyond the grid have dt = 0 (identity).  With WT > 0 the
 // chunk length is the compile-time constant WT: all operators are prepared
 // together and kept in `ops`.
-template <int N, bool INREG, typename G, int WT, bool REV>
+template <int N, bool INREG, typename G, int WT, bool REV, bool SU2 = false>
 __device__ __forceinline__ void pic_pass_a(const SpecTerms<N, INREG, G>& T, const PicGeom& g,
                                            const double* seps, const double* dtg, bool driven,
                                            double c1_fixed, int s, int m, double inv_s,
@@ -283,10 +283,27 @@ __device__ __forceinline__ void pic_pass_a(const SpecTerms<N, INREG, G>& T, cons
       heps[w] = h[w] * (driven ? seps[w * g.TC + g.t] : c1_fixed);
     }
     StepOp<N, INREG, G>::template prepare_batch<WB>(T, h, heps, m, ops);
+    if constexpr (SU2 && N == 2) {
+      // unitary, unimodular steps: the chunk propagator is [[a, -conj(b)], [b, conj(a)]],
+      // only its first column is propagated
+      cplx y[N];
 #pragma unroll
-    for (int ww = 0; ww < WB; ++ww) {
-      const int w = REV ? WB - 1 - ww : ww;
-      ops[w].template apply<N>(M, s, m);
+      for (int i = 0; i < N; ++i) y[i] = M[i];
+#pragma unroll
+      for (int ww = 0; ww < WB; ++ww) {
+        const int w = REV ? WB - 1 - ww : ww;
+        ops[w].template apply<1>(y, s, m);
+      }
+      M[0] = y[0];
+      M[1] = y[1];
+      M[2] = c_make(-y[1].x, y[1].y);
+      M[3] = c_make(y[0].x, -y[0].y);
+    } else {
+#pragma unroll
+      for (int ww = 0; ww < WB; ++ww) {
+        const int w = REV ? WB - 1 - ww : ww;
+        ops[w].template apply<N>(M, s, m);
+      }
     }
   } else {
     for (int ww = 0; ww < g.W; ++ww) {
@@ -306,9 +323,31 @@ __device__ __forceinline__ void pic_pass_a(const SpecTerms<N, INREG, G>& T, cons
 
 // Scan of the chunk propagators over the lanes (first half of the scan): after
 // it M is the product over this lane and all earlier (REV: later) lanes.
-template <int N, bool REV>
+template <int N, bool REV, bool SU2 = false>
 __device__ __forceinline__ void pic_scan_lanes(cplx (&M)[N * N], int lane) {
   constexpr int NN = N * N;
+  if constexpr (SU2 && N == 2) {
+    // SU(2) elements as (a, b): (a1,b1)(a2,b2) = (a1 a2 - conj(b1) b2, b1 a2 + conj(a1) b2)
+    cplx a1 = M[0], b1 = M[1];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const cplx a2 = REV ? shfl_down_c(a1, off) : shfl_up_c(a1, off);
+      const cplx b2 = REV ? shfl_down_c(b1, off) : shfl_up_c(b1, off);
+      if (REV ? (lane + off < 32) : (lane >= off)) {
+        cplx an, bn;
+        an.x = fma(-b1.y, b2.y, fma(-b1.x, b2.x, fma(-a1.y, a2.y, a1.x * a2.x)));
+        an.y = fma(b1.y, b2.x, fma(-b1.x, b2.y, fma(a1.y, a2.x, a1.x * a2.y)));
+        bn.x = fma(a1.y, b2.y, fma(a1.x, b2.x, fma(-b1.y, a2.y, b1.x * a2.x)));
+        bn.y = fma(-a1.y, b2.x, fma(a1.x, b2.y, fma(b1.y, a2.x, b1.x * a2.y)));
+        a1 = an;
+        b1 = bn;
+      }
+    }
+    M[0] = a1;
+    M[1] = b1;
+    M[2] = c_make(-b1.x, b1.y);
+    M[3] = c_make(a1.x, -a1.y);
+  } else {
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     cplx O[NN];
@@ -320,6 +359,7 @@ __device__ __forceinline__ void pic_scan_lanes(cplx (&M)[N * N], int lane) {
 #pragma unroll
       for (int e = 0; e < NN; ++e) M[e] = Cm[e];
     }
+  }
   }
 }
 
@@ -358,6 +398,20 @@ __device__ __forceinline__ void pic_scan_finish(const cplx (&M)[N * N], const cp
     const cplx nb = REV ? shfl_down_c(e_[i], 1) : shfl_up_c(e_[i], 1);
     b[i] = (g.lane == (REV ? 31 : 0)) ? v[i] : nb;
   }
+}
+
+// True (CTA-uniform; contains a barrier) if every objective of the CTA has real,
+// symmetric, traceless 2 x 2 generator terms: all step propagators are then in
+// SU(2) and the scan runs on two complex numbers instead of four.
+template <int N, bool INREG, typename G>
+__device__ __forceinline__ bool pic_is_su2(const SpecTerms<N, INREG, G>& T) {
+  return false;
+}
+template <>
+__device__ __forceinline__ bool pic_is_su2<2, true, double>(const SpecTerms<2, true, double>& T) {
+  const bool sym = (T.t0[1] == T.t0[2]) && (T.t1[1] == T.t1[2]) && (T.t0[0] == -T.t0[3]) &&
+                   (T.t1[0] == -T.t1[3]);
+  return __syncthreads_and(sym) != 0;
 }
 
 // CTA-uniform scaling count and Taylor degree for a norm bound x <= KQ_PIC_XCAP.
@@ -552,8 +606,15 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     pic_plan(dtmax * (fma(gmax, O1, O0) + Oc), s, m, inv_s);
     cplx M[NN], y[N];
     StepOp<N, INREG, G> ops[WA];
-    pic_pass_a<N, INREG, G, WT, true>(Tb, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
-    pic_scan_lanes<N, true>(M, lane);
+    const bool su2 = pic_is_su2<N, INREG, G>(Tb);
+    if (su2) {
+      pic_pass_a<N, INREG, G, WT, true, true>(Tb, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M,
+                                              ops);
+      pic_scan_lanes<N, true, true>(M, lane);
+    } else {
+      pic_pass_a<N, INREG, G, WT, true>(Tb, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
+      pic_scan_lanes<N, true>(M, lane);
+    }
     if (lane == 0) {
 #pragma unroll
       for (int e = 0; e < NN; ++e) wt[g.wq * NN + e] = M[e];
@@ -645,6 +706,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     T.s1 = T.s0 + NN;
     T.stride = 1;
   }
+  const bool su2_fw = pic_is_su2<N, INREG, G>(T);
   cplx phi0[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) phi0[i] = a.state0[(size_t)k * N + i];
@@ -719,9 +781,16 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       cplx* wt = wtot + ((size_t)(it & 1) * Q + g.q) * KQ_PIC_WPO * NN;
       cplx M[NN];
       StepOp<N, INREG, G> ops[WA];
-      pic_pass_a<N, INREG, G, WT, false>(T, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
-      KQ_TICK(2)
-      pic_scan_lanes<N, false>(M, lane);
+      if (su2_fw) {
+        pic_pass_a<N, INREG, G, WT, false, true>(T, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M,
+                                                 ops);
+        KQ_TICK(2)
+        pic_scan_lanes<N, false, true>(M, lane);
+      } else {
+        pic_pass_a<N, INREG, G, WT, false>(T, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
+        KQ_TICK(2)
+        pic_scan_lanes<N, false>(M, lane);
+      }
       if (lane == 31) {
 #pragma unroll
         for (int e = 0; e < NN; ++e) wt[g.wq * NN + e] = M[e];
@@ -919,6 +988,12 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       a.status[1] = (int)a.epoch;
       atomicCAS(a.status + 3, 0, (int)a.epoch);   // first epoch that did not converge
       if (!(em < kInf)) atomicExch(a.status, (int)-4);
+      if (a.diag_out) {
+        a.diag_out[0] = (em < kInf) ? 0 : -4;
+        a.diag_out[1] = (int)a.epoch;
+        a.diag_out[2] = it;
+        a.diag_out[3] = 0;
+      }
     }
     return;
   }
@@ -941,7 +1016,15 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     ga = block_sum(ga, scratch + 192);
     if (tid == 0) a.g_a[0] = ga;
   }
-  if (tid == 0 && blockIdx.x == 0) a.status[2] = it;   // Picard iterations used (diagnostics)
+  if (tid == 0 && blockIdx.x == 0) {
+    a.status[2] = it;   // fixed-point rounds used (diagnostics)
+    if (a.diag_out) {
+      a.diag_out[0] = *reinterpret_cast<volatile int*>(a.status);
+      a.diag_out[1] = 0;
+      a.diag_out[2] = it;
+      a.diag_out[3] = 0;
+    }
+  }
   KQ_TICK(8)
   // second order: the final pass B stored rows 0..NT-1 of the forward states;
   // row NT is the end of the last chunk

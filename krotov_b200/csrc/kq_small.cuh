@@ -80,6 +80,7 @@ struct KqSweepArgs {
   cplx* Xout;                // [NT+1][K][N] or null
   cplx* chi_out;             // [K][N] or null
   double* chi_norms_out;     // [K] or null
+  int* diag_out;             // [4] copy of the status words {status, failed epoch, rounds, 0} or null
 };
 
 __device__ __forceinline__ void kq_store(const KqSweepArgs& a, size_t idx, cplx v) {

@@ -185,7 +185,8 @@ class SweepEngine:
 
     def krotov_iteration(self, chi_kind, guess_t, opt_t, phiT_in, tau_in,
                          phiT_out, tau_out, store_X=False, sigma_t=None,
-                         Phi0=None, Phi1=None, prev_guess_t=None):
+                         Phi0=None, Phi1=None, prev_guess_t=None,
+                         diag_t=None):
         """One whole Krotov iteration (optimize.py:393-508) in one launch of
         the time-parallel kernel family: chi boundary (`chi_kind` 're', 'ss',
         'sm', 'hs', or None for the states already in :attr:`chi` /
@@ -206,8 +207,8 @@ class SweepEngine:
             _ptr(None if kind < 0 else self.chi),
             _ptr(None if kind < 0 else self.chi_norms),
             _ptr(sigma_t), _ptr(Phi0), _ptr(Phi1), _ptr(self.g_a),
-            _ptr(self.workspace), ctypes.c_uint32(self.epoch & 0xFFFFFFFF),
-            self._stream()))
+            _ptr(diag_t), _ptr(self.workspace),
+            ctypes.c_uint32(self.epoch & 0xFFFFFFFF), self._stream()))
         self.launches += 1
 
     def fused_supported(self):

@@ -68,10 +68,12 @@ class _PackedResults:
             tau=r[self.o_tau:self.o_tau + K * 16].view(t.complex128),
             diag=r[self.o_diag:self.o_diag + 16])
 
-    def fetch(self, i, eng):
-        """Copy buffer `i` (after appending the engine's status words) to
-        the host; returns (pulses [L][NT], g_a [L], tau [K], status words)."""
-        self.views[i]['diag'].copy_(eng.workspace[:16])
+    def fetch(self, i, eng, diag_written=False):
+        """Copy buffer `i` to the host (after appending the engine's status
+        words unless the kernel wrote them itself); returns (pulses [L][NT],
+        g_a [L], tau [K], status words)."""
+        if not diag_written:
+            self.views[i]['diag'].copy_(eng.workspace[:16])
         self.host.copy_(self.dev[i], non_blocking=True)
         self.torch.cuda.current_stream(eng.device).synchronize()
         eng.d2h_bytes += self.nbytes
@@ -345,7 +347,10 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     gather_comm = None
     if (hi - lo) != K_total:
         shard = ShardComm(dist, group, eng.device).attach(eng)
-    elif shard_mode == 'gather':
+    if shard_mode == 'replicate' and not (
+            engine_mode is None and eng.fused_supported()):
+        shard_mode = 'gather'     # outside the one-launch kernel family
+    if shard_mode == 'gather':
         # every rank holds the complete problem; only the backward sweep is
         # sharded (engine.sweep_backward)
         gather_comm = ShardComm(dist, group, eng.device).attach_gather(eng)
@@ -567,7 +572,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     chi_kind, guess_t, opt_t, phiT, tau_t, spare_phiT,
                     spare_tau, store_X=info_hook is not None,
                     sigma_t=sigma_t, Phi0=Phi0, Phi1=Phi1,
-                    prev_guess_t=prev_guess_t)
+                    prev_guess_t=prev_guess_t,
+                    diag_t=pv['diag'] if packed is not None else None)
                 ran_fused = True
             except KqError as exc:
                 if 'error -3' not in str(exc):
@@ -576,7 +582,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         fetched = None
         if ran_fused and host_loop:
             if packed is not None:
-                fetched = packed.fetch(ri, eng)        # synchronises
+                fetched = packed.fetch(ri, eng, diag_written=True)
                 fb_epoch = int(fetched[3][1])
             else:
                 fb_epoch, _ = eng.sweep_diagnostics()  # synchronises

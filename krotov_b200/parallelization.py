@@ -66,18 +66,30 @@ class GPUShards:
             state vectors, where the sweep is bound by the chain of nt-1
             dependent steps and not by throughput.
 
-            ``'auto'`` (default): ``'gather'`` if ``K * N * N <= 65536``.
+            ``'replicate'``: every rank runs the complete problem with the
+            one-launch time-parallel iteration kernel (``kq_krotov_iteration``)
+            and no communication at all; all ranks obtain identical pulses
+            (the kernel is deterministic).  For problems that fit that kernel
+            family a single GPU is already latency-bound, so sharding them
+            only adds exchange latency: this is the fastest correct choice.
+
+            ``'auto'`` (default): ``'replicate'`` for N <= 4 and K <= 1184
+            (falls back to ``'gather'`` if the engine declines), else
+            ``'gather'`` if ``K * N * N <= 65536``, else ``'exchange'``.
     """
 
     def __init__(self, group=None, mode='auto'):
-        if mode not in ('auto', 'exchange', 'gather'):
-            raise ValueError("mode must be 'auto', 'exchange' or 'gather'")
+        if mode not in ('auto', 'exchange', 'gather', 'replicate'):
+            raise ValueError("mode must be 'auto', 'exchange', 'gather' or "
+                             "'replicate'")
         self.group = group
         self.mode = mode
 
     def choose(self, K, N):
         if self.mode != 'auto':
             return self.mode
+        if N <= 4 and K <= 1184:
+            return 'replicate'
         return 'gather' if K * N * N <= 65536 else 'exchange'
 
     def resolve(self):
