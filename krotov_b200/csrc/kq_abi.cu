@@ -239,8 +239,8 @@ struct PicPlan {
   int Q, TC, W, lw, Wc, lwc, grid, block, stride;
   size_t smem;
 };
-// slots per mailbox / per owner region: grid * 2^lwc <= 2 NT + 18 * 148
-size_t pic_stride(const kq_problem* p) { return (size_t)2 * round_up(p->NT, 64) + 2688; }
+// slots per mailbox / per owner region: grid * 2^lwc + grid <= 2 NT + 19 * 148
+size_t pic_stride(const kq_problem* p) { return (size_t)2 * round_up(p->NT, 64) + 2880; }
 bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   const int K = p->K, N = p->N, NT = p->NT, NN = N * N;
   if (N < 2 || N > 4 || p->M != 2 || p->L != 1) return false;
@@ -259,7 +259,7 @@ bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   const int Wc = round_up((NT + grid - 1) / grid, 2);
   int lwc = 3;
   while ((1 << lwc) < Wc) ++lwc;
-  if (((size_t)grid << lwc) > pic_stride(p)) return false;
+  if (((size_t)grid << lwc) + grid > pic_stride(p)) return false;
   const size_t smem = 256 * sizeof(double) + 2 * NTP * sizeof(double) + (size_t)Q * NTP * sizeof(double) +
                       (size_t)4 * Wc * sizeof(double) + (size_t)Q * NTP * N * sizeof(cplx) +
                       (size_t)2 * Q * 8 * NN * sizeof(cplx) + (size_t)Q * 4 * NN * sizeof(cplx);

@@ -400,6 +400,10 @@ __device__ __forceinline__ void pic_scan_finish(const cplx (&M)[N * N], const cp
   }
 }
 
+__device__ __forceinline__ void pic_prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // True (CTA-uniform; contains a barrier) if every objective of the CTA has real,
 // symmetric, traceless 2 x 2 generator terms: all step propagators are then in
 // SU(2) and the scan runs on two complex numbers instead of four.
@@ -473,6 +477,33 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   const int eta_base = g.q * W * N * TC + g.t;
   const int dsm_base = g.q * NTP + g.t;
 
+  // warm L2 for everything this CTA reads later (the first touch of each array
+  // would otherwise be a dependent DRAM miss): this objective's operators and
+  // states, the time-grid arrays, and -- multi-CTA -- the exchange lines it polls
+  {
+    const int kk = min(blockIdx.x * Q + tid / TC, K - 1);
+    if ((tid % TC) == 0) {
+      pic_prefetch_l2(a.ops + (size_t)kk * 2 * NN);
+      pic_prefetch_l2(a.mu + (size_t)kk * NN);
+      pic_prefetch_l2(a.state0 + (size_t)kk * N);
+      if (a.pic_bw) pic_prefetch_l2(a.ops_adj + (size_t)kk * 2 * NN);
+      if (a.targets) pic_prefetch_l2(a.targets + (size_t)kk * N);
+    }
+    for (int n = tid * 16; n < NT; n += BT * 16) {   // 16 doubles = one 128-byte line
+      pic_prefetch_l2(a.dt + n);
+      pic_prefetch_l2(a.pulses + n);
+      pic_prefetch_l2(a.shape + n);
+      if (a.pic_hint) pic_prefetch_l2(a.pic_hint + n);
+    }
+    if (nblk > 1) {
+      const int nline = (nblk << lwc) >> 3;   // 8 slots per line
+      for (int j = tid; j < nline; j += BT) {
+        pic_prefetch_l2(a.pic_part + (((size_t)blockIdx.x * nblk) << lwc) + (size_t)j * 8);
+        pic_prefetch_l2(a.pic_eps + (size_t)blockIdx.x * a.pic_stride + (size_t)j * 8);
+      }
+    }
+  }
+
   // optional per-phase cycle counts (thread 0 of CTA 0): kq_set_option("picard_timing", 1)
   const bool timing = a.pic_timing && tid == 0 && blockIdx.x == 0;
   long long tacc[KQ_PIC_NTICK], tprev = 0;
@@ -508,13 +539,17 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
 
   // first iterate (the guess pulse), the owned slice's scalars, norm bounds
   double gmax = 0.0, dtmax = 0.0;
-  // round 1 evaluates the guess pulse (also the backward sweep's pulse)
+  // buffer 0: the guess pulse (backward sweep; overwritten by round 2);
+  // buffer 1: the first iterate = the guess pulse or, with the guess of the
+  // iteration before, the guess plus the previous update (successive Krotov
+  // updates are similar: saves about one round)
   for (int n = tid; n < NTP; n += BT) {
-    const double e = (n < NT) ? a.pulses[n] : 0.0;
+    const double gn = (n < NT) ? a.pulses[n] : 0.0;
+    const double e = (a.pic_hint && n < NT) ? gn + (gn - a.pic_hint[n]) : gn;
+    seps0[(n & (W - 1)) * TC + (n >> lw)] = gn;
     seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
-    seps0[(n & (W - 1)) * TC + (n >> lw)] = 0.0;
     if (n < NT) {
-      gmax = fmax(gmax, fabs(e));
+      gmax = fmax(gmax, fmax(fabs(gn), fabs(e)));
       dtmax = fmax(dtmax, fabs(a.dt[n]));
     }
   }
@@ -608,11 +643,11 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     StepOp<N, INREG, G> ops[WA];
     const bool su2 = pic_is_su2<N, INREG, G>(Tb);
     if (su2) {
-      pic_pass_a<N, INREG, G, WT, true, true>(Tb, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M,
+      pic_pass_a<N, INREG, G, WT, true, true>(Tb, g, seps0, a.dt, driven, c1_fixed, s, m, inv_s, M,
                                               ops);
       pic_scan_lanes<N, true, true>(M, lane);
     } else {
-      pic_pass_a<N, INREG, G, WT, true>(Tb, g, seps, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
+      pic_pass_a<N, INREG, G, WT, true>(Tb, g, seps0, a.dt, driven, c1_fixed, s, m, inv_s, M, ops);
       pic_scan_lanes<N, true>(M, lane);
     }
     if (lane == 0) {
@@ -635,7 +670,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         } else {
           double h[1], heps[1];
           h[0] = a.dt[n] * inv_s;
-          heps[0] = h[0] * (driven ? seps[w * TC + g.t] : c1_fixed);
+          heps[0] = h[0] * (driven ? seps0[w * TC + g.t] : c1_fixed);
           StepOp<N, INREG, G> op1[1];
           StepOp<N, INREG, G>::template prepare_batch<1>(Tb, h, heps, m, op1);
           op1[0].template apply<1>(y, s, m);
@@ -671,22 +706,6 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       }
     }
   }
-  // first iterate of the fixed-point iteration: the guess pulse, or -- with the
-  // guess of the iteration before -- the guess plus the previous update
-  // (successive Krotov updates are similar: saves about one round)
-  if (a.pic_hint) {
-    __syncthreads();   // the backward sweep has read the guess pulse from this buffer
-    double hmax = 0.0;
-    for (int n = tid; n < NT; n += BT) {
-      const double gn = a.pulses[n];
-      const double e = gn + (gn - a.pic_hint[n]);
-      seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
-      hmax = fmax(hmax, fabs(e));
-    }
-    double unused2 = 0.0;
-    block_max2(hmax, unused2, scratch + 128);
-    gmax = fmax(gmax, hmax);
-  }
   __syncthreads();   // wtot is reused by the forward scans
   KQ_TICK(1)
 
@@ -715,6 +734,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   const double kInf = __longlong_as_double(0x7ff0000000000000LL);
   bool failed = false, converged = false;
   double ga_acc = 0.0;   // this thread's share of the g_a integral (last update)
+  double ga_in = 0.0;    // CTA 0, multi-CTA: shares received from the owners
   double em = gmax;      // max |eps| of the previous iterate (plans the next evaluation)
   double dm_prev = kInf;         // CTA-wide max |eps_{it-1} - eps_{it-2}|
   double dm = kInf, en = gmax;   // this thread's share of max |eps_it - eps_{it-1}|, max |eps_it|
@@ -763,6 +783,11 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
             sw[idx] = e_new;
           }
         }
+      }
+      if (blockIdx.x == 0) {
+        // the owners' shares of the g_a integral of this update
+        ga_in = 0.0;
+        for (int cb = tid; cb < nblk; cb += BT) ga_in += slot_wait(mybox + nslot + cb, tagp, failed);
       }
       if (failed) en = kInf;   // exchange timed out
       __syncthreads();
@@ -901,16 +926,30 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     } else {
       const uint32_t tag = tag0 + (uint32_t)it;
       const int nslot = nblk << lwc;
-      // stage 1: this CTA's partial sums, one full 128-byte line of slots per
-      // owner (layout [owner][cta][ni])
-      __syncthreads();
-      for (int j = tid; j < nslot; j += BT) {
-        const int o = j >> lwc, ni = j & (WcP - 1), n = o * Wc + ni;
-        if (ni < Wc && n < NT) {
-          const int idx = (n & (W - 1)) * TC + (n >> lw);
-          double d1 = dsm[idx];
-          for (int qq = 1; qq < Q; ++qq) d1 += dsm[qq * NTP + idx];
-          slot_store(&a.pic_part[(((size_t)o * nblk + blockIdx.x) << lwc) + ni], d1, tag);
+      // stage 1: this CTA's partial sums, full 128-byte lines of slots (layout
+      // [owner][cta][ni]).  One objective per CTA: every warp publishes the 32 W
+      // consecutive time steps its own threads just evaluated (no CTA barrier).
+      if (Q == 1) {
+        __syncwarp();
+        const int n0 = (warp << 5) << lw;
+        for (int i = 0; i < Wl; ++i) {
+          const int n = n0 + (i << 5) + lane;
+          if (n < NT) {
+            const int o = (Wc == WcP) ? (n >> lwc) : n / Wc, ni = n - o * Wc;
+            slot_store(&a.pic_part[(((size_t)o * nblk + blockIdx.x) << lwc) + ni],
+                       dsm[(n & (W - 1)) * TC + (n >> lw)], tag);
+          }
+        }
+      } else {
+        __syncthreads();
+        for (int j = tid; j < nslot; j += BT) {
+          const int o = j >> lwc, ni = j & (WcP - 1), n = o * Wc + ni;
+          if (ni < Wc && n < NT) {
+            const int idx = (n & (W - 1)) * TC + (n >> lw);
+            double d1 = dsm[idx];
+            for (int qq = 1; qq < Q; ++qq) d1 += dsm[qq * NTP + idx];
+            slot_store(&a.pic_part[(((size_t)o * nblk + blockIdx.x) << lwc) + ni], d1, tag);
+          }
         }
       }
       KQ_TICK(4)
@@ -946,6 +985,12 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
           ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), own_dt[tid]));
           own_eps[tid] = __dadd_rn(own_g[tid], __dmul_rn(sl, acc));
         }
+        if (warp == 0) {   // Wc <= 16: the slice's g_a share sits in lanes 0..15
+          double gs = ga_acc;
+          for (int o = 8; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+          if (lane == 0)
+            slot_store(&a.pic_eps[(size_t)nslot + blockIdx.x], gs, tag);   // CTA 0's mailbox
+        }
       } else {
         for (int ni = tid; ni < Wc; ni += BT) {
           if (n_lo + ni < NT) {
@@ -968,6 +1013,8 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
             own_eps[ni] = __dadd_rn(own_g[ni], __dmul_rn(sl, acc));
           }
         }
+        const double gs = block_sum(ga_acc, scratch + 192);
+        if (tid == 0) slot_store(&a.pic_eps[(size_t)nslot + blockIdx.x], gs, tag);
       }
       // a failed wait publishes +inf: every CTA then stops in the next round
       const bool any_failed = __syncthreads_or(failed);
@@ -1005,15 +1052,8 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     const double ga = block_sum(ga_acc, scratch + 192);
     if (tid == 0) a.g_a[0] = ga;
   } else if (blockIdx.x == 0) {
-    // g_a = sum_n (S/lambda) d_n^2 dt_n with (S/lambda) d_n = eps_n - guess_n
-    // (every CTA holds the whole pulse: no exchange needed)
-    double ga = 0.0;
-    for (int n = tid; n < NT; n += BT) {
-      const double sl = a.shape[n] / lam;
-      const double df = seps[(n & (W - 1)) * TC + (n >> lw)] - a.pulses[n];
-      if (sl > 0.0) ga += (df * df) / sl * a.dt[n];
-    }
-    ga = block_sum(ga, scratch + 192);
+    // the owners' shares arrived with the last pulse (fixed summation order)
+    const double ga = block_sum(ga_in, scratch + 192);
     if (tid == 0) a.g_a[0] = ga;
   }
   if (tid == 0 && blockIdx.x == 0) {
