@@ -507,6 +507,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     if host_loop and shard is None:
         packed = _PackedResults(torch, eng.device, L, NT, cp.K)
     ri = 0
+    spec = None         # the next iteration, if it was launched ahead
+    X_spare = [None]    # second backward-state store for launches ahead
 
     # ---- main loop (optimize.py:393-577) ----------------------------------
     for krotov_iteration in range(iter_start + 1, iter_stop + 1):
@@ -565,7 +567,16 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         # guess of the iteration before: a starting hint for the fused kernel
         prev_guess_t = prev_guess_ref
         ran_fused = False
-        if use_fused:
+        launch_epoch = None
+        if spec is not None:
+            # this iteration was launched ahead, while the hooks of the
+            # previous one were running; its buffers are exactly the ones
+            # selected above
+            ran_fused = True
+            launch_epoch = spec['epoch']
+            eng.X = spec['X']
+            spec = None
+        elif use_fused:
             try:
                 # chi boundary, both sweeps and tau in ONE launch
                 eng.krotov_iteration(
@@ -575,6 +586,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     prev_guess_t=prev_guess_t,
                     diag_t=pv['diag'] if packed is not None else None)
                 ran_fused = True
+                launch_epoch = eng.epoch
             except KqError as exc:
                 if 'error -3' not in str(exc):
                     raise
@@ -586,7 +598,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 fb_epoch = int(fetched[3][1])
             else:
                 fb_epoch, _ = eng.sweep_diagnostics()  # synchronises
-            if fb_epoch == (eng.epoch & 0xFFFFFFFF):
+            if fb_epoch == (launch_epoch & 0xFFFFFFFF):
                 # the fixed-point iteration did not converge: outputs are
                 # untouched; repeat with the sweep kernels and stay there
                 ran_fused = use_fused = False
@@ -622,10 +634,32 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         # previous one and are already on the host
         guess_pulses_host = optimized_pulses if krotov_iteration > \
             first_iteration else guess_pulses
+        X_this = eng.X
         if packed is not None:
             if fetched is None:
                 fetched = packed.fetch(ri, eng)    # synchronises the stream
             ri ^= 1
+            if (ran_fused and use_fused and chi_kind is not None
+                    and not second_order
+                    and krotov_iteration < static['iter_stop']):
+                # Launch the NEXT iteration now, so that the device works
+                # while the hooks of this one run.  It reads this
+                # iteration's outputs and writes only buffers nothing else
+                # refers to any more; if a hook then modifies the pulses or
+                # lambda_a, or the loop ends, the launch is simply discarded
+                # (and repeated with the modified inputs).
+                pv2 = packed.views[ri]
+                eng.g_a = pv2['g_a']
+                if info_hook is not None:
+                    if X_spare[0] is None:
+                        X_spare[0] = eng.new_state_store()
+                    eng.X, X_spare[0] = X_spare[0], eng.X
+                eng.krotov_iteration(
+                    chi_kind, opt_t, pv2['pulses'], phiT, tau_t,
+                    spare['phiT'], pv2['tau'] if has_targets else None,
+                    store_X=info_hook is not None, prev_guess_t=guess_t,
+                    diag_t=pv2['diag'])
+                spec = dict(epoch=eng.epoch, X=eng.X)
             optimized_pulses = [fetched[0][l].copy() for l in range(L)]
             g_a_integrals[:] = fetched[1][:L]
             tau_vals = fetched[2].copy() if tau_t is not None \
@@ -640,7 +674,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             raise RuntimeError("sweep kernel reported exchange failure %d"
                                % st)
         fw_states_T = lazy_states(phiT)
-        backward_states = _LazyStates(eng.X, cp, eng)
+        backward_states = _LazyStates(X_this, cp, eng)
         if second_order:
             forward_states = _LazyStates(Phi1, cp, eng)
             forward_states0 = _LazyStates(Phi0, cp, eng)
@@ -661,9 +695,11 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             if not np.array_equal(lam_snapshot, np.asarray(lambda_vals)):
                 eng.set_lambda(lambda_vals)
                 lam_snapshot = np.array(lambda_vals, dtype=np.float64)
+                spec = None      # launched ahead with the old lambda_a
             if not all(np.array_equal(a, b) for a, b
                        in zip(optimized_pulses, opt_snapshot)):
                 opt_t.copy_(eng.pulses_to_device(optimized_pulses))
+                spec = None      # launched ahead with the unmodified pulses
         result.iters.append(krotov_iteration)
         result.iter_seconds.append(int(toc - tic))
         result.iter_seconds_device.append(toc - tic)
