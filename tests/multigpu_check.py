@@ -25,7 +25,9 @@ def main():
                              (6, 80, 'ss', 'exchange'),
                              (37, 120, 're', 'gather'),
                              (128, 300, 'sm', 'gather'),
-                             (5, 80, 'ss', 'gather')):
+                             (5, 80, 'ss', 'gather'),
+                             (37, 120, 're', 'replicate'),
+                             (128, 300, 'sm', 'auto')):
         if K < world:
             continue
         wl = krotov.workloads.tls_ensemble(K=K, nt=nt)
