@@ -237,6 +237,13 @@ int kq_overlaps(int32_t K, int32_t N, const kq_c128* a, const kq_c128* b,
 int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid,
             int32_t* block, int32_t* smem_bytes);
 
+/* Launch geometry of kq_krotov_iteration on a 148-SM device: CTAs, threads per
+ * CTA, time steps per thread (chunk) and dynamic shared memory; returns
+ * KQ_ERR_UNSUPPORTED if the problem is outside that kernel family.  Host-only
+ * (no device needed). */
+int kq_plan_fused(const kq_problem* p, int32_t* grid, int32_t* block,
+                  int32_t* chunk, int32_t* smem_bytes);
+
 #ifdef __cplusplus
 }
 #endif

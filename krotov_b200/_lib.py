@@ -95,6 +95,10 @@ _SIGNATURES = {
     'kq_overlaps': (ctypes.c_int, [
         ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p]),
+    'kq_plan_fused': (ctypes.c_int, [
+        ctypes.POINTER(KqProblem), ctypes.POINTER(ctypes.c_int32),
+        ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),
+        ctypes.POINTER(ctypes.c_int32)]),
     'kq_plan': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.POINTER(ctypes.c_int32),
         ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32),

@@ -582,6 +582,19 @@ int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
   return KQ_OK;
 }
 
+int kq_plan_fused(const kq_problem* p, int32_t* grid, int32_t* block, int32_t* chunk,
+                  int32_t* smem_bytes) {
+  if (!p || p->K < 1 || p->N < 1 || p->NT < 1) return fail(KQ_ERR_ARG, "invalid problem sizes");
+  PicPlan pp;
+  if (!picard_plan(p, 148, pp))
+    return fail(KQ_ERR_UNSUPPORTED, "problem is outside the time-parallel kernel family");
+  if (grid) *grid = pp.grid;
+  if (block) *block = pp.block;
+  if (chunk) *chunk = pp.W;
+  if (smem_bytes) *smem_bytes = (int32_t)pp.smem;
+  return KQ_OK;
+}
+
 int kq_propagate_forward(const kq_problem* p, const double* pulses, const kq_c128* state0,
                          kq_c128* stateT, kq_c128* store, void* stream) {
   return run_prop(p, false, pulses, state0, stateT, store, stream);

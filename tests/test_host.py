@@ -250,3 +250,32 @@ def test_result_dump_load_roundtrip(tmp_path):
     assert r2.objectives[0].H[1][1] is None   # lambda control dropped
     r3 = krotov.Result.load(fn, objectives=r.objectives)
     assert r3.objectives is r.objectives
+
+
+def test_fused_iteration_plan_geometry():
+    """Launch geometry of the one-launch iteration kernel (host-only query):
+    one objective per CTA up to 148, power-of-two chunk lengths, and a clean
+    refusal outside the kernel family."""
+    import ctypes
+    from krotov_b200 import _lib
+    lib = _lib.load()
+
+    def plan(K, N, nt, L=1, M=2):
+        p = _lib.KqProblem(K=K, N=N, NT=nt - 1, L=L, M=M, is_super=0)
+        vals = [ctypes.c_int32() for _ in range(4)]
+        rc = lib.kq_plan_fused(ctypes.byref(p), *[ctypes.byref(v) for v in vals])
+        return rc, tuple(v.value for v in vals)
+
+    rc, (grid, block, chunk, smem) = plan(128, 2, 1000)      # C4
+    assert rc == 0 and (grid, block, chunk) == (128, 256, 4)
+    assert smem < 100 * 1024
+    rc, (grid, block, chunk, _) = plan(1, 2, 500)            # C1
+    assert rc == 0 and (grid, block, chunk) == (1, 256, 2)
+    rc, (grid, block, chunk, _) = plan(4, 4, 2000)           # C3
+    assert rc == 0 and (grid, block, chunk) == (4, 256, 8)
+    rc, (grid, block, chunk, _) = plan(300, 2, 1000)         # 3 objectives per CTA
+    assert rc == 0 and grid == 100 and block == 192 and chunk == 16
+    assert plan(128, 2, 5000)[0] == -3     # state stores exceed shared memory
+    assert plan(128, 5, 1000)[0] == -3     # N > 4: lane-per-row kernels
+    assert plan(8, 2, 100, L=2, M=3)[0] == -3
+    assert plan(2000, 2, 1000)[0] == -3    # more than 8 objectives per CTA
