@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
 
   // warm L2 for everything this CTA reads later (the first touch of each array
   // would otherwise be a dependent DRAM miss): this objective's operators and
-  // states, the time-grid arrays, and -- multi-CTA -- the exchange lines it polls
+  // states and the time-grid arrays (the exchange slots are written before they
+  // are read and need no fill from DRAM)
   {
     const int kk = min(blockIdx.x * Q + tid / TC, K - 1);
     if ((tid % TC) == 0) {
@@ -494,13 +495,6 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       pic_prefetch_l2(a.pulses + n);
       pic_prefetch_l2(a.shape + n);
       if (a.pic_hint) pic_prefetch_l2(a.pic_hint + n);
-    }
-    if (nblk > 1) {
-      const int nline = (nblk << lwc) >> 3;   // 8 slots per line
-      for (int j = tid; j < nline; j += BT) {
-        pic_prefetch_l2(a.pic_part + (((size_t)blockIdx.x * nblk) << lwc) + (size_t)j * 8);
-        pic_prefetch_l2(a.pic_eps + (size_t)blockIdx.x * a.pic_stride + (size_t)j * 8);
-      }
     }
   }
 
