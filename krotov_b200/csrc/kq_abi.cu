@@ -297,7 +297,6 @@ int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* w
                (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
   b.pic_part = reinterpret_cast<KqSlot*>(base);
   b.pic_eps = b.pic_part + (size_t)kPicMaxBlocks * pp.stride;
-  b.pic_ga = b.pic_eps + (size_t)kPicMaxBlocks * pp.stride;
   Plan ppl;
   std::memset(&ppl, 0, sizeof ppl);
   ppl.grid = pp.grid;
@@ -564,7 +563,7 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* st
 size_t kq_workspace_bytes(const kq_problem* p) {
   size_t bytes = kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
   if (p && p->NT > 0)   // slots of the time-parallel fused sweep: part | eps | ga
-    bytes += ((size_t)2 * kPicMaxBlocks * pic_stride(p) + kPicMaxBlocks) * sizeof(KqSlot);
+    bytes += (size_t)2 * kPicMaxBlocks * pic_stride(p) * sizeof(KqSlot);
   return bytes;
 }
 

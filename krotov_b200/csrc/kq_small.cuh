@@ -57,8 +57,8 @@ struct KqSweepArgs {
   int pic_Q, pic_TC, pic_W, pic_maxit, pic_stride;
   double pic_rtol;
   KqSlot* pic_part;   // [owner][cta][2^pic_lwc] per-CTA partial sums over its objectives
-  KqSlot* pic_eps;    // [cta][pic_stride]: mailbox of updated pulse values [owner][2^pic_lwc]
-  KqSlot* pic_ga;     // [gridDim.x] per-CTA share of the g_a integral
+  KqSlot* pic_eps;    // [cta][pic_stride]: mailbox of updated pulse values [owner][2^pic_lwc];
+                      // CTA 0's mailbox continues with the owners' g_a shares [gridDim.x]
   // sequential kernels launched as the fall-back of the time-parallel sweep run
   // only if status[1] == cond_epoch (0 = unconditional)
   uint32_t cond_epoch, epoch;
