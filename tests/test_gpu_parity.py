@@ -532,3 +532,118 @@ def test_fused_iteration_custom_chi_and_weights(krotov):
     for it in (1, 2):
         assert rel(res.all_pulses[it],
                    rec[it]['optimized_pulses']) < PULSE_RTOL
+
+
+def _oracle_pulses(objs, opts, tlist, iters, is_super=False, chi='re'):
+    from oracle import krotov_oracle as orc
+    from krotov_b200.compiler import initialize_controls
+    (controls, _, pulses, mapping, lam, shp) = initialize_controls(
+        objs, opts, tlist)
+
+    def vec(s):
+        s = np.asarray(s, dtype=complex)
+        return s.reshape(-1, order='F') if (s.ndim == 2 and s.shape[1] > 1) \
+            else s.ravel()
+    terms = [[(np.asarray(o.H[0], dtype=complex), -1),
+              (np.asarray(o.H[1][0], dtype=complex), 0)] for o in objs]
+    rec = orc.optimize(
+        terms, [vec(o.initial_state) for o in objs],
+        [vec(o.target) for o in objs], pulses, shp, lam, tlist,
+        getattr(orc, 'chis_' + chi), iter_stop=iters, is_super=is_super,
+        operator_norm='fro')
+    return [r['optimized_pulses'] for r in rec]
+
+
+@pytest.mark.parametrize('case', [
+    'runtime_chunk_nt60',      # W = 1: run-time chunk loop (WT = 0)
+    'runtime_chunk_nt3000',    # W = 16: run-time chunk loop, long grid
+    'three_per_cta_K300',      # Q = 3 objectives per CTA, 100 CTAs
+    'complex_drive',           # complex generator: Taylor path, general scan
+    'non_hermitian_trace',     # real generator with trace and decay: phase path
+])
+def test_fused_iteration_kernel_variants_vs_oracle(krotov, case):
+    """Template / geometry variants of k_krotov_picard against the oracle."""
+    sx = np.array([[0, 1], [1, 0]], dtype=complex)
+    sy = np.array([[0, -1j], [1j, 0]], dtype=complex)
+    sz = np.array([[1, 0], [0, -1]], dtype=complex)
+    K, nt, H0, H1 = {
+        'runtime_chunk_nt60': (5, 60, -0.5 * sz, sx),
+        'runtime_chunk_nt3000': (3, 3000, -0.5 * sz, sx),
+        'three_per_cta_K300': (300, 200, -0.5 * sz, sx),
+        'complex_drive': (4, 300, -0.5 * sz, sy),
+        'non_hermitian_trace': (4, 300, np.diag([0.3, 1.7 - 0.05j]) + 0.1 * sx,
+                                sx + 0.2 * np.diag([1.0, 0.0])),
+    }[case]
+    objs, opts, tlist = _tls_variant(krotov, H0, H1, K=K, nt=nt)
+    res = krotov.optimize_pulses(
+        objs, opts, tlist, propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+        store_all_pulses=True)
+    assert res.fused_iterations == 2, case
+    want = _oracle_pulses(objs, opts, tlist, 2)
+    for it in (1, 2):
+        assert rel(res.all_pulses[it], want[it]) < PULSE_RTOL, (case, it)
+
+
+def test_fused_iteration_liouville_n4_and_three_level(krotov):
+    """Super-operator generators (factor 1 instead of -i; N = 4: a damped
+    two-level density matrix) and a three-level Hilbert-space problem through
+    the fused kernel, against the oracle."""
+    from functools import partial
+    from krotov_b200.objectives import liouvillian
+    T, nt = 5.0, 200
+    tlist = np.linspace(0, T, nt)
+    S = partial(krotov.shapes.flattop, t_start=0, t_stop=T, t_rise=0.5,
+                func='sinsq')
+    guess = lambda t, args: 0.3 * S(t)  # noqa: E731
+    H0 = np.diag([-0.5, 0.5]).astype(complex)
+    H1 = np.array([[0, 1], [1, 0]], dtype=complex)
+    c_op = np.sqrt(0.05) * np.array([[0, 1], [0, 0]], dtype=complex)
+    L = liouvillian([H0, [H1, guess]], [c_op])
+    rho0 = np.diag([0.0, 1.0]).astype(complex)
+    rho1 = np.diag([1.0, 0.0]).astype(complex)
+    objs = [krotov.Objective(initial_state=rho0, target=rho1, H=L)]
+    opts = {guess: dict(lambda_a=2.0, update_shape=S)}
+    res = krotov.optimize_pulses(
+        objs, opts, tlist, propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+        store_all_pulses=True)
+    assert res.fused_iterations == 2
+    want = _oracle_pulses(objs, opts, tlist, 2, is_super=True)
+    for it in (1, 2):
+        assert rel(res.all_pulses[it], want[it]) < PULSE_RTOL, it
+    # three levels, complex Hermitian drift
+    rng = np.random.default_rng(7)
+    A = rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3))
+    H0 = (A + A.conj().T) / 4
+    H1 = np.diag([0.0, 1.0, 2.0]).astype(complex) + 0.5 * np.array(
+        [[0, 1, 0], [1, 0, 1], [0, 1, 0]], dtype=complex)
+    psi0 = np.array([[1], [0], [0]], dtype=complex)
+    psi1 = np.array([[0], [0], [1]], dtype=complex)
+    objs = [krotov.Objective(initial_state=psi0, target=psi1,
+                             H=[H0 * (1 + 0.1 * k), [H1, guess]])
+            for k in range(3)]
+    res = krotov.optimize_pulses(
+        objs, opts, tlist, propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+        store_all_pulses=True)
+    assert res.fused_iterations == 2
+    want = _oracle_pulses(objs, opts, tlist, 2)
+    for it in (1, 2):
+        assert rel(res.all_pulses[it], want[it]) < PULSE_RTOL, it
+
+
+def test_fused_iteration_is_deterministic(krotov):
+    """Fixed reduction orders, no atomics: two runs give bit-identical pulses
+    (C4 at full size: 128 CTAs exchanging through tagged slots)."""
+    wl = krotov.workloads.tls_ensemble(K=128, nt=1000)
+    runs = [krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=4,
+        store_all_pulses=True) for _ in range(2)]
+    assert runs[0].fused_iterations == 4
+    assert np.array_equal(np.array(runs[0].all_pulses),
+                          np.array(runs[1].all_pulses))
+    assert np.array_equal(np.array(runs[0].tau_vals),
+                          np.array(runs[1].tau_vals))
