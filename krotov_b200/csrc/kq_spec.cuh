@@ -445,31 +445,49 @@ __global__ void __launch_bounds__(256, 1) k_prop_spec(const KqSweepArgs a) {
 }
 
 // Boundary states of the segments: B[0] = state0, B[q+1] = P_q B[q].
+// The segment propagators do not depend on the chain: they are loaded in
+// batches (independent loads in flight together), so a step costs one small
+// matvec instead of one global-memory round trip.
 template <int N>
 __global__ void k_seg_chain(const KqSweepArgs a, int nseg) {
+  constexpr int NN = N * N;
+  constexpr int NB = (N <= 2) ? 8 : (N == 3 ? 4 : 2);   // propagators per batch (registers)
   const int k = a.k_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= a.k_lo + a.k_cnt) return;
   const int K = a.K;
+  const cplx* __restrict__ segP = a.seg_P;
+  cplx* __restrict__ segB = a.seg_B;
   cplx b[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     b[i] = a.state0[(size_t)k * N + i];
-    a.seg_B[((size_t)0 * K + k) * N + i] = b[i];
+    segB[((size_t)0 * K + k) * N + i] = b[i];
   }
-  for (int q = 0; q < nseg; ++q) {
-    const cplx* P = a.seg_P + ((size_t)q * K + k) * N * N;
-    cplx o[N];
+  for (int q0 = 0; q0 < nseg; q0 += NB) {
+    cplx P[NB][NN];
 #pragma unroll
-    for (int r = 0; r < N; ++r) {
-      cplx acc = c_zero();
+    for (int u = 0; u < NB; ++u) {
+      const int q = min(q0 + u, nseg - 1);
 #pragma unroll
-      for (int c = 0; c < N; ++c) acc = c_fma(P[c * N + r], b[c], acc);
-      o[r] = acc;
+      for (int e = 0; e < NN; ++e) P[u][e] = segP[((size_t)q * K + k) * NN + e];
     }
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      b[i] = o[i];
-      a.seg_B[((size_t)(q + 1) * K + k) * N + i] = o[i];
+    for (int u = 0; u < NB; ++u) {
+      if (q0 + u < nseg) {
+        cplx o[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+          cplx acc = c_zero();
+#pragma unroll
+          for (int c = 0; c < N; ++c) acc = c_fma(P[u][c * N + r], b[c], acc);
+          o[r] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          b[i] = o[i];
+          segB[((size_t)(q0 + u + 1) * K + k) * N + i] = o[i];
+        }
+      }
     }
   }
 }

@@ -568,7 +568,7 @@ def test_fused_iteration_kernel_variants_vs_oracle(krotov, case):
     sz = np.array([[1, 0], [0, -1]], dtype=complex)
     K, nt, H0, H1 = {
         'runtime_chunk_nt60': (5, 60, -0.5 * sz, sx),
-        'runtime_chunk_nt3000': (3, 3000, -0.5 * sz, sx),
+        'runtime_chunk_nt3000': (8, 3000, -0.5 * sz, sx),
         'three_per_cta_K300': (300, 200, -0.5 * sz, sx),
         'complex_drive': (4, 300, -0.5 * sz, sy),
         'non_hermitian_trace': (4, 300, np.diag([0.3, 1.7 - 0.05j]) + 0.1 * sx,
