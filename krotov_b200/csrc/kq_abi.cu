@@ -345,6 +345,70 @@ int launch_warp(const KqSweepArgs& a, const Plan& pl, int fsel, bool second, boo
   return kq_launch_warp0(a, pl, fsel, second, update, st);
 }
 
+// Boundary states of the segments for the lane-per-row family (any N <= 64):
+// B[0] = state0, B[q+1] = P_q B[q].  One CTA per objective, one thread per row;
+// the next segment propagator's row is loaded into registers (NC columns) while
+// the current product is formed.
+template <int NC>
+__global__ void k_seg_chain_rows(const KqSweepArgs a, int nseg) {
+  extern __shared__ __align__(16) unsigned char chain_smem[];
+  cplx* sb = reinterpret_cast<cplx*>(chain_smem);   // [2][N]
+  const int N = a.N, K = a.K, NN = N * N;
+  const int k = a.k_lo + blockIdx.x, r = threadIdx.x;
+  const bool act = r < N;
+  const cplx* __restrict__ segP = a.seg_P;
+  cplx* __restrict__ segB = a.seg_B;
+  if (act) {
+    sb[r] = a.state0[(size_t)k * N + r];
+    segB[((size_t)0 * K + k) * N + r] = sb[r];
+  }
+  cplx Pn[NC > 0 ? NC : 1];
+  if (NC > 0 && act) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      Pn[c] = (c < N) ? segP[((size_t)0 * K + k) * NN + (size_t)c * N + r] : c_zero();
+  }
+  __syncthreads();
+  int p = 0;
+  for (int q = 0; q < nseg; ++q) {
+    cplx acc0 = c_zero(), acc1 = c_zero(), acc2 = c_zero(), acc3 = c_zero();
+    if (act) {
+      if (NC > 0) {
+        cplx Pc[NC > 0 ? NC : 1];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) Pc[c] = Pn[c];
+        if (q + 1 < nseg) {
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+            Pn[c] = (c < N) ? segP[((size_t)(q + 1) * K + k) * NN + (size_t)c * N + r] : c_zero();
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c += 4) {
+          if (c < N) acc0 = c_fma(Pc[c], sb[p * N + c], acc0);
+          if (c + 1 < N) acc1 = c_fma(Pc[c + 1], sb[p * N + c + 1], acc1);
+          if (c + 2 < N) acc2 = c_fma(Pc[c + 2], sb[p * N + c + 2], acc2);
+          if (c + 3 < N) acc3 = c_fma(Pc[c + 3], sb[p * N + c + 3], acc3);
+        }
+      } else {
+        const cplx* P = segP + ((size_t)q * K + k) * NN + r;
+        int c = 0;
+        for (; c + 3 < N; c += 4) {
+          acc0 = c_fma(P[(size_t)c * N], sb[p * N + c], acc0);
+          acc1 = c_fma(P[(size_t)(c + 1) * N], sb[p * N + c + 1], acc1);
+          acc2 = c_fma(P[(size_t)(c + 2) * N], sb[p * N + c + 2], acc2);
+          acc3 = c_fma(P[(size_t)(c + 3) * N], sb[p * N + c + 3], acc3);
+        }
+        for (; c < N; ++c) acc0 = c_fma(P[(size_t)c * N], sb[p * N + c], acc0);
+      }
+      const cplx acc = c_add(c_add(acc0, acc1), c_add(acc2, acc3));
+      sb[(p ^ 1) * N + r] = acc;
+      segB[((size_t)(q + 1) * K + k) * N + r] = acc;
+    }
+    __syncthreads();
+    p ^= 1;
+  }
+}
+
 int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_c128* state0,
              kq_c128* stateT, kq_c128* store, void* stream, int k_lo = 0, int k_cnt = -1) {
   int rc = check_problem(p);
@@ -393,7 +457,60 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
     if (p->real_ops && !p->is_super) return kq_launch_prop_spec_re(a, pl, fsel, nseg, st);
     return kq_launch_prop_spec(a, pl, fsel, nseg, st);
   }
-  return launch_warp(a, pl, fsel, false, false, st);
+  // lane-per-row family: time-parallel propagation when the objectives alone
+  // leave most of the GPU idle (one wave of tasks holds capacity objectives;
+  // the segmented sweep does N + 1 times the work)
+  Plan plmax;                    // the largest CTA the kernels take: tasks per wave
+  sub.K = 1 << 20;
+  rc = make_plan(&sub, false, false, g_dev[dev].sms, plmax);
+  if (rc) return rc;
+  const int capacity = g_dev[dev].sms * (plmax.block / 32) * plmax.geom.G;
+  int nseg = 1;
+  if (!g_disable_segments && p->NT >= 64)
+    nseg = std::min(128, std::min(p->NT / 16, capacity / (k_cnt * (p->N + 1))));
+  if (nseg < 4) return launch_warp(a, pl, fsel, false, false, st);
+  a.seg_len = (p->NT + nseg - 1) / nseg;
+  nseg = (p->NT + a.seg_len - 1) / a.seg_len;
+  a.seg_count = nseg;
+  {
+    const size_t nP = (size_t)nseg * p->K * p->N * p->N, nB = (size_t)(nseg + 1) * p->K * p->N;
+    void* scratch = nullptr;
+    rc = get_scratch(dev, (nP + nB) * sizeof(cplx), &scratch);
+    if (rc) return rc;
+    a.seg_P = reinterpret_cast<cplx*>(scratch);
+    a.seg_B = a.seg_P + nP;
+  }
+  // pass 1: the N basis vectors through every segment -> segment propagators
+  KqSweepArgs a1 = a;
+  a1.seg_pass = 1;
+  a1.store = nullptr;
+  a1.stateT = nullptr;
+  Plan pl1;
+  sub.K = k_cnt * nseg * p->N;
+  rc = make_plan(&sub, false, false, g_dev[dev].sms, pl1);
+  if (rc) return rc;
+  rc = launch_warp(a1, pl1, fsel, false, false, st);
+  if (rc) return rc;
+  // boundary states of the segments (sweep order)
+  {
+    const int bt = round_up(p->N, 32);
+    const size_t sm = (size_t)2 * p->N * sizeof(cplx);
+    if (p->N <= 16)
+      k_seg_chain_rows<16><<<k_cnt, bt, sm, st>>>(a, nseg);
+    else if (p->N <= 32)
+      k_seg_chain_rows<32><<<k_cnt, bt, sm, st>>>(a, nseg);
+    else
+      k_seg_chain_rows<0><<<k_cnt, bt, sm, st>>>(a, nseg);
+    KQ_CUDA(cudaGetLastError());
+  }
+  // pass 2: every segment from its boundary state, all states stored
+  KqSweepArgs a2 = a;
+  a2.seg_pass = 2;
+  Plan pl2;
+  sub.K = k_cnt * nseg;
+  rc = make_plan(&sub, false, false, g_dev[dev].sms, pl2);
+  if (rc) return rc;
+  return launch_warp(a2, pl2, fsel, false, false, st);
 }
 
 // ---- boundary condition / overlaps --------------------------------------

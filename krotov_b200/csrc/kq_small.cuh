@@ -50,6 +50,7 @@ struct KqSweepArgs {
   // at the segment boundaries seg_B [S+1][K][N], pass 2 propagates every
   // segment from its boundary state and stores all states.  seg_pass 0 = off.
   int seg_len, seg_pass;
+  int seg_count;      // number of segments (lane-per-row kernels: part of the task index)
   cplx* seg_P;
   cplx* seg_B;
   // time-parallel fused sweep (kq_picard.cuh): CTA = pic_Q objectives x pic_TC

@@ -55,10 +55,27 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   const int nwarps = blockDim.x >> 5;
   const int R = g.R, G = g.G;
   const int grp = lane / R, lig = lane - grp * R;
-  const int k_end = UPDATE ? K : a.k_lo + a.k_cnt;
-  const int ob = (UPDATE ? 0 : a.k_lo) + (blockIdx.x * nwarps + warp) * G + grp;
-  const bool valid = ob < k_end;
-  const int kk = valid ? ob : k_end - 1;
+  // Task index.  Plain sweeps: one task per objective.  Time-parallel
+  // propagation (seg_pass 1/2, UPDATE = false): one task per (objective,
+  // segment[, basis vector]) -- pass 1 sends the N basis vectors through every
+  // segment (segment propagators), pass 2 propagates every segment from its
+  // boundary state and stores all states (see k_prop_spec in kq_spec.cuh).
+  const int seg_pass = UPDATE ? 0 : a.seg_pass;
+  const int n_task = UPDATE ? K
+                            : (seg_pass ? a.k_cnt * a.seg_count * (seg_pass == 1 ? N : 1)
+                                        : a.k_cnt);
+  int task = (blockIdx.x * nwarps + warp) * G + grp;
+  const bool valid = task < n_task;
+  if (!valid) task = n_task - 1;
+  int seg = 0, vec = 0;
+  if (seg_pass) {
+    const int rest = task / a.k_cnt;
+    task -= rest * a.k_cnt;
+    seg = rest % a.seg_count;
+    vec = rest / a.seg_count;
+  }
+  const int ob = (UPDATE ? 0 : a.k_lo) + task;
+  const int kk = ob;
   const int nblk = gridDim.x;
 
   // ---- shared memory carve-up ------------------------------------------
@@ -95,7 +112,15 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   for (int q = 0; q < RPL; ++q) {
     row[q] = lig + R * q;
     act[q] = row[q] < N;
-    y[q] = act[q] ? a.state0[(size_t)kk * N + row[q]] : c_zero();
+    y[q] = c_zero();
+    if (act[q]) {
+      if (seg_pass == 1)
+        y[q] = c_make(row[q] == vec ? 1.0 : 0.0, 0.0);
+      else if (seg_pass == 2)
+        y[q] = a.seg_B[((size_t)seg * K + kk) * N + row[q]];
+      else
+        y[q] = a.state0[(size_t)kk * N + row[q]];
+    }
     chi[q] = c_zero();
     dphi[q] = c_zero();
     if (UPDATE && act[q]) chi[q] = a.X[((size_t)0 * K + kk) * N + row[q]];
@@ -107,9 +132,21 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   }
   cplx arow[AREG > 0 ? AREG : 1];
   const double cnorm = (UPDATE && valid) ? a.chi_norms[kk] : 0.0;
-  const int n_first = (!UPDATE && a.backward) ? NT - 1 : 0;
-  const int n_step = (!UPDATE && a.backward) ? -1 : 1;
-  if (a.store && valid && (!UPDATE || SECOND)) {
+  const bool bwd = !UPDATE && a.backward;
+  int n_first = bwd ? NT - 1 : 0, n_count = NT;
+  if (seg_pass) {   // time window of this segment, in sweep order
+    if (bwd) {
+      const int w1 = NT - seg * a.seg_len, w0 = max(0, w1 - a.seg_len);
+      n_first = w1 - 1;
+      n_count = w1 - w0;
+    } else {
+      const int w0 = seg * a.seg_len, w1 = min(NT, w0 + a.seg_len);
+      n_first = w0;
+      n_count = w1 - w0;
+    }
+  }
+  const int n_step = bwd ? -1 : 1;
+  if (a.store && valid && (!UPDATE || SECOND) && seg == 0 && seg_pass != 1) {
     const size_t r0 = (!UPDATE && a.backward) ? (size_t)NT : 0;
 #pragma unroll
     for (int q = 0; q < RPL; ++q)
@@ -124,7 +161,7 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   int p = 0;  // xb[p] holds the current state
   __syncwarp();
 
-  for (int it = 0, n = n_first; it < NT; ++it, n += n_step) {
+  for (int it = 0, n = n_first; it < n_count; ++it, n += n_step) {
     const int par = it & 1;
     const double dtn = a.dt[n];
     cplx chi_next[RPL], p0_next[RPL];
@@ -326,7 +363,7 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
         if (SECOND) dphi[q] = c_sub(y[q], p0_next[q]);
       }
     }
-    if (a.store && valid && (!UPDATE || SECOND)) {
+    if (a.store && valid && (!UPDATE || SECOND) && seg_pass != 1) {
       const size_t r1 = (!UPDATE && a.backward) ? (size_t)n : (size_t)n + 1;
 #pragma unroll
       for (int q = 0; q < RPL; ++q)
@@ -336,7 +373,14 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
         }
     }
   }
-  if (a.stateT && valid) {
+  if (seg_pass == 1) {
+    // column `vec` of the segment propagator (column-major)
+    if (valid) {
+#pragma unroll
+      for (int q = 0; q < RPL; ++q)
+        if (act[q]) a.seg_P[((size_t)seg * K + ob) * NN + (size_t)vec * N + row[q]] = y[q];
+    }
+  } else if (a.stateT && valid && (seg_pass == 0 || seg == a.seg_count - 1)) {
 #pragma unroll
     for (int q = 0; q < RPL; ++q)
       if (act[q]) a.stateT[(size_t)ob * N + row[q]] = y[q];

@@ -647,3 +647,23 @@ def test_fused_iteration_is_deterministic(krotov):
                           np.array(runs[1].all_pulses))
     assert np.array_equal(np.array(runs[0].tau_vals),
                           np.array(runs[1].tau_vals))
+
+
+def test_lane_per_row_time_parallel_sweeps_match_sequential(krotov):
+    """The lane-per-row family (N >= 5) also cuts the propagation sweeps under
+    known pulses into concurrent time segments (segment propagators ->
+    boundary states -> states): backward states, final states and pulses must
+    agree with the purely sequential sweeps (kq_set_option time_parallel 0)."""
+    lib = krotov._lib.load()
+    wl = krotov.workloads.transmon_xgate(nstates=2, nt=400)   # N = 5
+    out = {}
+    for tp in (1, 0):
+        assert lib.kq_set_option(b"time_parallel", tp) == 0
+        try:
+            res, rec = run_gpu(krotov, wl, 2, keep_states=True)
+        finally:
+            lib.kq_set_option(b"time_parallel", 1)
+        out[tp] = (np.array(rec.pulses), rec.bw, np.array(rec.fwT))
+    assert rel(out[1][0][1:], out[0][0][1:]) < 1e-12
+    assert np.allclose(out[1][1], out[0][1], rtol=0, atol=1e-12)
+    assert np.allclose(out[1][2], out[0][2], rtol=0, atol=1e-12)
