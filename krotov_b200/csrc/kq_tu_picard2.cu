@@ -8,6 +8,8 @@ namespace {
 template <int FSEL, bool SECOND, typename G>
 int by_chunk(const KqSweepArgs& a, const KqPlan& pl, cudaStream_t st) {
   void* params[] = {(void*)&a};
+  // N = 2: compile-time chunk lengths (unrolled, step operators kept in registers)
+  // halve pass A / pass B against the run-time loop
   switch (a.pic_W) {
     case 2: return launch(k_krotov_picard<2, FSEL, SECOND, G, 2>, pl, true, st, params);
     case 4: return launch(k_krotov_picard<2, FSEL, SECOND, G, 4>, pl, true, st, params);

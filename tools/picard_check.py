@@ -102,7 +102,10 @@ def timing(name, wl, iters=3, fused=True):
 if __name__ == '__main__':
     W = krotov.workloads
     if len(sys.argv) > 1 and sys.argv[1] == 'timing':
-        for r in timing('C4', W.tls_ensemble(K=128, nt=1000), 4):
+        name = sys.argv[2] if len(sys.argv) > 2 else 'C4'
+        wl = {'C4': lambda: W.tls_ensemble(K=128, nt=1000), 'C1': W.tls_state_to_state,
+              'C2': W.transmon_xgate, 'C3': W.two_qubit_gate}[name]()
+        for r in timing(name, wl, 4):
             cyc = r['cycles']
             its = max(r['pit'], 1)
             names = ['prologue', 'bw', 'passA', 'passB', 'stage1', 'stage2', 'stage3', 'blockmax', 'outputs', 'final',
