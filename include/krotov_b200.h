@@ -84,7 +84,8 @@ typedef struct {
   int32_t real_ops;   /* 1: every matrix in ops/ops_adj has zero imaginary part
                          (real Hamiltonians): kernels use the purely imaginary
                          form of f*A in Hilbert space; 0: general complex */
-  int32_t reserved;
+  int32_t reserved;   /* kq_sweep_forward_update: number of time windows of the
+                         time-parallel update sweep (0 = as few as fit shared memory) */
 } kq_problem;
 
 /* Cross-GPU exchange descriptor for the per-time-step reduction of the pulse

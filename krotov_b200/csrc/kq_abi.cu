@@ -63,6 +63,7 @@ int g_picard_timing = 0;
 int g_picard_maxit = 64;           // kq_set_option("picard_maxit", n)
 constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
 constexpr int kPicMaxItCap = 1000;
+constexpr int kPicMaxWindows = 64;   // time windows of one windowed update sweep
 
 int get_scratch(int dev, size_t bytes, void** out) {
   std::lock_guard<std::mutex> lock(g_mu);
@@ -279,8 +280,9 @@ bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
 
 // Fill the time-parallel family's launch arguments and launch it.
 int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* workspace,
-                  uint32_t epoch, bool second, cudaStream_t st) {
+                  uint32_t epoch, bool second, cudaStream_t st, int window = 0) {
   b.epoch = epoch ? epoch : 1u;
+  b.pic_window = window;
   b.pic_Q = pp.Q;
   b.pic_TC = pp.TC;
   b.pic_W = pp.W;
@@ -291,7 +293,8 @@ int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* w
   b.pic_maxit = std::min(g_picard_maxit, p->NT + 1);
   b.pic_rtol = 2e-14;
   b.pic_timing = g_picard_timing;
-  b.tag_base = epoch * (uint32_t)(kPicMaxItCap + 2);
+  // one tag range per (call, time window)
+  b.tag_base = (epoch * (uint32_t)kPicMaxWindows + (uint32_t)window) * (uint32_t)(kPicMaxItCap + 2);
   b.status = reinterpret_cast<int*>(workspace);
   char* base = static_cast<char*>(workspace) + kStatusBytes +
                (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
@@ -792,15 +795,56 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   a.epoch = epoch;
   // time-parallel fused sweep (kq_picard.cuh), with the sequential kernel
-  // queued behind it as a conditional fall-back
-  PicPlan pp;
-  if (g_picard && pl.family == 0 && pl.spec && a.world == 1 && g_dev[dev].coop &&
-      picard_plan(p, g_dev[dev].sms, pp)) {
-    KqSweepArgs b = a;
-    b.pic_bw = 0;
-    rc = launch_picard(p, b, pp, workspace, epoch, second, st);
-    if (rc) return rc;
-    a.cond_epoch = epoch ? epoch : 1u;   // the sequential kernel below runs only on request
+  // queued behind it as a conditional fall-back.  The sweep may be cut into
+  // time windows that are solved one after the other (each a fixed-point
+  // problem of its own, started from the final states of the window before):
+  // needed when the state stores of the whole grid exceed shared memory, and
+  // faster for strongly coupled problems, where the number of rounds grows with
+  // the length of the interval (kq_problem.reserved = number of windows, 0 = as
+  // few as fit).
+  if (g_picard && pl.family == 0 && pl.spec && a.world == 1 && g_dev[dev].coop) {
+    int nwin = p->reserved > 0 ? std::min(p->reserved, kPicMaxWindows) : 1;
+    nwin = std::min(nwin, std::max(1, p->NT / 32));
+    kq_problem pw = *p;
+    PicPlan pp;
+    bool ok = false;
+    for (; nwin <= kPicMaxWindows && nwin <= std::max(1, p->NT / 8); nwin *= 2) {
+      pw.NT = (p->NT + nwin - 1) / nwin;
+      if (picard_plan(&pw, g_dev[dev].sms, pp)) {
+        ok = true;
+        break;
+      }
+      if (p->N < 2 || p->N > 4 || p->M != 2 || p->L != 1) break;   // not a size problem
+    }
+    if (ok && nwin > 1 && !phiT) ok = false;   // windows hand their final states on through phiT
+    if (ok) {
+      const int len = pw.NT;
+      const size_t row = (size_t)p->K * p->N;
+      for (int w = 0, n0 = 0; n0 < p->NT; ++w, n0 += len) {
+        const int n1 = std::min(p->NT, n0 + len);
+        pw.NT = n1 - n0;
+        pw.dt = p->dt + n0;
+        pw.shape = p->shape + n0;
+        PicPlan ppw;
+        if (!picard_plan(&pw, g_dev[dev].sms, ppw)) return fail(KQ_ERR_UNSUPPORTED, "window plan");
+        KqSweepArgs b = a;
+        b.NT = pw.NT;
+        b.dt = pw.dt;
+        b.shape = pw.shape;
+        b.pulses = guess_pulses + n0;
+        b.opt_pulses = opt_pulses + n0;
+        b.X = a.X + (size_t)n0 * row;
+        if (a.sigma) b.sigma = a.sigma + n0;
+        if (a.Phi0) b.Phi0 = a.Phi0 + (size_t)n0 * row;
+        if (a.store) b.store = a.store + (size_t)n0 * row;
+        if (w > 0) b.state0 = reinterpret_cast<const cplx*>(phiT);
+        b.pic_bw = 0;
+        b.pic_accumulate = (w > 0) ? 1 : 0;
+        rc = launch_picard(&pw, b, ppw, workspace, epoch, second, st, w);
+        if (rc) return rc;
+      }
+      a.cond_epoch = epoch ? epoch : 1u;   // the sequential kernel below runs only on request
+    }
   }
   if (pl.family == 0) {
     if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);

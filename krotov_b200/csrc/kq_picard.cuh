@@ -861,7 +861,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         double d = e0 + e1;   // eta = 0 beyond the grid
         if (n < NT) {
           if (SECOND) {
-            if (n > 0 && valid) {
+            if ((n > 0 || a.pic_window > 0) && valid) {   // delta phi = 0 at the first grid point
               double v2 = 0.0;
 #pragma unroll
               for (int r = 0; r < N; ++r) {
@@ -1044,14 +1044,14 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   }
   if (single) {
     const double ga = block_sum(ga_acc, scratch + 192);
-    if (tid == 0) a.g_a[0] = ga;
+    if (tid == 0) a.g_a[0] = a.pic_accumulate ? a.g_a[0] + ga : ga;
   } else if (blockIdx.x == 0) {
     // the owners' shares arrived with the last pulse (fixed summation order)
     const double ga = block_sum(ga_in, scratch + 192);
-    if (tid == 0) a.g_a[0] = ga;
+    if (tid == 0) a.g_a[0] = a.pic_accumulate ? a.g_a[0] + ga : ga;
   }
   if (tid == 0 && blockIdx.x == 0) {
-    a.status[2] = it;   // fixed-point rounds used (diagnostics)
+    a.status[2] = a.pic_accumulate ? a.status[2] + it : it;   // fixed-point rounds used (diagnostics)
     if (a.diag_out) {
       a.diag_out[0] = *reinterpret_cast<volatile int*>(a.status);
       a.diag_out[1] = 0;

@@ -64,6 +64,8 @@ struct KqSweepArgs {
   // only if status[1] == cond_epoch (0 = unconditional)
   uint32_t cond_epoch, epoch;
   int pic_timing;     // 1: CTA 0 writes per-phase cycle counts to status[16..]
+  int pic_window;     // index of the time window of a windowed update sweep
+  int pic_accumulate; // 1: add g_a and the round count to the values of the window before
   // fused Krotov iteration (k_krotov_picard): chi boundary and backward sweep
   // inside the kernel
   int pic_lw, pic_Wc;        // log2(pic_W); time steps reduced per CTA (even)

@@ -802,6 +802,11 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     result.optimized_controls = [
         pulse_onto_tlist(np.asarray(p)) for p in result.optimized_controls]
     result.gpu_launches = eng.launches
+    # diagnostics of the last update sweep: fixed-point rounds (0: sequential
+    # kernel) and whether the sequential kernel had to take over
+    _fb, _rounds = eng.sweep_diagnostics()
+    result.update_sweep_rounds = _rounds
+    result.sequential_fallback = bool(_fb != 0 and _fb == (eng.epoch & 0xFFFFFFFF))
     result.fused_iterations = n_fused
     result.h2d_bytes, result.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
     if shard is not None:

@@ -667,3 +667,30 @@ def test_lane_per_row_time_parallel_sweeps_match_sequential(krotov):
     assert rel(out[1][0][1:], out[0][0][1:]) < 1e-12
     assert np.allclose(out[1][1], out[0][1], rtol=0, atol=1e-12)
     assert np.allclose(out[1][2], out[0][2], rtol=0, atol=1e-12)
+
+
+def test_windowed_update_sweep_long_grid(krotov):
+    """nt = 5000: the state stores of the whole grid exceed shared memory, so
+    the one-launch kernel declines and kq_sweep_forward_update solves the
+    update sweep in time windows (each a fixed-point problem started from the
+    final states of the window before); same pulses as the sequential kernel
+    (picard option 0), and explicit window counts agree as well."""
+    lib = krotov._lib.load()
+    wl = krotov.workloads.tls_ensemble(K=16, nt=5000)
+    out = {}
+    for picard in (1, 0):
+        assert lib.kq_set_option(b"picard", picard) == 0
+        try:
+            out[picard] = krotov.optimize_pulses(
+                wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+                propagator=krotov.propagators.expm,
+                chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+                store_all_pulses=True)
+        finally:
+            lib.kq_set_option(b"picard", 1)
+    assert out[1].fused_iterations == 0      # outside the one-launch family
+    assert out[1].update_sweep_rounds > 0 and not out[1].sequential_fallback
+    for it in (1, 2):
+        assert rel(out[1].all_pulses[it], out[0].all_pulses[it]) < 1e-12
+    assert np.allclose(out[1].tau_vals[-1].astype(complex),
+                       out[0].tau_vals[-1].astype(complex), rtol=0, atol=1e-12)
