@@ -510,6 +510,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     spec = None         # the next iteration, if it was launched ahead
     X_spare = [None]    # second backward-state store for launches ahead
 
+    h2d_setup, d2h_setup = eng.h2d_bytes, eng.d2h_bytes   # traffic before the loop
+
     # ---- main loop (optimize.py:393-577) ----------------------------------
     for krotov_iteration in range(iter_start + 1, iter_stop + 1):
         logger.info("Started Krotov iteration %d", krotov_iteration)
@@ -809,6 +811,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     result.sequential_fallback = bool(_fb != 0 and _fb == (eng.epoch & 0xFFFFFFFF))
     result.fused_iterations = n_fused
     result.h2d_bytes, result.d2h_bytes = eng.h2d_bytes, eng.d2h_bytes
+    result.h2d_bytes_loop = eng.h2d_bytes - h2d_setup
+    result.d2h_bytes_loop = eng.d2h_bytes - d2h_setup
     if shard is not None:
         shard.close()
     if gather_comm is not None:
