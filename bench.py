@@ -20,8 +20,15 @@ Our arm prints ONE JSON line with
   cpu_baseline  the numpy oracle port of the reference loop timed on this
              box's host cores: the faster of the serial loop (bounded sample)
              and the reference's multi-process mode on all host cores.
+  parity     max relative deviation of the updated pulses (Krotov iterations
+             1..4, full workload) between the CUDA path and the CPU port
+             timed in the same run (tolerance 1e-10).
 The reference arm (--impl reference) times the oracle port (the reference is
-pure Python + QuTiP and cannot travel to the GPU box).
+pure Python + QuTiP and cannot travel to the GPU box): the
+faster of its serial loop and its multi-process mode on all host cores.
+With --gpus N > 1 the default is N independent replicas (one ensemble
+optimisation per GPU, "replicas only", scaling "weak"); --shard-mode
+exchange|gather|replicate select the distributions of one problem.
 """
 import argparse
 import json
@@ -125,12 +132,14 @@ class ClockSampler:
                     "samples": 0}
 
 
-def build_workload():
+def build_workload(replica=0):
+    """`replica` > 0 (multi-GPU 'independent' mode): the same ensemble with a
+    different guess amplitude -- an independent optimisation per GPU."""
     import krotov_b200 as krotov
     name = WORKLOAD['workload']
     if name == 'C4_tls_ensemble':
-        return krotov.workloads.tls_ensemble(K=WORKLOAD['K'],
-                                             nt=WORKLOAD['nt'])
+        return krotov.workloads.tls_ensemble(
+            K=WORKLOAD['K'], nt=WORKLOAD['nt'], ampl0=0.2 * (1 + 0.05 * replica))
     wl = krotov.workloads.by_name(name[:2])
     low = wl.lowered()
     WORKLOAD.update(K=wl.K, N=len(low['psi0'][0]), nt=wl.nt,
@@ -184,7 +193,7 @@ def time_oracle(wl, iters, k_sample=None):
     return per_iter, ks
 
 
-def time_oracle_parallel(wl, iters, warmup=1):
+def time_oracle_parallel(wl, iters, warmup=1, dump=None):
     """Seconds per Krotov iteration of the multi-process numpy port (the
     reference's parallel mode, parallelization.py:51-57: backward sweep
     parallel over the objectives, update/forward sweep synchronised per time
@@ -199,7 +208,7 @@ def time_oracle_parallel(wl, iters, warmup=1):
         fw_T = po.forward(pulses)
         tau = np.array([np.vdot(low['targets'][k], fw_T[k])
                         for k in range(K)])
-        times = []
+        times, history = [], []
         for it in range(warmup + iters):
             t0 = time.perf_counter()
             rec = po.iteration(pulses, fw_T, tau, orc.chis_re)
@@ -207,24 +216,28 @@ def time_oracle_parallel(wl, iters, warmup=1):
                 times.append(time.perf_counter() - t0)
             pulses, fw_T, tau = rec['optimized_pulses'], \
                 rec['fw_states_T'], rec['tau_vals']
+            history.append(np.array(pulses))
         nproc = po.nproc
+    if dump:   # pulses after Krotov iterations 1, 2, ... (parity check)
+        np.save(dump, np.array(history))
     return float(np.mean(times)), nproc
 
 
-def parallel_leg(wl, iters, warmup=1, in_subprocess=False):
+def parallel_leg(wl, iters, warmup=1, in_subprocess=False, dump=None):
     """cpu_baseline-style dict for the multi-process port.  With
     `in_subprocess` the workers are forked from a fresh interpreter (never
     from a process that holds a CUDA context)."""
     if in_subprocess:
         out = subprocess.run(
             [sys.executable, os.path.abspath(__file__), '--cpu-parallel-leg',
-             '--steps', str(iters), '--warmup', str(warmup)],
+             '--steps', str(iters), '--warmup', str(warmup)] +
+            (['--dump-pulses', dump] if dump else []),
             capture_output=True, text=True, timeout=600)
         for ln in reversed(out.stdout.strip().splitlines()):
             if ln.startswith('{'):
                 return json.loads(ln)
         raise RuntimeError('parallel leg failed: ' + out.stderr[-300:])
-    per_iter, nproc = time_oracle_parallel(wl, iters, warmup)
+    per_iter, nproc = time_oracle_parallel(wl, iters, warmup, dump)
     return {"value": 1.0 / per_iter, "unit": UNIT, "cores": nproc,
             "kind": "port", "host_cpus": os.cpu_count(),
             "sample": "%d Krotov iterations of the full workload (K=%d, "
@@ -346,14 +359,30 @@ def run_ours(args):
     if args.picard is not None:
         krotov._lib.check(krotov._lib.load().kq_set_option(
             b"picard", args.picard))
+    # Multi-GPU: where the library would only replicate the problem (the path
+    # does not shard at this size) bench.py runs N
+    # INDEPENDENT replicas, one ensemble optimisation per GPU, no collective
+    # on the data path ("replicas only"); --shard-mode selects the sharded
+    # (exchange / gather) or the redundant (replicate) distributions instead.
     wl = build_workload()
+    K = len(wl.Hs)
+    n_state = len(wl.lowered()['psi0'][0])
+    independent = False
+    if world > 1:
+        if args.shard_mode in ('auto', 'independent'):
+            independent = (args.shard_mode == 'independent' or (
+                args.engine != 'sweeps' and
+                GPUShards(mode='auto').choose(K, n_state) == 'replicate'))
+        if independent:
+            wl = build_workload(replica=rank)
     objectives = wl.objectives(krotov.Objective)
     (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(
         objectives, wl.pulse_options, wl.tlist)
-    K = len(objectives)
-    selector = GPUShards(mode=args.shard_mode)
-    n_state = len(wl.lowered()['psi0'][0])
+    selector = GPUShards(mode='auto' if args.shard_mode == 'independent'
+                         else args.shard_mode)
     mode = selector.choose(K, n_state) if world > 1 else None
+    if independent:
+        mode = 'replicate'   # every rank runs its own complete problem
     if args.engine == 'sweeps' and mode == 'replicate':
         mode = 'gather'
     lo, hi = shard_bounds(K, world, rank) if mode == 'exchange' else (0, K)
@@ -361,7 +390,8 @@ def run_ours(args):
                          wl.tlist)
     eng = SweepEngine(cp, shp, lam)
     shard = gather_comm = None
-    if mode == 'replicate' and not eng.fused_supported():
+    if mode == 'replicate' and not independent and \
+            not eng.fused_supported():
         mode = 'gather'
     if mode == 'exchange':
         shard = ShardComm(dist, None, eng.device).attach(eng)
@@ -459,7 +489,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = 1e3 / ms_per_step
+    # independent replicas: every rank completed its own iteration per step
+    units = world if independent else 1
+    value = units * 1e3 / ms_per_step
+    if dist is not None:
+        t = torch.tensor([launches], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches = int(t.item())
 
     # ---- end to end through the public API, host buffers ------------------
     stamps = []
@@ -474,7 +510,8 @@ def run_ours(args):
         wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
         propagator=krotov.propagators.expm,
         chi_constructor=chi_of(krotov, wl), info_hook=hook,
-        iter_stop=n_e2e, parallel_map=selector if world > 1 else None)
+        iter_stop=n_e2e,
+        parallel_map=selector if (world > 1 and not independent) else None)
     t_call = time.perf_counter() - t0
     steady = (stamps[-1] - stamps[args.warmup]) / args.steps
     e2e_value = 1.0 / steady
@@ -497,7 +534,7 @@ def run_ours(args):
     if dist is not None:
         t = torch.tensor([steady], dtype=torch.float64, device=eng.device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e["value"] = 1.0 / float(t.item())
+        e2e["value"] = units / float(t.item())
 
     # ---- roofline of the dominant kernel -----------------------------------
     peaks, which = load_peaks()
@@ -556,11 +593,30 @@ def run_ours(args):
                          % (ks, K, NT + 1, K, ks)}
 
     cpu_serial = cpu
+    parity = None
     if cpu is not None and WORKLOAD['workload'] == 'C4_tls_ensemble':
         try:   # reference's multi-process mode, all host cores
-            par = parallel_leg(wl, 3, 1, in_subprocess=True)
+            import tempfile
+            dump = os.path.join(tempfile.mkdtemp(), 'cpu_pulses.npy')
+            par = parallel_leg(wl, 3, 1, in_subprocess=True, dump=dump)
             if par["value"] > cpu["value"]:
                 cpu = par
+            # parity in the same run: the pulses after Krotov iterations
+            # 1..4 of the full workload, CUDA path vs the CPU port timed above
+            want = np.load(dump)[:, 0, :]
+            got = krotov.optimize_pulses(
+                wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+                propagator=krotov.propagators.expm,
+                chi_constructor=chi_of(krotov, wl), iter_stop=len(want),
+                store_all_pulses=True).all_pulses[-len(want):]
+            devs = [float(np.max(np.abs(np.array(g)[0] - w))
+                          / np.max(np.abs(w))) for g, w in zip(got, want)]
+            parity = {"max_rel_pulse_deviation": max(devs),
+                      "per_iteration": devs, "tolerance": 1e-10,
+                      "ok": bool(max(devs) <= 1e-10),
+                      "against": "numpy port (cpu_baseline leg of this run), "
+                                 "full workload, Krotov iterations 1..%d "
+                                 "from the same guess" % len(want)}
         except Exception as exc:  # pragma: no cover
             cpu_serial = dict(cpu_serial, parallel_leg_error=repr(exc))
 
@@ -576,15 +632,22 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+            "scaling": "weak" if (independent or world == 1) else "strong",
+            "vs_baseline": None, "dtype": "c128",
             "data": "synthetic",
             "config": dict(WORKLOAD, l2="flushed between timed iterations "
                            "(256 MB write)", parallelism=(
                                "1 GPU" if world == 1 else
+                               "%d independent replicas, one %d-objective "
+                               "ensemble optimisation per GPU (replicas only: "
+                               "the path does not shard at this size), value "
+                               "= iterations of all replicas / max time over "
+                               "ranks" % (world, K) if independent else
                                "%d GPUs, GPUShards mode '%s'" % (world, mode))),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu,
             "cpu_baseline_serial": cpu_serial, "cpu_baseline_c": cpu_c,
+            "parity": parity,
             "wall_seconds_timed_region": wall,
         }
         print(json.dumps(line))
@@ -605,7 +668,8 @@ def main():
     ap.add_argument('--no-cpu', action='store_true',
                     help='skip the CPU baseline leg')
     ap.add_argument('--shard-mode', default='auto',
-                    choices=['auto', 'exchange', 'gather', 'replicate'],
+                    choices=['auto', 'independent', 'exchange', 'gather',
+                             'replicate'],
                     help='multi-GPU distribution of the fused sweep')
     ap.add_argument('--engine', default='auto', choices=['auto', 'sweeps'],
                     help="'sweeps' forces the four-launch sweep sequence")
@@ -617,10 +681,12 @@ def main():
                          'additional measurements')
     ap.add_argument('--cpu-parallel-leg', action='store_true',
                     help='internal: print the multi-process CPU leg and exit')
+    ap.add_argument('--dump-pulses', default=None, help='internal')
     args = ap.parse_args()
     if args.cpu_parallel_leg:
         print(json.dumps(parallel_leg(build_workload(), args.steps,
-                                      max(args.warmup, 1))))
+                                      max(args.warmup, 1),
+                                      dump=args.dump_pulses)))
         return
     if args.workload == 'C4sat':
         WORKLOAD.update(workload='C4_tls_ensemble', K=131072)

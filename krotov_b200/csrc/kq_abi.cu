@@ -60,6 +60,7 @@ Scratch g_scratch[kMaxDevices];
 bool g_disable_segments = false;   // kq_set_option("time_parallel", 0)
 int g_picard = 1;                  // kq_set_option("picard", 0|1|2): off / auto / forced
 int g_picard_timing = 0;
+int g_picard_history = 1;          // kq_set_option("picard_history", 0|1): update-history hint
 int g_picard_maxit = 64;           // kq_set_option("picard_maxit", n)
 constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
 constexpr int kPicMaxItCap = 1000;
@@ -242,6 +243,7 @@ struct PicPlan {
 };
 // slots per mailbox / per owner region: grid * 2^lwc + grid <= 2 NT + 19 * 148
 size_t pic_stride(const kq_problem* p) { return (size_t)2 * round_up(p->NT, 64) + 2880; }
+int pic_hist_ld(const kq_problem* p) { return round_up(p->NT, 16); }
 bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
   const int K = p->K, N = p->N, NT = p->NT, NN = N * N;
   if (N < 2 || N > 4 || p->M != 2 || p->L != 1) return false;
@@ -300,6 +302,13 @@ int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* w
                (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
   b.pic_part = reinterpret_cast<KqSlot*>(base);
   b.pic_eps = b.pic_part + (size_t)kPicMaxBlocks * pp.stride;
+  if (b.pic_bw && window == 0 && g_picard_history) {
+    // whole-iteration calls keep the last updates in the workspace (first-iterate hint)
+    char* hist = reinterpret_cast<char*>(b.pic_eps + (size_t)kPicMaxBlocks * pp.stride);
+    b.pic_hist_hdr = reinterpret_cast<unsigned long long*>(hist);
+    b.pic_hist = reinterpret_cast<double*>(hist + 64);
+    b.pic_hist_ld = pic_hist_ld(p);
+  }
   Plan ppl;
   std::memset(&ppl, 0, sizeof ppl);
   ppl.grid = pp.grid;
@@ -619,6 +628,10 @@ int kq_set_option(const char* name, int value) {
     g_picard_timing = value ? 1 : 0;
     return KQ_OK;
   }
+  if (name && std::strcmp(name, "picard_history") == 0) {
+    g_picard_history = value ? 1 : 0;
+    return KQ_OK;
+  }
   if (name && std::strcmp(name, "picard_maxit") == 0) {
     if (value < 1 || value > kPicMaxItCap) return fail(KQ_ERR_ARG, "picard_maxit out of range");
     g_picard_maxit = value;
@@ -682,8 +695,10 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* st
 
 size_t kq_workspace_bytes(const kq_problem* p) {
   size_t bytes = kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
-  if (p && p->NT > 0)   // slots of the time-parallel fused sweep: part | eps | ga
+  if (p && p->NT > 0) {   // slots of the time-parallel fused sweep: part | eps | ga
     bytes += (size_t)2 * kPicMaxBlocks * pic_stride(p) * sizeof(KqSlot);
+    bytes += 64 + (size_t)4 * pic_hist_ld(p) * sizeof(double);   // update history: header | ring
+  }
   return bytes;
 }
 

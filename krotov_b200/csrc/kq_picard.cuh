@@ -495,6 +495,12 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       pic_prefetch_l2(a.pulses + n);
       pic_prefetch_l2(a.shape + n);
       if (a.pic_hint) pic_prefetch_l2(a.pic_hint + n);
+      if (a.pic_hist_hdr) {
+        pic_prefetch_l2(a.pic_hist + n);
+        pic_prefetch_l2(a.pic_hist + a.pic_hist_ld + n);
+        pic_prefetch_l2(a.pic_hist + 2 * (size_t)a.pic_hist_ld + n);
+        pic_prefetch_l2(a.pic_hist + 3 * (size_t)a.pic_hist_ld + n);
+      }
     }
   }
 
@@ -537,9 +543,34 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   // buffer 1: the first iterate = the guess pulse or, with the guess of the
   // iteration before, the guess plus the previous update (successive Krotov
   // updates are similar: saves about one round)
+  // ... or, with the updates of up to three iterations before in the workspace
+  // (valid if this guess sits where the last update was written), the guess
+  // plus the polynomial extrapolation of the update: D1 | 2 D1 - D2 |
+  // 3 D1 - 3 D2 + D3 (each order cuts the error of the first iterate ~4x: about
+  // one round less).  A hint only: the fixed point does not depend on it.
+  int hcnt = 0, hhead = 0;
+  if (a.pic_hist_hdr) {
+    const unsigned long long key = a.pic_hist_hdr[0], ch = a.pic_hist_hdr[1];
+    hhead = (int)(ch >> 32) & 3;
+    if (key == (unsigned long long)(uintptr_t)a.pulses) hcnt = min((int)(ch & 0xffffffffu), 3);
+  }
+  const double* hD1 = a.pic_hist + (size_t)((hhead + 3) & 3) * a.pic_hist_ld;
+  const double* hD2 = a.pic_hist + (size_t)((hhead + 2) & 3) * a.pic_hist_ld;
+  const double* hD3 = a.pic_hist + (size_t)((hhead + 1) & 3) * a.pic_hist_ld;
+  const double hc1 = (double)hcnt, hc2 = (hcnt == 3) ? -3.0 : -1.0;
   for (int n = tid; n < NTP; n += BT) {
     const double gn = (n < NT) ? a.pulses[n] : 0.0;
-    const double e = (a.pic_hint && n < NT) ? gn + (gn - a.pic_hint[n]) : gn;
+    double e = gn;
+    if (n < NT) {
+      if (hcnt > 0) {
+        double d = hc1 * hD1[n];
+        if (hcnt > 1) d = fma(hc2, hD2[n], d);
+        if (hcnt > 2) d += hD3[n];
+        e = gn + d;
+      } else if (a.pic_hint) {
+        e = gn + (gn - a.pic_hint[n]);
+      }
+    }
     seps0[(n & (W - 1)) * TC + (n >> lw)] = gn;
     seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
     if (n < NT) {
@@ -1026,6 +1057,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
 
   if (!converged) {
     if (blockIdx.x == 0 && tid == 0) {
+      if (a.pic_hist_hdr) a.pic_hist_hdr[1] = 0ull;   // no update: the history ends here
       a.status[1] = (int)a.epoch;
       atomicCAS(a.status + 3, 0, (int)a.epoch);   // first epoch that did not converge
       if (!(em < kInf)) atomicExch(a.status, (int)-4);
@@ -1040,7 +1072,18 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   }
   // ---- outputs ----------------------------------------------------------------
   if (blockIdx.x == 0) {
-    for (int n = tid; n < NT; n += BT) a.opt_pulses[n] = seps[(n & (W - 1)) * TC + (n >> lw)];
+    double* hnew = a.pic_hist_hdr ? a.pic_hist + (size_t)hhead * a.pic_hist_ld : nullptr;
+    for (int n = tid; n < NT; n += BT) {
+      const double en = seps[(n & (W - 1)) * TC + (n >> lw)];
+      a.opt_pulses[n] = en;
+      if (hnew) hnew[n] = en - a.pulses[n];   // this update, for the next first iterate
+    }
+    if (hnew && tid == 0) {
+      // every CTA read the header before its first exchange round, i.e. long ago
+      a.pic_hist_hdr[0] = (unsigned long long)(uintptr_t)a.opt_pulses;
+      a.pic_hist_hdr[1] = ((unsigned long long)((hhead + 1) & 3) << 32) |
+                          (unsigned long long)min(hcnt + 1, 3);
+    }
   }
   if (single) {
     const double ga = block_sum(ga_acc, scratch + 192);

@@ -80,6 +80,12 @@ struct KqSweepArgs {
   cplx* tau_out;
   const cplx* phiT_in;
   const double* pic_hint;    // [NT] guess pulse of the iteration before, or null
+  // history of the last Krotov updates in the caller's workspace (kq_krotov_iteration):
+  // header {key = address the next guess is expected at, count, head} + ring of
+  // 4 x pic_hist_ld doubles; the first iterate extrapolates the update from it
+  unsigned long long* pic_hist_hdr;
+  double* pic_hist;
+  int pic_hist_ld;
   cplx* Xout;                // [NT+1][K][N] or null
   cplx* chi_out;             // [K][N] or null
   double* chi_norms_out;     // [K] or null

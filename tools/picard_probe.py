@@ -8,7 +8,11 @@ from oracle import krotov_oracle as orc
 def probe(name, iters=2, **kw):
     wl = workloads.by_name(name, **kw)
     low = wl.lowered()
-    chi = {'re': orc.chis_re, 'ss': orc.chis_ss, 'sm': orc.chis_sm, 'hs': orc.chis_hs}[wl.chi]
+    if wl.chi == 'qubit_reset':
+        fixed = wl.meta['chi_fixed'].reshape(-1, order='F')
+        chi = lambda fw, targets, tau, weights=None: [fixed.copy() for _ in fw]
+    else:
+        chi = {'re': orc.chis_re, 'ss': orc.chis_ss, 'sm': orc.chis_sm, 'hs': orc.chis_hs}[wl.chi]
     rec = orc.optimize(low['terms'], low['psi0'], low['targets'], low['pulses'], low['shapes'],
                        low['lambdas'], low['tlist'], chi, iter_stop=iters, is_super=low['is_super'],
                        operator_norm='fro')
