@@ -364,6 +364,9 @@ def run_ours(args):
     # INDEPENDENT replicas, one ensemble optimisation per GPU, no collective
     # on the data path ("replicas only"); --shard-mode selects the sharded
     # (exchange / gather) or the redundant (replicate) distributions instead.
+    if args.picard_history is not None:
+        krotov._lib.check(krotov._lib.load().kq_set_option(
+            b"picard_history", args.picard_history))
     wl = build_workload()
     K = len(wl.Hs)
     n_state = len(wl.lowered()['psi0'][0])
@@ -676,6 +679,9 @@ def main():
     ap.add_argument('--picard', type=int, default=None, choices=[0, 1, 2],
                     help='time-parallel fused sweep: 0 off (sequential '
                          'kernel), 1 on (library default)')
+    ap.add_argument('--picard-history', type=int, default=None,
+                    choices=[0, 1], help='update-history first iterate of '
+                    'the fixed-point kernel (library default: on)')
     ap.add_argument('--workload', default='C4',
                     help='C4 (contract workload) or C1/C2/C3/C5/C4sat for '
                          'additional measurements')

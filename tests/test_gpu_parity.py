@@ -694,3 +694,38 @@ def test_windowed_update_sweep_long_grid(krotov):
         assert rel(out[1].all_pulses[it], out[0].all_pulses[it]) < 1e-12
     assert np.allclose(out[1].tau_vals[-1].astype(complex),
                        out[0].tau_vals[-1].astype(complex), rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('hooked', [False, True])
+def test_fused_iteration_update_history_hint(krotov, hooked):
+    """The first iterate of the fixed-point kernel extrapolates the last
+    updates kept in the workspace (kq_set_option picard_history).  A hint
+    only: pulses with and without it agree to rounding, also when a hook
+    modifies lambda_a in between (launch-ahead discarded, history stale)."""
+    lib = krotov._lib.load()
+    wl = krotov.workloads.tls_ensemble(K=128, nt=1000)
+
+    def halve(**kw):     # like tests/test_infohooks.py:30-37
+        if kw['iteration'] in (3, 5):
+            kw['lambda_vals'][0] *= 0.5
+
+    def fid(**kw):
+        return np.average(np.array(kw['tau_vals']).real)
+
+    runs = []
+    try:
+        for hist in (0, 1):
+            assert lib.kq_set_option(b"picard_history", hist) == 0
+            runs.append(krotov.optimize_pulses(
+                wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+                propagator=krotov.propagators.expm,
+                chi_constructor=krotov.functionals.chis_re, iter_stop=8,
+                info_hook=fid if hooked else None,
+                modify_params_after_iter=halve if hooked else None,
+                store_all_pulses=True))
+    finally:
+        lib.kq_set_option(b"picard_history", 1)
+    assert runs[0].fused_iterations == runs[1].fused_iterations == 8
+    for a, b in zip(runs[0].all_pulses, runs[1].all_pulses):
+        assert rel(a, b) < 1e-13
