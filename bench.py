@@ -315,7 +315,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_iter * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "c128",
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128",
         "data": "synthetic", "config": dict(WORKLOAD),
         "cpu_baseline": best,
         "cpu_baseline_serial": serial,

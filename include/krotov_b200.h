@@ -110,7 +110,9 @@ const char* kq_last_error(void);
  * kq_sweep_forward_update uses the time-parallel fixed-point kernels where the
  * problem allows (0: always the sequential kernels); "picard_maxit" (default
  * 64): rounds before the time-parallel sweep gives up; "picard_timing": per
- * phase cycle counts in workspace status words 16..25.
+ * phase cycle counts in workspace status words 16..25; "picard_history"
+ * (default 1): kq_krotov_iteration starts the fixed-point iteration from the
+ * extrapolation of the updates of the calls before (kept in the workspace).
  * "time_parallel" (default 1): propagation
  * sweeps under known pulses (kq_propagate_forward, kq_sweep_backward*) are cut
  * into time segments that run concurrently (segment propagators -> boundary
@@ -192,7 +194,11 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses,
  * prev_guess_pulses (may be NULL, may alias opt_pulses) = the guess pulses of
  * the Krotov iteration before: the fixed-point iteration then starts from
  * guess + (guess - prev_guess) instead of guess (a hint only: the result does
- * not depend on it beyond rounding).
+ * not depend on it beyond rounding).  The kernel also keeps the last three
+ * updates (opt - guess) in `workspace`; when guess_pulses is the buffer the
+ * previous call wrote its opt_pulses to, the first iterate is the guess plus
+ * the polynomial extrapolation of those updates instead (about one to two
+ * rounds fewer; option "picard_history", default 1).
  * sigma/Phi0/Phi1 as in kq_sweep_forward_update.  tau_in/phiT_in must not alias
  * tau_out/phiT_out.  Returns KQ_ERR_UNSUPPORTED when the problem is outside the
  * family (N in 2..4, two generator terms, one pulse, single GPU, state stores
