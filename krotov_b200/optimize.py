@@ -12,6 +12,7 @@ without hooks needs no host round trip at all.  Host callbacks
 `check_convergence`, ``sigma.refresh``) keep their reference signatures and
 run once per iteration.
 """
+import collections
 import copy
 import logging
 import time
@@ -43,8 +44,10 @@ _BUILTIN_CHI = {
 
 class _PackedResults:
     """Pulses | g_a | tau | status words of one iteration in ONE device buffer
-    (two of them, alternating), so that an iteration with host hooks needs a
-    single device->host copy into pinned memory and one synchronisation."""
+    (three of them, iteration j uses buffer j % 3: up to two iterations are
+    launched ahead of the one whose hooks run), so that an iteration with host
+    hooks needs a single device->host copy into pinned memory and one
+    synchronisation."""
 
     def __init__(self, torch, device, L, NT, K):
         def up16(x):
@@ -55,7 +58,7 @@ class _PackedResults:
         self.o_diag = self.o_tau + K * 16
         self.nbytes = self.o_diag + 16
         self.dev = [torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
-                    for _ in (0, 1)]
+                    for _ in (0, 1, 2)]
         self.host = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
         self.hnp = self.host.numpy()
         self.views = [self._views(r) for r in self.dev]
@@ -507,8 +510,23 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     if host_loop and shard is None:
         packed = _PackedResults(torch, eng.device, L, NT, cp.K)
     ri = 0
-    spec = None         # the next iteration, if it was launched ahead
-    X_spare = [None]    # second backward-state store for launches ahead
+    # Hooked iterations rotate through three sets of output buffers (iteration
+    # j: packed buffer, phi(T) and backward-state store number j % 3), so that
+    # iterations j+1 and j+2 can be in flight while the hooks of j read j's.
+    ahead = collections.deque()   # iterations launched ahead, oldest first
+    phiT_ring = [None, None, None]
+    X_ring = [None, None, None]
+
+    def ring_phiT(m):
+        if phiT_ring[m % 3] is None:
+            phiT_ring[m % 3] = eng.new_states()
+        return phiT_ring[m % 3]
+
+    def ring_X(m):
+        if X_ring[m % 3] is None:
+            X_ring[m % 3] = eng.X if all(x is None for x in X_ring) \
+                else eng.new_state_store()
+        return X_ring[m % 3]
 
     h2d_setup, d2h_setup = eng.h2d_bytes, eng.d2h_bytes   # traffic before the loop
 
@@ -559,10 +577,14 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
 
         if packed is not None:
             # this iteration's outputs live in one buffer
+            ri = krotov_iteration % 3
             pv = packed.views[ri]
             opt_t = pv['pulses']
             spare['tau'] = pv['tau']
             eng.g_a = pv['g_a']
+            spare['phiT'] = ring_phiT(krotov_iteration)
+            if info_hook is not None:
+                eng.X = ring_X(krotov_iteration)
         spare_phiT = spare['phiT']
         spare_tau = spare['tau'] if has_targets else None
         # the buffer about to receive the optimized pulses still holds the
@@ -570,14 +592,14 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         prev_guess_t = prev_guess_ref
         ran_fused = False
         launch_epoch = None
-        if spec is not None:
-            # this iteration was launched ahead, while the hooks of the
-            # previous one were running; its buffers are exactly the ones
+        if ahead and ahead[0]['iteration'] != krotov_iteration:
+            ahead.clear()   # cannot happen; never consume a stale launch
+        if ahead:
+            # this iteration was launched ahead, while the hooks of an
+            # earlier one were running; its buffers are exactly the ones
             # selected above
             ran_fused = True
-            launch_epoch = spec['epoch']
-            eng.X = spec['X']
-            spec = None
+            launch_epoch = ahead.popleft()['epoch']
         elif use_fused:
             try:
                 # chi boundary, both sweeps and tau in ONE launch
@@ -605,6 +627,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 # untouched; repeat with the sweep kernels and stay there
                 ran_fused = use_fused = False
                 fetched = None
+                ahead.clear()   # launched with the outputs this one never wrote
                 eng.clear_fused_failure()
         if ran_fused:
             new_phiT, new_tau = spare_phiT, spare_tau
@@ -640,28 +663,37 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         if packed is not None:
             if fetched is None:
                 fetched = packed.fetch(ri, eng)    # synchronises the stream
-            ri ^= 1
             if (ran_fused and use_fused and chi_kind is not None
-                    and not second_order
-                    and krotov_iteration < static['iter_stop']):
-                # Launch the NEXT iteration now, so that the device works
-                # while the hooks of this one run.  It reads this
-                # iteration's outputs and writes only buffers nothing else
-                # refers to any more; if a hook then modifies the pulses or
-                # lambda_a, or the loop ends, the launch is simply discarded
-                # (and repeated with the modified inputs).
-                pv2 = packed.views[ri]
-                eng.g_a = pv2['g_a']
-                if info_hook is not None:
-                    if X_spare[0] is None:
-                        X_spare[0] = eng.new_state_store()
-                    eng.X, X_spare[0] = X_spare[0], eng.X
-                eng.krotov_iteration(
-                    chi_kind, opt_t, pv2['pulses'], phiT, tau_t,
-                    spare['phiT'], pv2['tau'] if has_targets else None,
-                    store_X=info_hook is not None, prev_guess_t=guess_t,
-                    diag_t=pv2['diag'])
-                spec = dict(epoch=eng.epoch, X=eng.X)
+                    and not second_order):
+                # Launch the NEXT TWO iterations now, so that the device never
+                # waits for the host: while the hooks of iteration j run, j+1
+                # executes and j+2 is queued behind it.  Each reads the
+                # outputs of the one before and writes only buffers nothing
+                # else refers to (sets (j+1) % 3, (j+2) % 3); if a hook then
+                # modifies the pulses or lambda_a, or the loop ends, the
+                # launches are simply discarded (and repeated with the
+                # modified inputs).
+                last = ahead[-1] if ahead else dict(
+                    iteration=krotov_iteration, guess=guess_t, opt=opt_t,
+                    phiT=phiT, tau=tau_t)
+                while len(ahead) < 2 and \
+                        last['iteration'] < static['iter_stop']:
+                    m = last['iteration'] + 1
+                    pvm = packed.views[m % 3]
+                    eng.g_a = pvm['g_a']
+                    if info_hook is not None:
+                        eng.X = ring_X(m)
+                    phiT_m = ring_phiT(m)
+                    tau_m = pvm['tau'] if has_targets else None
+                    eng.krotov_iteration(
+                        chi_kind, last['opt'], pvm['pulses'], last['phiT'],
+                        last['tau'], phiT_m, tau_m,
+                        store_X=info_hook is not None,
+                        prev_guess_t=last['guess'], diag_t=pvm['diag'])
+                    last = dict(iteration=m, guess=last['opt'],
+                                opt=pvm['pulses'], phiT=phiT_m, tau=tau_m,
+                                epoch=eng.epoch)
+                    ahead.append(last)
             optimized_pulses = [fetched[0][l].copy() for l in range(L)]
             g_a_integrals[:] = fetched[1][:L]
             tau_vals = fetched[2].copy() if tau_t is not None \
@@ -697,11 +729,11 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             if not np.array_equal(lam_snapshot, np.asarray(lambda_vals)):
                 eng.set_lambda(lambda_vals)
                 lam_snapshot = np.array(lambda_vals, dtype=np.float64)
-                spec = None      # launched ahead with the old lambda_a
+                ahead.clear()    # launched ahead with the old lambda_a
             if not all(np.array_equal(a, b) for a, b
                        in zip(optimized_pulses, opt_snapshot)):
                 opt_t.copy_(eng.pulses_to_device(optimized_pulses))
-                spec = None      # launched ahead with the unmodified pulses
+                ahead.clear()    # launched ahead with the unmodified pulses
         result.iters.append(krotov_iteration)
         result.iter_seconds.append(int(toc - tic))
         result.iter_seconds_device.append(toc - tic)
