@@ -235,6 +235,16 @@ int kq_chi_boundary(const kq_problem* p, int kind, int32_t K_total,
                     const kq_c128* tau_sum, kq_c128* chi_out,
                     double* chi_norms, void* stream);
 
+/* Asynchronous device->host copy of one iteration's packed results (pulses |
+ * g_a | tau | status words, written by kq_krotov_iteration into caller-owned
+ * device memory) into pinned host memory, on `stream` -- normally a copy
+ * stream that waits on an event recorded behind that iteration's launch, so
+ * that iterations already queued behind it do not delay the hooks
+ * (reference: the per-iteration results handed to info_hook,
+ * optimize.py:511-533). */
+int kq_fetch_results(void* dst_host, const void* src_device, size_t nbytes,
+                     void* stream);
+
 /* out[k] = <a_k | b_k> for K vectors of length N (tau_vals). */
 int kq_overlaps(int32_t K, int32_t N, const kq_c128* a, const kq_c128* b,
                 kq_c128* out, void* stream);

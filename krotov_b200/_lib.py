@@ -92,6 +92,8 @@ _SIGNATURES = {
         ctypes.POINTER(KqProblem), ctypes.c_int, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    'kq_fetch_results': (ctypes.c_int, [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     'kq_overlaps': (ctypes.c_int, [
         ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p]),

@@ -955,6 +955,13 @@ int kq_chi_boundary(const kq_problem* p, int kind, int32_t K_total, const kq_c12
   return KQ_OK;
 }
 
+int kq_fetch_results(void* dst_host, const void* src_device, size_t nbytes, void* stream) {
+  if (!dst_host || !src_device) return fail(KQ_ERR_ARG, "NULL argument to kq_fetch_results");
+  KQ_CUDA(cudaMemcpyAsync(dst_host, src_device, nbytes, cudaMemcpyDeviceToHost,
+                          static_cast<cudaStream_t>(stream)));
+  return KQ_OK;
+}
+
 int kq_overlaps(int32_t K, int32_t N, const kq_c128* a, const kq_c128* b, kq_c128* out,
                 void* stream) {
   if (K < 1 || N < 1 || !a || !b || !out) return fail(KQ_ERR_ARG, "invalid argument");

@@ -79,6 +79,7 @@ class SweepEngine:
         self._p = ctypes.byref(self.problem)
         nbytes = self.lib.kq_workspace_bytes(self._p)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self._iter_args = {}    # marshalled kq_krotov_iteration arguments
         self.epoch = 0
         self.comm = None      # KqComm: per-time-step exchange ('exchange' mode)
         self.gather = None    # dict set by ShardComm.attach_gather
@@ -90,8 +91,14 @@ class SweepEngine:
 
     # -- helpers -----------------------------------------------------------
     def _stream(self):
-        return ctypes.c_void_p(
-            self.torch.cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(self.raw_stream())
+
+    def raw_stream(self):
+        """cudaStream_t of torch's current stream on this device."""
+        try:
+            return self.torch._C._cuda_getCurrentRawStream(self.device.index)
+        except Exception:   # pragma: no cover
+            return self.torch.cuda.current_stream(self.device).cuda_stream
 
     def new_state_store(self):
         return self.torch.empty((self.cp.NT + 1, self.cp.K, self.cp.N),
@@ -196,19 +203,35 @@ class SweepEngine:
         iteration before, a starting hint for the fixed-point iteration."""
         self.epoch += 1
         kind = -1 if chi_kind is None else CHI_KINDS[chi_kind]
+        # the pointer arguments repeat with the rotating buffer sets of the
+        # caller: marshal them once per combination (the cache keeps the
+        # tensors alive, so an id cannot be re-used by another tensor)
+        tensors = (tau_in, phiT_in, guess_t, prev_guess_t, opt_t, phiT_out,
+                   tau_out, self.X if store_X else None, sigma_t, Phi0, Phi1,
+                   self.g_a, diag_t)
+        key = (kind,) + tuple(map(id, tensors))
+        hit = self._iter_args.get(key)
+        if hit is None:
+            if len(self._iter_args) >= 32:
+                self._iter_args.clear()
+
+            def ptr(t):
+                return 0 if t is None else t.data_ptr()
+            hit = (tensors, (
+                self._p, kind, self.cp.K, ptr(self.t_targets),
+                ptr(self.t_weights),
+                ptr(self.chi if kind < 0 else None),
+                ptr(self.chi_norms if kind < 0 else None),
+                ptr(tau_in), ptr(phiT_in), ptr(guess_t), ptr(prev_guess_t),
+                ptr(opt_t), ptr(self.t_psi0), ptr(phiT_out), ptr(tau_out),
+                ptr(self.X if store_X else None),
+                ptr(None if kind < 0 else self.chi),
+                ptr(None if kind < 0 else self.chi_norms),
+                ptr(sigma_t), ptr(Phi0), ptr(Phi1), ptr(self.g_a),
+                ptr(diag_t), ptr(self.workspace)))
+            self._iter_args[key] = hit
         check(self.lib.kq_krotov_iteration(
-            self._p, kind, self.cp.K, _ptr(self.t_targets),
-            _ptr(self.t_weights),
-            _ptr(self.chi if kind < 0 else None),
-            _ptr(self.chi_norms if kind < 0 else None),
-            _ptr(tau_in), _ptr(phiT_in), _ptr(guess_t), _ptr(prev_guess_t),
-            _ptr(opt_t), _ptr(self.t_psi0), _ptr(phiT_out), _ptr(tau_out),
-            _ptr(self.X if store_X else None),
-            _ptr(None if kind < 0 else self.chi),
-            _ptr(None if kind < 0 else self.chi_norms),
-            _ptr(sigma_t), _ptr(Phi0), _ptr(Phi1), _ptr(self.g_a),
-            _ptr(diag_t), _ptr(self.workspace),
-            ctypes.c_uint32(self.epoch & 0xFFFFFFFF), self._stream()))
+            *hit[1], self.epoch & 0xFFFFFFFF, self.raw_stream()))
         self.launches += 1
 
     def fused_supported(self):

@@ -23,6 +23,7 @@ from . import functionals as _functionals
 from .compiler import compile_problem, initialize_controls
 from .conversions import control_onto_interval, pulse_onto_tlist
 from ._lib import KqError
+from ._lib import check as _check
 from .engine import SweepEngine
 from .info_hooks import chain
 from .mu import derivative_wrt_pulse
@@ -62,6 +63,19 @@ class _PackedResults:
         self.host = torch.zeros(self.nbytes, dtype=torch.uint8).pin_memory()
         self.hnp = self.host.numpy()
         self.views = [self._views(r) for r in self.dev]
+        # results are copied on a stream of their own, behind an event that
+        # follows the iteration's launch: iterations already queued behind it
+        # on the compute stream do not delay the copy
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.events = [torch.cuda.Event() for _ in self.dev]
+        self.marked = [False] * len(self.dev)
+        self._host_ptr = self.host.data_ptr()
+        self._dev_ptr = [r.data_ptr() for r in self.dev]
+
+    def mark(self, i, eng):
+        """Record 'buffer i is complete' behind the launch just made."""
+        self.events[i].record(self.torch.cuda.current_stream(eng.device))
+        self.marked[i] = True
 
     def _views(self, r):
         t, L, NT, K = self.torch, self.L, self.NT, self.K
@@ -77,8 +91,15 @@ class _PackedResults:
         g_a [L], tau [K], status words)."""
         if not diag_written:
             self.views[i]['diag'].copy_(eng.workspace[:16])
-        self.host.copy_(self.dev[i], non_blocking=True)
-        self.torch.cuda.current_stream(eng.device).synchronize()
+            self.marked[i] = False
+        if not self.marked[i]:
+            self.events[i].record(self.torch.cuda.current_stream(eng.device))
+        self.marked[i] = False
+        self.copy_stream.wait_event(self.events[i])
+        _check(eng.lib.kq_fetch_results(
+            self._host_ptr, self._dev_ptr[i], self.nbytes,
+            self.copy_stream.cuda_stream))
+        self.copy_stream.synchronize()
         eng.d2h_bytes += self.nbytes
         h, L, NT, K = self.hnp, self.L, self.NT, self.K
         pulses = h[:L * NT * 8].view(np.float64).reshape(L, NT)
@@ -611,6 +632,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     diag_t=pv['diag'] if packed is not None else None)
                 ran_fused = True
                 launch_epoch = eng.epoch
+                if packed is not None:
+                    packed.mark(ri, eng)
             except KqError as exc:
                 if 'error -3' not in str(exc):
                     raise
@@ -690,6 +713,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                         last['tau'], phiT_m, tau_m,
                         store_X=info_hook is not None,
                         prev_guess_t=last['guess'], diag_t=pvm['diag'])
+                    packed.mark(m % 3, eng)
                     last = dict(iteration=m, guess=last['opt'],
                                 opt=pvm['pulses'], phiT=phiT_m, tau=tau_m,
                                 epoch=eng.epoch)
