@@ -532,6 +532,11 @@ def run_ours(args):
            "whole_call_value": n_e2e / t_call,
            "whole_call_seconds": t_call,
            "api": "krotov_b200.optimize_pulses(numpy objectives, info_hook)",
+           "note": "hooked iterations are pipelined: two iterations are "
+                   "launched ahead of the one whose hook runs and results "
+                   "are fetched on a copy stream, so iterations run back to "
+                   "back with a warm L2 -- e2e can exceed `value`, which "
+                   "flushes L2 before every (isolated, event-timed) iteration",
            "measured_total_h2d_bytes": res.h2d_bytes,
            "measured_total_d2h_bytes": res.d2h_bytes}
     if dist is not None:

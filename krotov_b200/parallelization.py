@@ -32,7 +32,9 @@ import numpy as np
 from . import _lib
 from ._lib import KqComm, check
 
-__all__ = ['GPUShards', 'shard_bounds', 'ShardComm', 'USE_THREADPOOL_LIMITS']
+__all__ = ['GPUShards', 'shard_bounds', 'ShardComm', 'USE_THREADPOOL_LIMITS',
+           'serial_map', 'parallel_map', 'parallel_map_fw_prop_step',
+           'set_parallelization']
 
 USE_THREADPOOL_LIMITS = True
 
@@ -250,3 +252,47 @@ class ShardComm:
         v = self.torch.view_as_real(t) if t.dtype.is_complex else t
         self.dist.all_reduce(v, group=self.group)
         return t
+
+
+# --- names of the reference's process-level maps ------------------------------
+# The reference parallelises over objectives with Python process pools
+# (parallelization.py:233-311, 433-495).  Here all objectives of a sweep run in
+# one kernel launch, so `optimize_pulses` accepts these maps in `parallel_map`
+# for source compatibility and ignores them; called directly they are plain
+# serial maps with the interface of qutip.parallel.serial_map.
+
+def serial_map(task, values, task_args=None, task_kwargs=None, **kwargs):
+    """``[task(value, *task_args, **task_kwargs) for value in values]``
+    (interface of :func:`qutip.parallel.serial_map`, the reference's default
+    map, optimize.py:266-269)."""
+    task_args = () if task_args is None else task_args
+    task_kwargs = {} if task_kwargs is None else task_kwargs
+    return [task(value, *task_args, **task_kwargs) for value in values]
+
+
+def parallel_map(task, values, task_args=None, task_kwargs=None,
+                 num_cpus=None, progress_bar=None):
+    """Signature of the reference's process-pool map
+    (parallelization.py:233-240); evaluated serially -- the GPU engine does
+    not use process-level parallelism."""
+    return serial_map(task, values, task_args, task_kwargs)
+
+
+def parallel_map_fw_prop_step(shared, values, task_args):
+    """Marker for the third entry of the reference's ``parallel_map`` tuple
+    (parallelization.py:433-495).  The per-time-step synchronisation it
+    implements with consumer processes happens inside the update kernel
+    here; `optimize_pulses` never calls it."""
+    raise NotImplementedError(
+        "parallel_map_fw_prop_step is only accepted as a marker in "
+        "optimize_pulses(parallel_map=...); the time-step exchange runs "
+        "inside the CUDA kernels")
+
+
+def set_parallelization(use_loky=False, start_method=None, loky_pickler=None,
+                        use_threadpool_limits=True):
+    """Accepted for compatibility (parallelization.py:176-230); only
+    `use_threadpool_limits` is recorded, nothing else applies to the GPU
+    engine."""
+    global USE_THREADPOOL_LIMITS
+    USE_THREADPOOL_LIMITS = bool(use_threadpool_limits)

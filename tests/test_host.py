@@ -279,3 +279,17 @@ def test_fused_iteration_plan_geometry():
     assert plan(128, 5, 1000)[0] == -3     # N > 4: lane-per-row kernels
     assert plan(8, 2, 100, L=2, M=3)[0] == -3
     assert plan(2000, 2, 1000)[0] == -3    # more than 8 objectives per CTA
+
+
+def test_reference_process_maps_are_accepted_names():
+    """parallelization.py:233-311 of the reference: the process maps exist
+    under the same names with the serial_map interface."""
+    from krotov_b200 import parallelization as par
+    assert par.serial_map(lambda v, a, b=0: v + a + b, [1, 2], (10,),
+                          {'b': 5}) == [16, 17]
+    assert par.parallel_map(lambda v: 2 * v, [1, 2], num_cpus=4) == [2, 4]
+    par.set_parallelization(use_threadpool_limits=False)
+    assert par.USE_THREADPOOL_LIMITS is False
+    par.set_parallelization()
+    with pytest.raises(NotImplementedError):
+        par.parallel_map_fw_prop_step(None, [0], ())
