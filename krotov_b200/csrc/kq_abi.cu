@@ -12,6 +12,8 @@
 
 #include "kq_host.cuh"
 
+int g_kq_coop_launch = 1;
+
 namespace {
 
 thread_local std::string g_err;
@@ -626,6 +628,10 @@ int kq_set_option(const char* name, int value) {
   }
   if (name && std::strcmp(name, "picard_timing") == 0) {
     g_picard_timing = value ? 1 : 0;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "cooperative_launch") == 0) {
+    g_kq_coop_launch = value ? 1 : 0;
     return KQ_OK;
   }
   if (name && std::strcmp(name, "picard_history") == 0) {

@@ -38,6 +38,10 @@ typedef KqPlan Plan;
 // Launch helper.  The attribute / occupancy queries are cached per kernel
 // instantiation (they cost several microseconds per call and the fused
 // iteration kernel is launched once per Krotov iteration).
+// kq_set_option("cooperative_launch", 0): kernels that need co-resident CTAs are
+// still checked against the occupancy limit but launched with cudaLaunchKernel
+extern int g_kq_coop_launch;
+
 template <typename Kern>
 int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** params) {
   // Kern is only the function-pointer TYPE (all sweep kernels share it): the
@@ -81,8 +85,13 @@ int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** 
       return kq_fail(KQ_ERR_UNSUPPORTED,
                   "fused sweep needs %d co-resident CTAs but only %d fit (K too large)", pl.grid,
                   c_per_sm * c_sms);
-    KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1), dim3(pl.block),
-                                        params, pl.smem, st));
+    if (g_kq_coop_launch) {
+      KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1), dim3(pl.block),
+                                          params, pl.smem, st));
+    } else {
+      KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1),
+                               dim3(pl.block), params, pl.smem, st));
+    }
   } else {
     KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1),
                              dim3(pl.block), params, pl.smem, st));

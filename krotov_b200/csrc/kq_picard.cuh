@@ -430,6 +430,9 @@ __device__ __forceinline__ void pic_plan(double x, int& s, int& m, double& inv_s
 template <int N, int FSEL, bool SECOND, typename G, int WT>
 __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long long t_entry = clock64();   // picard_timing: cycles from kernel entry to exit (slot 15)
+  unsigned long long ns_entry;           // ... and nanoseconds (slot 7): the actual SM clock
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_entry));
   constexpr int NN = N * N;
   constexpr bool INREG = (N <= 3);
   constexpr int FSEL_BW = (FSEL == 0) ? 1 : 2;
@@ -548,34 +551,62 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   // plus the polynomial extrapolation of the update: D1 | 2 D1 - D2 |
   // 3 D1 - 3 D2 + D3 (each order cuts the error of the first iterate ~4x: about
   // one round less).  A hint only: the fixed point does not depend on it.
+  // All global loads of this loop are independent of each other and of the
+  // history header (every ring row is read, the header only selects the
+  // coefficients), and four entries per thread are in flight at once.
   int hcnt = 0, hhead = 0;
   if (a.pic_hist_hdr) {
     const unsigned long long key = a.pic_hist_hdr[0], ch = a.pic_hist_hdr[1];
     hhead = (int)(ch >> 32) & 3;
     if (key == (unsigned long long)(uintptr_t)a.pulses) hcnt = min((int)(ch & 0xffffffffu), 3);
   }
-  const double* hD1 = a.pic_hist + (size_t)((hhead + 3) & 3) * a.pic_hist_ld;
-  const double* hD2 = a.pic_hist + (size_t)((hhead + 2) & 3) * a.pic_hist_ld;
-  const double* hD3 = a.pic_hist + (size_t)((hhead + 1) & 3) * a.pic_hist_ld;
-  const double hc1 = (double)hcnt, hc2 = (hcnt == 3) ? -3.0 : -1.0;
-  for (int n = tid; n < NTP; n += BT) {
-    const double gn = (n < NT) ? a.pulses[n] : 0.0;
-    double e = gn;
-    if (n < NT) {
-      if (hcnt > 0) {
-        double d = hc1 * hD1[n];
-        if (hcnt > 1) d = fma(hc2, hD2[n], d);
-        if (hcnt > 2) d += hD3[n];
-        e = gn + d;
-      } else if (a.pic_hint) {
-        e = gn + (gn - a.pic_hint[n]);
-      }
+  const bool use_hist = a.pic_hist_hdr != nullptr;
+  // coefficient of ring row r: row (head-1) holds D1, (head-2) D2, (head-3) D3
+  double hcf[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int age = (hhead - r) & 3;   // 1, 2, 3 = D1, D2, D3; 0 = the row written by this launch
+    double c = 0.0;
+    if (age == 1 && hcnt >= 1) c = (double)hcnt;
+    if (age == 2 && hcnt >= 2) c = (hcnt == 3) ? -3.0 : -1.0;
+    if (age == 3 && hcnt >= 3) c = 1.0;
+    hcf[r] = c;
+  }
+  for (int n0 = tid; n0 < NTP; n0 += 4 * BT) {
+    double gn[4], dtv[4], hv[4][4], ph[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = n0 + u * BT;
+      const bool in = n < NT;
+      gn[u] = in ? a.pulses[n] : 0.0;
+      dtv[u] = in ? a.dt[n] : 0.0;
+      ph[u] = (in && a.pic_hint) ? a.pic_hint[n] : gn[u];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        hv[u][r] = (in && use_hist) ? a.pic_hist[(size_t)r * a.pic_hist_ld + n] : 0.0;
     }
-    seps0[(n & (W - 1)) * TC + (n >> lw)] = gn;
-    seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
-    if (n < NT) {
-      gmax = fmax(gmax, fmax(fabs(gn), fabs(e)));
-      dtmax = fmax(dtmax, fabs(a.dt[n]));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = n0 + u * BT;
+      if (n < NTP) {
+        double e = gn[u];
+        if (n < NT) {
+          if (hcnt > 0) {
+            double d = hcf[0] * hv[u][0];
+            d = fma(hcf[1], hv[u][1], d);
+            d = fma(hcf[2], hv[u][2], d);
+            d = fma(hcf[3], hv[u][3], d);
+            e = gn[u] + d;
+          } else if (a.pic_hint) {
+            e = gn[u] + (gn[u] - ph[u]);
+          }
+          if (!(fabs(e) < 1e300)) e = gn[u];   // never start from a non-finite value
+          gmax = fmax(gmax, fmax(fabs(gn[u]), fabs(e)));
+          dtmax = fmax(dtmax, fabs(dtv[u]));
+        }
+        seps0[(n & (W - 1)) * TC + (n >> lw)] = gn[u];
+        seps0[NTP + (n & (W - 1)) * TC + (n >> lw)] = e;
+      }
     }
   }
   for (int i = tid; i < Wc; i += BT) {
@@ -1123,6 +1154,10 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
   }
   KQ_TICK(9)
   if (timing) {
+    tacc[KQ_PIC_NTICK - 1] = clock64() - t_entry;
+    unsigned long long ns_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_exit));
+    tacc[7] = (long long)(ns_exit - ns_entry);
     for (int i = 0; i < KQ_PIC_NTICK; ++i) a.status[16 + i] = (int)tacc[i];
   }
 #undef KQ_TICK

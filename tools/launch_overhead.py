@@ -8,6 +8,8 @@ import krotov_b200 as krotov
 from krotov_b200.compiler import compile_problem, initialize_controls
 from krotov_b200.engine import SweepEngine
 
+if os.environ.get('KQ_COOP') is not None:
+    krotov._lib.load().kq_set_option(b"cooperative_launch", int(os.environ['KQ_COOP']))
 wl = krotov.workloads.tls_ensemble(K=128, nt=1000)
 objectives = wl.objectives(krotov.Objective)
 (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(objectives, wl.pulse_options, wl.tlist)

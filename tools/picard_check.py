@@ -105,13 +105,13 @@ if __name__ == '__main__':
         name = sys.argv[2] if len(sys.argv) > 2 else 'C4'
         wl = {'C4': lambda: W.tls_ensemble(K=128, nt=1000), 'C1': W.tls_state_to_state,
               'C2': W.transmon_xgate, 'C3': W.two_qubit_gate}[name]()
-        for r in timing(name, wl, 4):
+        for r in timing(name, wl, 40)[-3:]:
             cyc = r['cycles']
             its = max(r['pit'], 1)
-            names = ['prologue', 'bw', 'passA', 'passB', 'stage1', 'stage2', 'stage3', 'blockmax', 'outputs', 'final',
-                     'scan-shfl', 'scan-bar', 'scan-finish', 'passB-bar', 'fetch', '-']
+            names = ['prologue', 'bw', 'passA', 'passB', 'stage1', 'stage2', 'stage3', 'entry-to-exit-ns', 'outputs', 'final',
+                     'scan-shfl', 'scan-bar', 'scan-finish', 'passB-bar', 'fetch', 'entry-to-exit']
             print('kernel %.1f us, %d its; cycles (per iter except prologue/bw/outputs/final): ' % (r['ms'] * 1e3, its) + ', '.join(
-                '%s %d' % (n, c // (1 if i in (0, 1, 8, 9) else its)) for i, (n, c) in enumerate(zip(names, cyc)) if n != '-'))
+                '%s %d' % (n, c // (1 if i in (0, 1, 7, 8, 9, 15) else its)) for i, (n, c) in enumerate(zip(names, cyc)) if n != '-') + '  => SM clock %.3f GHz' % (cyc[15] / max(cyc[7], 1)))
         sys.exit(0)
     compare('C4 K=8 nt=100', W.tls_ensemble(K=8, nt=100))
     compare('C4 K=128 nt=1000', W.tls_ensemble(K=128, nt=1000), iters=5)
