@@ -616,11 +616,29 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
     own_g[i] = in ? a.pulses[n] : 0.0;
     own_dt[i] = in ? a.dt[n] : 0.0;
   }
-  block_max2(gmax, dtmax, scratch);          // barrier: also orders the writes above
-  double O0 = opn0, O1 = driven ? opn1 : 0.0;
-  block_max2(O0, O1, scratch + 64);
-  double Oc = driven ? 0.0 : c1_fixed * opn1, unused = 0.0;
-  block_max2(Oc, unused, scratch + 128);
+  double O0 = opn0, O1 = driven ? opn1 : 0.0, Oc = driven ? 0.0 : c1_fixed * opn1;
+  {
+    // CTA-wide maxima of the five bounds with ONE barrier (which also orders the
+    // shared-memory writes above); scratch[0..159] is not reused before the next barrier
+    double v[5] = {gmax, dtmax, O0, O1, Oc};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      v[j] = warp_max_nonneg(v[j]);
+      if (lane == 0) scratch[32 * j + warp] = v[j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      double r = scratch[32 * j];
+      for (int w = 1; w < nwarps; ++w) r = fmax(r, scratch[32 * j + w]);
+      v[j] = r;
+    }
+    gmax = v[0];
+    dtmax = v[1];
+    O0 = v[2];
+    O1 = v[3];
+    Oc = v[4];
+  }
 
   // ---- boundary condition chi_k(T), normalised (optimize.py:404-410) ---------
   cplx chiT[N];
