@@ -346,8 +346,20 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device(
-            'cuda', local_rank))
+        # NCCL announces its version on stdout when the first communicator is
+        # created: send that to stderr so that stdout carries the JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=torch.device(
+                'cuda', local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if dist is not None:
