@@ -5,6 +5,9 @@
 //   span          first CTA entry -> last CTA exit inside one launch (%globaltimer),
 //   entry spread  last CTA entry - first CTA entry,
 //   gap           period - span  (kernel boundary: drain + launch + CTA dispatch).
+// The "pdl" rows launch with programmatic stream serialization (cudaLaunchKernelEx +
+// griddepcontrol.launch_dependents / griddepcontrol.wait): the next launch's CTAs may become
+// resident while the previous grid drains; overhead = period - spin time.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o launch_gap launch_gap.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -20,8 +23,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 template <int TOUCH>
 __global__ void __launch_bounds__(256, 1) k_body(unsigned long long* stamps, int launch, int spin_ns,
-                                                 int touch_bytes) {
+                                                 int touch_bytes, int pdl) {
   extern __shared__ double sm[];
+  if (pdl) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
   const unsigned long long t0 = gtime();
   if (TOUCH) {   // touch the shared memory like the real kernel's prologue does
     for (int i = threadIdx.x; i < touch_bytes / 8; i += blockDim.x) sm[i] = (double)i;
@@ -48,20 +55,36 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e1);
   printf("%-8s %-6s %-8s %10s %10s %12s %10s\n", "launch", "smemKB", "spin_us", "period_us", "span_us",
          "entry_spread", "gap_us");
-  for (int coop = 0; coop < 2; ++coop)
-    for (int smem_kb : {0, 48, 100, 200})
+  for (int coop = 0; coop < 4; ++coop)   // 0 regular, 1 cooperative, 2 pdl, 3 pdl + cooperative
+    for (int smem_kb : {0, 200})
       for (int spin_us : {5, 40}) {
+        int pdl = coop >= 2;
         int smem = smem_kb * 1024, spin_ns = spin_us * 1000, touch = smem;
         cudaFuncSetAttribute(k_body<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         for (int rep = 0; rep < 2; ++rep) {   // rep 0 = warm-up
           cudaStreamSynchronize(st);
           cudaEventRecord(e0, st);
           for (int i = 0; i < n; ++i) {
-            void* params[] = {(void*)&d, (void*)&i, (void*)&spin_ns, (void*)&touch};
-            if (coop)
+            void* params[] = {(void*)&d, (void*)&i, (void*)&spin_ns, (void*)&touch, (void*)&pdl};
+            if (coop == 1)
               cudaLaunchCooperativeKernel((const void*)k_body<1>, dim3(grid), dim3(block), params, smem, st);
-            else
+            else if (coop == 0)
               cudaLaunchKernel((const void*)k_body<1>, dim3(grid), dim3(block), params, smem, st);
+            else {
+              cudaLaunchConfig_t cfg = {};
+              cfg.gridDim = dim3(grid);
+              cfg.blockDim = dim3(block);
+              cfg.dynamicSmemBytes = smem;
+              cfg.stream = st;
+              cudaLaunchAttribute at[2];
+              at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+              at[0].val.programmaticStreamSerializationAllowed = 1;
+              at[1].id = cudaLaunchAttributeCooperative;
+              at[1].val.cooperative = 1;
+              cfg.attrs = at;
+              cfg.numAttrs = (coop == 3) ? 2 : 1;
+              cudaLaunchKernelExC(&cfg, (const void*)k_body<1>, params);
+            }
           }
           cudaEventRecord(e1, st);
           cudaStreamSynchronize(st);
@@ -83,7 +106,7 @@ int main(int argc, char** argv) {
         span /= (n - n / 2) * 1e3;
         spread /= (n - n / 2) * 1e3;
         const double period = ms * 1e3 / n;
-        printf("%-8s %-6d %-8d %10.2f %10.2f %12.2f %10.2f\n", coop ? "coop" : "regular", smem_kb, spin_us,
+        printf("%-8s %-6d %-8d %10.2f %10.2f %12.2f %10.2f\n", coop == 0 ? "regular" : coop == 1 ? "coop" : coop == 2 ? "pdl" : "pdl+coop", smem_kb, spin_us,
                period, span, spread, period - span);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) printf("  CUDA error: %s\n", cudaGetErrorString(err));
