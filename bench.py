@@ -379,6 +379,10 @@ def run_ours(args):
     if args.picard_history is not None:
         krotov._lib.check(krotov._lib.load().kq_set_option(
             b"picard_history", args.picard_history))
+    if args.pdl:
+        for opt, val in ((b"cooperative_launch", 0),
+                         (b"programmatic_launch", 1)):
+            krotov._lib.check(krotov._lib.load().kq_set_option(opt, val))
     wl = build_workload()
     K = len(wl.Hs)
     n_state = len(wl.lowered()['psi0'][0])
@@ -699,6 +703,9 @@ def main():
     ap.add_argument('--picard-history', type=int, default=None,
                     choices=[0, 1], help='update-history first iterate of '
                     'the fixed-point kernel (library default: on)')
+    ap.add_argument('--pdl', action='store_true',
+                    help='experimental: regular launches with programmatic '
+                         'stream serialization instead of cooperative ones')
     ap.add_argument('--workload', default='C4',
                     help='C4 (contract workload) or C1/C2/C3/C5/C4sat for '
                          'additional measurements')

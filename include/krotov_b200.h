@@ -113,6 +113,12 @@ const char* kq_last_error(void);
  * phase cycle counts in workspace status words 16..25; "picard_history"
  * (default 1): kq_krotov_iteration starts the fixed-point iteration from the
  * extrapolation of the updates of the calls before (kept in the workspace).
+ * "cooperative_launch" (default 1) / "programmatic_launch" (default 0,
+ * experimental): with 0 / 1 the kernels that exchange data between CTAs are
+ * launched with cudaLaunchKernelEx + programmatic stream serialization instead
+ * of cudaLaunchCooperativeKernel (co-residency is still checked against the
+ * occupancy limit; the kernels wait for the preceding launches before they
+ * touch memory).
  * "time_parallel" (default 1): propagation
  * sweeps under known pulses (kq_propagate_forward, kq_sweep_backward*) are cut
  * into time segments that run concurrently (segment propagators -> boundary

@@ -13,6 +13,7 @@
 #include "kq_host.cuh"
 
 int g_kq_coop_launch = 1;
+int g_kq_pdl_launch = 0;
 
 namespace {
 
@@ -632,6 +633,10 @@ int kq_set_option(const char* name, int value) {
   }
   if (name && std::strcmp(name, "cooperative_launch") == 0) {
     g_kq_coop_launch = value ? 1 : 0;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "programmatic_launch") == 0) {
+    g_kq_pdl_launch = value ? 1 : 0;
     return KQ_OK;
   }
   if (name && std::strcmp(name, "picard_history") == 0) {

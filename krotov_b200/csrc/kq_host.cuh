@@ -41,6 +41,11 @@ typedef KqPlan Plan;
 // kq_set_option("cooperative_launch", 0): kernels that need co-resident CTAs are
 // still checked against the occupancy limit but launched with cudaLaunchKernel
 extern int g_kq_coop_launch;
+// kq_set_option("programmatic_launch", 1) (experimental, needs cooperative_launch 0): launch
+// with programmatic stream serialization, so that the next launch's CTAs become resident while
+// this grid drains (profiles/micro/launch_gap.cu: kernel boundary 2.9 -> 0.7 us); the kernels
+// call griddepcontrol.wait before touching memory, so stream-order semantics are unchanged
+extern int g_kq_pdl_launch;
 
 template <typename Kern>
 int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** params) {
@@ -88,6 +93,18 @@ int launch(Kern kern, const Plan& pl, bool cooperative, cudaStream_t st, void** 
     if (g_kq_coop_launch) {
       KQ_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1), dim3(pl.block),
                                           params, pl.smem, st));
+    } else if (g_kq_pdl_launch) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1);
+      cfg.blockDim = dim3(pl.block);
+      cfg.dynamicSmemBytes = pl.smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      KQ_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kern, params));
     } else {
       KQ_CUDA(cudaLaunchKernel((const void*)kern, dim3(pl.grid, pl.grid_y > 1 ? pl.grid_y : 1),
                                dim3(pl.block), params, pl.smem, st));

@@ -430,6 +430,11 @@ __device__ __forceinline__ void pic_plan(double x, int& s, int& m, double& inv_s
 template <int N, int FSEL, bool SECOND, typename G, int WT>
 __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // programmatic dependent launch (only when launched with that attribute, else no-ops): let
+  // the next launch's CTAs become resident early, and wait for the launches before this one
+  // before touching any memory
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long t_entry = clock64();   // picard_timing: cycles from kernel entry to exit (slot 15)
   unsigned long long ns_entry;           // ... and nanoseconds (slot 7): the actual SM clock
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_entry));

@@ -10,6 +10,8 @@ from krotov_b200.engine import SweepEngine
 
 if os.environ.get('KQ_COOP') is not None:
     krotov._lib.load().kq_set_option(b"cooperative_launch", int(os.environ['KQ_COOP']))
+if os.environ.get('KQ_PDL') is not None:
+    krotov._lib.load().kq_set_option(b"programmatic_launch", int(os.environ['KQ_PDL']))
 wl = krotov.workloads.tls_ensemble(K=128, nt=1000)
 objectives = wl.objectives(krotov.Objective)
 (controls, _, guess_pulses, mapping, lam, shp) = initialize_controls(objectives, wl.pulse_options, wl.tlist)
