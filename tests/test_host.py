@@ -293,3 +293,24 @@ def test_reference_process_maps_are_accepted_names():
     par.set_parallelization()
     with pytest.raises(NotImplementedError):
         par.parallel_map_fw_prop_step(None, [0], ())
+
+
+def test_bench_cpu_legs_on_a_small_ensemble(monkeypatch, tmp_path):
+    """bench.py's CPU legs (serial numpy port, multi-process port with the
+    pulse dump used for the same-run parity key) on a 4-objective ensemble."""
+    import numpy as np
+    import bench
+    monkeypatch.setitem(bench.WORKLOAD, 'K', 4)
+    monkeypatch.setitem(bench.WORKLOAD, 'nt', 60)
+    wl = bench.build_workload()
+    per_iter, ks = bench.time_oracle(wl, 1)
+    assert per_iter > 0 and ks == 4
+    dump = str(tmp_path / 'pulses.npy')
+    leg = bench.parallel_leg(wl, 1, 1, dump=dump)
+    assert leg['kind'] == 'port' and 1 <= leg['cores'] <= 4
+    assert leg['value'] > 0 and leg['unit'] == bench.UNIT
+    assert np.load(dump).shape == (2, 1, 59)
+    # replica r > 0 is a different optimisation problem (guess amplitude)
+    p0 = np.array(bench.build_workload().lowered()['pulses'])
+    p1 = np.array(bench.build_workload(replica=1).lowered()['pulses'])
+    assert np.allclose(p1, 1.05 * p0)
