@@ -29,7 +29,8 @@ from .conversions import (control_onto_interval, discretize, extract_controls,
 __all__ = [
     'Workload', 'tls_state_to_state', 'tls_reference_fixture',
     'transmon_xgate', 'two_qubit_gate', 'tls_ensemble',
-    'dissipative_qubit_reset', 'by_name',
+    'dissipative_qubit_reset', 'lambda_system', 'tls_shared_controls',
+    'by_name',
 ]
 
 _SX = np.array([[0, 1], [1, 0]], dtype=np.complex128)
@@ -309,6 +310,86 @@ def dissipative_qubit_reset(nt=5000, T=25.0, omega_q=1.0, omega_T=3.0,
         tlist=np.linspace(0, T, nt), chi='qubit_reset', is_super=True,
         meta=dict(chi_fixed=np.kron(np.diag([1, 0]), np.diag([1, 1])).astype(
             np.complex128)),
+    )
+
+
+# --- several controls (notebooks 02/03/08, tests/test_mu.py) ---------------
+
+def _blackman_guess(t, args, ampl, t0, t1):
+    return ampl * shapes.blackman(t, t_start=t0, t_stop=t1)
+
+
+def _zero_guess(t, args):
+    return 0.0
+
+
+def lambda_system(nt=500, T=5.0, gamma=0.5, ensemble_mu=None, lambda_a=2.0,
+                  E1=0.0, E2=10.0, E3=5.0, omega_P=9.5, omega_S=4.5,
+                  ampl=5.0):
+    """Λ-system in the rotating-wave approximation with FOUR real controls
+    (real/imaginary parts of pump and Stokes pulse; N=3, L=4, M=5):
+    docs/notebooks/03_example_lambda_system_rwa_non_hermitian.ipynb cells
+    5-26 (``gamma`` > 0: decay -i gamma on the intermediate level, a
+    non-Hermitian H0), notebook 02 (``gamma=0``), and with `ensemble_mu` the
+    robustness ensemble of docs/notebooks/08_example_ensemble.ipynb cells
+    20-39 (control Hamiltonians scaled by mu, all copies share the four
+    control objects; notebook values: mu = 0.9 ... 1.1, lambda_a = 0.5).
+    |1> -> e^{i (E2 - omega_S) T} |3>, ``chis_re``."""
+    dP = E1 + omega_P - E2
+    dS = E3 + omega_S - E2
+    H0 = np.diag([dP, -1j * gamma, dS]).astype(np.complex128)
+    HP_re = -0.5 * np.array([[0, 1, 0], [1, 0, 0], [0, 0, 0]], dtype=complex)
+    HP_im = -0.5 * np.array([[0, 1j, 0], [-1j, 0, 0], [0, 0, 0]],
+                            dtype=complex)
+    HS_re = -0.5 * np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0]], dtype=complex)
+    HS_im = -0.5 * np.array([[0, 0, 0], [0, 0, 1j], [0, -1j, 0]],
+                            dtype=complex)
+    P1 = partial(_blackman_guess, ampl=ampl, t0=2.0, t1=5.0)
+    S1 = partial(_blackman_guess, ampl=ampl, t0=0.0, t1=3.0)
+    # distinct control objects for the two zero guesses (controls are
+    # identified by object identity, conversions.py:43-58)
+    P2 = partial(_zero_guess)
+    S2 = partial(_zero_guess)
+    ctrl_ops = [(HP_re, P1), (HP_im, P2), (HS_re, S1), (HS_im, S2)]
+    mus = [1.0] if ensemble_mu is None else list(ensemble_mu)
+    Hs = [[H0] + [[mu * op, c] for op, c in ctrl_ops] for mu in mus]
+    shape = partial(shapes.flattop, t_start=0.0, t_stop=T, t_rise=0.3,
+                    func='sinsq')
+    psi0 = _ket(3, 0)
+    tgt = np.exp(1j * (E2 - omega_S) * T) * _ket(3, 2)
+    return Workload(
+        name='lambda_system_K%d' % len(mus),
+        Hs=Hs, initial_states=[psi0] * len(mus), targets=[tgt] * len(mus),
+        pulse_options={c: dict(lambda_a=lambda_a, update_shape=shape)
+                       for _, c in ctrl_ops},
+        tlist=np.linspace(0, T, nt), chi='re',
+    )
+
+
+def tls_shared_controls(nt=100, T=2.0):
+    """The control system of the reference's tests/test_mu.py:8-27 as an
+    optimisation problem: objective 0 contains control eps1 TWICE (sigma_+
+    and sigma_- terms, so mu = sigma_x/2 + ... is a sum, mu.py:124) and not
+    eps2; objective 1 contains only eps2 (a sigma_z term): the mapping of
+    eps2 for objective 0 and of eps1 for objective 1 is empty (zero mu,
+    mu.py:133-138).  N=2, L=2."""
+    sp = np.array([[0, 1], [0, 0]], dtype=np.complex128)   # qutip sigmap()
+    sm = sp.T.copy()
+    eps1 = lambda t, args: 0.5   # noqa: E731
+    eps2 = lambda t, args: 1.0   # noqa: E731
+    H1 = [0.5 * _SZ, [sp, eps1], [sm, eps1]]
+    H2 = [0.5 * _SZ, [_SZ.copy(), eps2]]
+    shape = partial(shapes.flattop, t_start=0.0, t_stop=T, t_rise=0.2 * T,
+                    func='sinsq')
+    r = 1 / np.sqrt(2)
+    return Workload(
+        name='tls_shared_controls',
+        Hs=[H1, H2],
+        initial_states=[_ket(2, 0), r * (_ket(2, 0) + _ket(2, 1))],
+        targets=[_ket(2, 1), r * (_ket(2, 0) - 1j * _ket(2, 1))],
+        pulse_options={eps1: dict(lambda_a=1.0, update_shape=shape),
+                       eps2: dict(lambda_a=2.0, update_shape=shape)},
+        tlist=np.linspace(0, T, nt), chi='re',
     )
 
 

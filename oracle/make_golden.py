@@ -234,6 +234,36 @@ def case_c5():
     save('C5_nt500_qobj', **run_reference(wl, 3, 'qobj', keep_states=True))
 
 
+def case_multi_control():
+    """Several controls per objective (L > 1, M > 2): the non-Hermitian
+    Lambda system of notebook 03, the 5-member Lambda ensemble of notebook 08
+    and the repeated / absent control system of tests/test_mu.py:8-27."""
+    wl = workloads.lambda_system(nt=500, gamma=0.5)
+    save('lambda_nonherm_qobj', **run_reference(wl, 3, 'qobj',
+                                                 keep_states=True))
+    wl = workloads.lambda_system(nt=500, gamma=0.0, lambda_a=0.5,
+                                 ensemble_mu=[0.9, 0.95, 1.0, 1.05, 1.1])
+    save('lambda_ensemble_qobj', **run_reference(wl, 3, 'qobj',
+                                                  keep_states=False))
+    wl = workloads.tls_shared_controls()
+    save('shared_controls_qobj', **run_reference(wl, 3, 'qobj',
+                                                  keep_states=True))
+
+
+def case_full_size():
+    """C3 and C5 at the sizes BASELINE.json's configs name (nt=2000 / 5000);
+    pulses, tau and final states only."""
+    wl = workloads.two_qubit_gate(nt=2000)
+    save('C3_nt2000_first_order_qobj',
+         **run_reference(wl, 3, 'qobj', keep_states=False))
+    sig = ConstSigma(A=0.5)
+    out = run_reference(wl, 3, 'qobj', keep_states=False, sigma=sig)
+    out['sigma_A'] = np.array(sig.A_hist)
+    save('C3_nt2000_second_order_qobj', **out)
+    wl = workloads.dissipative_qubit_reset(nt=5000)
+    save('C5_nt5000_qobj', **run_reference(wl, 2, 'qobj', keep_states=False))
+
+
 def case_infohook_kat():
     """tests/test_infohooks.py:15-72: lambda halved after each iteration;
     golden info_vals[1][0] = 0.001978333994757067."""
@@ -283,7 +313,8 @@ def case_infohook_kat():
 
 
 CASES = dict(tls_fixture=case_tls_fixture, c1=case_c1, c2=case_c2,
-             c3=case_c3, c4=case_c4, c5=case_c5, kat=case_infohook_kat)
+             c3=case_c3, c4=case_c4, c5=case_c5, kat=case_infohook_kat,
+             multi=case_multi_control, full=case_full_size)
 
 if __name__ == '__main__':
     names = sys.argv[1:] or list(CASES)

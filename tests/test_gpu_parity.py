@@ -238,6 +238,153 @@ def test_infohook_kat_lambda_update(krotov, golden):
     assert np.allclose(res.info_vals, g['info_vals'], rtol=0, atol=1e-13)
 
 
+# ---- several controls per objective (L > 1, M > 2) ---------------------------
+
+@pytest.mark.parametrize('engine_mode', [None, 'sweeps'])
+def test_lambda_system_four_controls_nonhermitian(krotov, golden, engine_mode):
+    """Notebook 03: N=3, four real controls (two of them with a zero guess),
+    non-Hermitian drift; golden from the unmodified reference.  All pulses
+    of a time step are updated before the forward step (optimize.py:454-491)."""
+    g = golden('lambda_nonherm_qobj')
+    wl = krotov.workloads.lambda_system(nt=500, gamma=0.5)
+    res, rec = run_gpu(krotov, wl, 3, keep_states=True,
+                       engine_mode=engine_mode)
+    assert rec.pulses[0].shape == (4, 499)
+    check_against_golden(rec, g, 3)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+    assert rel(res.optimized_controls, g['optimized_controls']) < PULSE_RTOL
+    # the imaginary-part pulses start from zero and must have moved
+    assert np.max(np.abs(rec.pulses[3][1])) > 1e-3
+    assert np.max(np.abs(rec.pulses[3][3])) > 1e-3
+
+
+@pytest.mark.parametrize('engine_mode', [None, 'sweeps'])
+def test_lambda_ensemble_shared_controls(krotov, golden, engine_mode):
+    """Notebook 08: five copies of the Lambda system with scaled control
+    Hamiltonians share the four control objects."""
+    g = golden('lambda_ensemble_qobj')
+    wl = krotov.workloads.lambda_system(
+        nt=500, gamma=0.0, lambda_a=0.5,
+        ensemble_mu=[0.9, 0.95, 1.0, 1.05, 1.1])
+    _, rec = run_gpu(krotov, wl, 3, engine_mode=engine_mode)
+    check_against_golden(rec, g, 3)
+
+
+@pytest.mark.parametrize('engine_mode', [None, 'sweeps'])
+def test_repeated_and_absent_controls(krotov, golden, engine_mode):
+    """/root/reference/tests/test_mu.py:8-27,52-101 as an optimisation: a
+    control that appears twice in one objective (mu is the SUM of its
+    operators) and controls that are absent from an objective (zero mu)."""
+    g = golden('shared_controls_qobj')
+    wl = krotov.workloads.tls_shared_controls()
+    _, rec = run_gpu(krotov, wl, 3, keep_states=True, engine_mode=engine_mode)
+    check_against_golden(rec, g, 3)
+    assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
+
+
+# ---- BASELINE sizes for C3 (nt=2000) and C5 (nt=5000) -----------------------
+
+def test_c3_full_size_first_and_second_order(krotov, golden):
+    g = golden('C3_nt2000_first_order_qobj')
+    wl = krotov.workloads.two_qubit_gate(nt=2000)
+    _, rec = run_gpu(krotov, wl, 3)
+    check_against_golden(rec, g, 3)
+    g = golden('C3_nt2000_second_order_qobj')
+
+    class ConstSigma(krotov.second_order.Sigma):
+        def __init__(self, A):
+            self.A, self.A_hist = A, [A]
+
+        def __call__(self, t):
+            return -max(0.0, 2 * self.A)
+
+        def refresh(self, forward_states, forward_states0, chi_states,
+                    chi_norms, optimized_pulses, guess_pulses, objectives,
+                    result):
+            taus = result.tau_vals
+            dJ = (1 - abs(np.mean(taus[-1])) ** 2) - (
+                1 - abs(np.mean(taus[-2])) ** 2)
+            self.A = krotov.second_order.numerical_estimate_A(
+                forward_states, forward_states0, chi_states, chi_norms, dJ)
+            self.A_hist.append(self.A)
+
+    sig = ConstSigma(0.5)
+    _, rec = run_gpu(krotov, wl, 3, sigma=sig)
+    check_against_golden(rec, g, 3)
+    assert np.allclose(sig.A_hist, g['sigma_A'], rtol=1e-7)
+
+
+def test_c5_full_size(krotov, golden):
+    g = golden('C5_nt5000_qobj')
+    wl = krotov.workloads.dissipative_qubit_reset(nt=5000)
+    _, rec = run_gpu(krotov, wl, 2)
+    check_against_golden(rec, g, 2)
+
+
+# ---- continuation (optimize.py:707-803, tests/test_krotov.py:166-432) --------
+
+def test_continue_from_dumped_result(krotov, tmp_path):
+    """An optimisation interrupted after 4 iterations (dump written by
+    convergence.dump_result) and continued to 7 gives the pulses of the
+    uninterrupted run to 1e-10, with and without
+    skip_initial_forward_propagation; a finished Result continued with a
+    smaller iter_stop is a no-op."""
+    wl = krotov.workloads.tls_reference_fixture()
+    objectives = wl.objectives(krotov.Objective)
+    dumpfile = str(tmp_path / 'oct_result_{iter:03d}.dump')
+    common = dict(propagator=krotov.propagators.expm,
+                  chi_constructor=krotov.functionals.chis_re,
+                  store_all_pulses=True)
+
+    def run(**kw):
+        return krotov.optimize_pulses(
+            objectives, wl.pulse_options, wl.tlist,
+            info_hook=krotov.functionals.J_T_re,
+            check_convergence=krotov.convergence.Or(
+                krotov.convergence.check_monotonic_error,
+                krotov.convergence.dump_result(dumpfile, every=2)),
+            **common, **kw)
+
+    full = run(iter_stop=7)
+    assert full.iters == list(range(8))
+    assert "7 iterations" in full.message
+    # continue a finished result with fewer iterations: nothing happens
+    noop = run(iter_stop=5, continue_from=full,
+               skip_initial_forward_propagation=True)
+    assert noop.iters == full.iters and noop.message == full.message
+    assert noop.start_local_time_str == full.start_local_time_str
+    assert len(noop.all_pulses) == 8
+    for skip in (True, False):
+        part = krotov.result.Result.load(
+            str(tmp_path / 'oct_result_004.dump'), objectives=objectives)
+        assert part.iters[-1] == 4
+        cont = run(iter_stop=7, continue_from=part,
+                   skip_initial_forward_propagation=skip)
+        assert cont.iters == full.iters
+        assert len(cont.iter_seconds) == 8 and len(cont.info_vals) == 8
+        assert len(cont.all_pulses) == 8 and len(cont.tau_vals) == 8
+        assert "7 iterations" in cont.message
+        delta = np.max(np.abs(cont.optimized_controls[-1]
+                              - full.optimized_controls[-1]))
+        assert delta < 1e-10, (skip, delta)
+        for a, b in zip(cont.all_pulses, full.all_pulses):
+            assert rel(a, b) < PULSE_RTOL
+        assert np.allclose(cont.info_vals, full.info_vals, rtol=0, atol=1e-12)
+    # continuing without the objectives (control placeholders) is refused
+    part = krotov.result.Result.load(str(tmp_path / 'oct_result_004.dump'))
+    with pytest.raises(ValueError, match='objectives must remain unchanged'):
+        run(iter_stop=7, continue_from=part)
+    # hook-free continuation takes the fast path and agrees as well
+    part = krotov.result.Result.load(
+        str(tmp_path / 'oct_result_004.dump'), objectives=objectives)
+    fast = krotov.optimize_pulses(
+        objectives, wl.pulse_options, wl.tlist, iter_stop=7,
+        continue_from=part, **common)
+    assert fast.iters == full.iters
+    assert np.max(np.abs(fast.optimized_controls[-1]
+                         - full.optimized_controls[-1])) < 1e-10
+
+
 def test_multi_cta_exchange_vs_oracle(krotov):
     """More objectives than one CTA holds: the per-time-step sum crosses CTAs
     through the flag-tagged exchange slots (cooperative launch)."""

@@ -314,3 +314,52 @@ def test_bench_cpu_legs_on_a_small_ensemble(monkeypatch, tmp_path):
     p0 = np.array(bench.build_workload().lowered()['pulses'])
     p1 = np.array(bench.build_workload(replica=1).lowered()['pulses'])
     assert np.allclose(p1, 1.05 * p0)
+
+
+def test_convergence_specs_follow_reference():
+    """convergence.py:109-297 of the reference: glom-style specs (default
+    ('info_vals', T[-1])), error propagation, Or()."""
+    from krotov_b200 import convergence as cv
+    from krotov_b200.result import Result
+    r = Result()
+    chk = cv.value_below('1e-4', spec=lambda res: res.info_vals[-1],
+                         name='J_T')
+    r.info_vals.append(1e-4)
+    assert chk(r) is None
+    r.info_vals.append(9e-5)
+    assert chk(r) == 'J_T < 1e-4'
+    # default spec, tuple entries are NOT unwrapped
+    assert cv.value_below(1e-3)(r) == "%s < 0.001" % (
+        str(('info_vals', cv.T[-1])),)
+    # a spec that selects another attribute is honoured, not ignored
+    r.tau_vals.append(np.array([0.5 + 0j]))
+    chk = cv.value_above('0.4', spec=('tau_vals', cv.T[-1], cv.T[0],
+                                      lambda z: z.real), name='F')
+    assert chk(r) == 'F > 0.4'
+    assert cv.value_below('0.4', spec=('tau_vals', cv.T[-1], cv.T[0],
+                                       abs))(r) is None
+    assert cv.extract(r, 'info_vals')[-1] == 9e-5
+    # no info_hook -> empty info_vals -> the reference raises IndexError
+    with pytest.raises(IndexError):
+        cv.value_below(1e-3)(Result())
+    with pytest.raises(TypeError):
+        cv.value_below(1e-3, spec={'a': 'info_vals'})(r)
+    # delta_below: one missing value passes, two missing values re-raise
+    d = cv.delta_below('1e-4', name='ΔJ_T')
+    r2 = Result()
+    with pytest.raises(IndexError):
+        d(r2)
+    for v, want in [(9e-1, None), (1e-1, None), (4e-4, None), (2e-4, None),
+                    (1e-6, None), (1e-7, 'ΔJ_T < 1e-4')]:
+        r2.info_vals.append(v)
+        assert d(r2) == want
+    r3 = Result()
+    for v, want in [(9e-1, None), (1e-1, None), (2e-1, (
+            'Loss of monotonic convergence; error decrease < 0'))]:
+        r3.info_vals.append(v)
+        assert cv.check_monotonic_error(r3) == want
+    assert cv.check_monotonic_fidelity(r3) is None
+    assert cv.Or(cv.check_monotonic_fidelity, cv.check_monotonic_error)(
+        r3).startswith('Loss of monotonic')
+    with pytest.raises(ValueError):
+        cv.dump_result('x', every=0)
