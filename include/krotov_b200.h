@@ -206,9 +206,23 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses,
  * the polynomial extrapolation of those updates instead (about one to two
  * rounds fewer; option "picard_history", default 1).
  * sigma/Phi0/Phi1 as in kq_sweep_forward_update.  tau_in/phiT_in must not alias
- * tau_out/phiT_out.  Returns KQ_ERR_UNSUPPORTED when the problem is outside the
- * family (N in 2..4, two generator terms, one pulse, single GPU, state stores
- * fit shared memory): use the four-call sequence then.  If the fixed-point
+ * tau_out/phiT_out.
+ * Objectives sharded over GPUs (comm != NULL, comm->world > 1; one process per
+ * GPU, every rank calls with the same epoch): this rank holds K <=
+ * ceil(K_total / world) objectives; all ranks run the same launch geometry.  In
+ * every fixed-point round the CTA that owns a time slice adds the sums of the
+ * other GPUs to its own -- one 16-byte flag-tagged store per value into every
+ * peer's exchange buffer (comm->slots[r], kq_comm_slot_bytes() bytes) over
+ * NVLink, polling of the local buffer only, summation in rank order -- so the
+ * reduction over ALL objectives of optimize.py:454-470 crosses the GPUs once per
+ * round (nt doubles) instead of once per time step, and every rank obtains
+ * bit-identical pulses.  No NCCL call or host synchronisation inside the
+ * iteration.  tau_out / phiT_out / X hold this rank's objectives.  For
+ * KQ_CHI_SM tau_sum points to sum_j w_j tau_j over ALL ranks (one complex value
+ * on the device, e.g. from an NCCL all-reduce on the same stream); NULL otherwise.
+ * Returns KQ_ERR_UNSUPPORTED when the problem is outside the
+ * family (N in 2..4, state stores fit shared memory): use the four-call
+ * sequence then.  If the fixed-point
  * iteration does not converge ("picard_maxit" option) the outputs are left
  * untouched, workspace status word 1 is set to `epoch` and word 3 to the first
  * such epoch; word 2 holds the number of fixed-point rounds of the last
@@ -225,7 +239,8 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
                         kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
                         double* chi_norms_out, const double* sigma,
                         const kq_c128* Phi0, kq_c128* Phi1, double* g_a,
-                        int32_t* diag_out, void* workspace, uint32_t epoch,
+                        int32_t* diag_out, const kq_comm* comm,
+                        const kq_c128* tau_sum, void* workspace, uint32_t epoch,
                         void* stream);
 
 /* Boundary condition chi_k(T) for the built-in functionals, followed by the

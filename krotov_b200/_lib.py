@@ -30,7 +30,12 @@ class EngineUnavailable(RuntimeError):
 
 
 class KqError(RuntimeError):
-    """An ABI call returned a negative status."""
+    """An ABI call returned a negative status (``.status``: the kq_status
+    value, e.g. -3 = KQ_ERR_UNSUPPORTED)."""
+
+    def __init__(self, message, status=None):
+        super().__init__(message)
+        self.status = status
 
 
 class KqProblem(ctypes.Structure):
@@ -87,7 +92,9 @@ _SIGNATURES = {
         ctypes.c_void_p]),
     'kq_krotov_iteration': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.c_int, ctypes.c_int32] +
-        [ctypes.c_void_p] * 21 + [ctypes.c_uint32, ctypes.c_void_p]),
+        [ctypes.c_void_p] * 20 + [ctypes.POINTER(KqComm), ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_uint32,
+                                ctypes.c_void_p]),
     'kq_chi_boundary': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.c_int, ctypes.c_int32,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -185,4 +192,4 @@ def check(status):
     if status != 0:
         msg = load().kq_last_error()
         raise KqError("libkrotov_b200 error %d: %s"
-                      % (status, msg.decode() if msg else '?'))
+                      % (status, msg.decode() if msg else '?'), status)

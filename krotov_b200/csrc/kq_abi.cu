@@ -245,10 +245,16 @@ struct PicPlan {
   size_t smem;
 };
 // slots per mailbox / per owner region: grid * 2^lwc + grid <= 2 NT + 19 * 148
+// slots of a rank's exchange buffer that precede the cross-GPU region of the time-parallel
+// iteration: per-step slots of the sequential sweep | barrier flags
+size_t xg_offset_slots() { return (size_t)2 * kMaxWorld * KQ_LMAX + kMaxWorld; }
 size_t pic_stride(const kq_problem* p) { return (size_t)2 * round_up(p->NT, 64) + 2880; }
 int pic_hist_ld(const kq_problem* p) { return round_up(p->NT, 16); }
-bool picard_plan(const kq_problem* p, int sms, PicPlan& pp) {
-  const int K = p->K, N = p->N, NT = p->NT, NN = N * N;
+// `K_plan` (default p->K): number of objectives the geometry is made for -- with objectives
+// sharded over GPUs every rank plans for the largest block, so that all ranks run the same
+// grid and the same time slices.
+bool picard_plan(const kq_problem* p, int sms, PicPlan& pp, int K_plan = 0) {
+  const int K = K_plan > 0 ? K_plan : p->K, N = p->N, NT = p->NT, NN = N * N;
   if (N < 2 || N > 4 || p->M != 2 || p->L != 1) return false;
   const int gmax = std::min(sms, kPicMaxBlocks);
   const int Q = (K + gmax - 1) / gmax;
@@ -305,6 +311,10 @@ int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* w
                (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
   b.pic_part = reinterpret_cast<KqSlot*>(base);
   b.pic_eps = b.pic_part + (size_t)kPicMaxBlocks * pp.stride;
+  if (b.world > 1) {
+    b.pic_xg_off = xg_offset_slots();
+    b.pic_xg_buf = (size_t)b.world * pp.stride;
+  }
   if (b.pic_bw && window == 0 && g_picard_history) {
     // whole-iteration calls keep the last updates in the workspace (first-iterate hint)
     char* hist = reinterpret_cast<char*>(b.pic_eps + (size_t)kPicMaxBlocks * pp.stride);
@@ -689,8 +699,11 @@ int kq_comm_free(void* ptr) {
 
 const char* kq_last_error(void) { return g_err.c_str(); }
 
-size_t kq_comm_slot_bytes(const kq_problem*) {
-  return ((size_t)2 * kMaxWorld * KQ_LMAX + kMaxWorld) * sizeof(KqSlot);
+size_t kq_comm_slot_bytes(const kq_problem* p) {
+  size_t slots = xg_offset_slots();
+  // time-parallel iteration with sharded objectives: [4][cta][rank][slice] sums
+  if (p && p->NT > 0) slots += (size_t)4 * kMaxWorld * pic_stride(p);
+  return slots * sizeof(KqSlot);
 }
 
 int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* stream) {
@@ -896,8 +909,9 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
                         const double* guess_pulses, const double* prev_guess_pulses,
                         double* opt_pulses, const kq_c128* phi0, kq_c128* phiT_out, kq_c128* tau_out, kq_c128* X, kq_c128* chi_out,
                         double* chi_norms_out, const double* sigma, const kq_c128* Phi0,
-                        kq_c128* Phi1, double* g_a, int32_t* diag_out, void* workspace,
-                        uint32_t epoch, void* stream) {
+                        kq_c128* Phi1, double* g_a, int32_t* diag_out, const kq_comm* comm,
+                        const kq_c128* tau_sum, void* workspace, uint32_t epoch,
+                        void* stream) {
   int rc = check_problem(p);
   if (rc) return rc;
   if (!guess_pulses || !opt_pulses || !phi0 || !g_a || !workspace)
@@ -909,17 +923,34 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   if ((chi_kind == KQ_CHI_SS || chi_kind == KQ_CHI_SM) && !tau_in)
     return fail(KQ_ERR_ARG, "chis_ss/chis_sm need tau_in");
   if (chi_kind == KQ_CHI_HS && !phiT_in) return fail(KQ_ERR_ARG, "chis_hs needs phiT_in");
-  if (chi_kind >= 0 && K_total != p->K)
-    return fail(KQ_ERR_UNSUPPORTED, "kq_krotov_iteration is single-GPU (K_total must equal K)");
+  const int world = (comm && comm->world > 1) ? comm->world : 1;
+  if (world > 1 && (comm->world > kMaxWorld || !comm->slots || comm->rank < 0 ||
+                    comm->rank >= comm->world))
+    return fail(KQ_ERR_ARG, "invalid kq_comm (world=%d)", comm->world);
+  if (world == 1 && chi_kind >= 0 && K_total != p->K)
+    return fail(KQ_ERR_ARG, "K_total must equal K without a kq_comm");
+  if (world > 1 && (K_total < p->K || (K_total + world - 1) / world < p->K))
+    return fail(KQ_ERR_ARG, "K=%d objectives on this rank exceed ceil(K_total/world) = %d", p->K,
+                (K_total + world - 1) / world);
+  if (world > 1 && chi_kind == KQ_CHI_SM && !tau_sum)
+    return fail(KQ_ERR_ARG, "chis_sm with sharded objectives needs tau_sum");
   const bool second = sigma != nullptr;
   if (second && !Phi0) return fail(KQ_ERR_ARG, "second order needs Phi0");
   int dev;
   rc = device_init(&dev);
   if (rc) return rc;
   PicPlan pp;
-  if (!g_picard || !g_dev[dev].coop || !picard_plan(p, g_dev[dev].sms, pp))
+  // all ranks use the geometry of the largest block of objectives
+  const int K_plan = world > 1 ? (K_total + world - 1) / world : p->K;
+  if (!g_picard || !g_dev[dev].coop || !picard_plan(p, g_dev[dev].sms, pp, K_plan))
     return fail(KQ_ERR_UNSUPPORTED, "problem is outside the time-parallel kernel family");
   KqSweepArgs a = base_args(p);
+  if (world > 1) {
+    a.rank = comm->rank;
+    a.world = world;
+    a.peer_slots = reinterpret_cast<KqSlot* const*>(comm->slots);
+    a.tau_sum = reinterpret_cast<const cplx*>(tau_sum);
+  }
   a.ops = reinterpret_cast<const cplx*>(p->ops);
   a.ops_adj = reinterpret_cast<const cplx*>(p->ops_adj);
   a.pulses = guess_pulses;

@@ -400,6 +400,39 @@ __device__ __forceinline__ void pic_scan_finish(const cplx (&M)[N * N], const cp
   }
 }
 
+// Sum over the GPUs of one partial sum (entry `ni` of the time slice owned by this CTA) in
+// rank order; every rank obtains the same bits.  One NVLink store per peer, then polling of
+// this rank's own buffer only.  `round` selects the sub-buffer together with the epoch: a
+// slot is rewritten two launches (or two rounds) later at the earliest, when every rank has
+// long finished reading it (each rank contributes to a round only after it has completed
+// the round before).
+__device__ __forceinline__ double pic_xg_allreduce(const KqSweepArgs& a, double v, int ni,
+                                                   int lwc, int round, uint32_t tag,
+                                                   bool& failed) {
+  const int world = a.world;
+  const size_t base = a.pic_xg_off +
+                      (size_t)((((int)a.epoch & 1) << 1) | (round & 1)) * a.pic_xg_buf +
+                      (((size_t)blockIdx.x * world) << lwc) + ni;
+  for (int r = 0; r < world; ++r)
+    slot_store(a.peer_slots[r] + base + ((size_t)a.rank << lwc), v, tag);
+  const KqSlot* mine = a.peer_slots[a.rank] + base;
+  double acc = 0.0;
+  for (int r0 = 0; r0 < world; r0 += 4) {
+    const KqSlot* ptr[4];
+    bool act[4];
+    double pv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      act[u] = r0 + u < world;
+      ptr[u] = mine + ((size_t)(act[u] ? r0 + u : 0) << lwc);
+    }
+    slot_wait_batch<4>(ptr, act, tag, pv, failed);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += pv[u];
+  }
+  return acc;
+}
+
 __device__ __forceinline__ void pic_prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
@@ -664,14 +697,19 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         cf = c_make(tk.x / Kt * wgt, tk.y / Kt * wgt);
       } else {   // KQ_CHI_SM: sum_j w_j tau_j over all objectives, fixed order
         double sx = 0.0, sy = 0.0;
-        for (int j = tid; j < K; j += BT) {
-          const double wj = a.weights ? a.weights[j] : 1.0;
-          const cplx tj = a.tau_in[j];
-          sx = fma(wj, tj.x, sx);
-          sy = fma(wj, tj.y, sy);
+        if (a.tau_sum) {   // sharded objectives: the caller summed over the ranks
+          sx = a.tau_sum[0].x;
+          sy = a.tau_sum[0].y;
+        } else {
+          for (int j = tid; j < K; j += BT) {
+            const double wj = a.weights ? a.weights[j] : 1.0;
+            const cplx tj = a.tau_in[j];
+            sx = fma(wj, tj.x, sx);
+            sy = fma(wj, tj.y, sy);
+          }
+          sx = block_sum(sx, scratch + 192);
+          sy = block_sum(sy, scratch + 192);
         }
-        sx = block_sum(sx, scratch + 192);
-        sy = block_sum(sy, scratch + 192);
         const double f = (1.0 / (Kt * Kt)) * wgt;
         cf = c_make(f * sx, f * sy);
       }
@@ -1060,6 +1098,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
         if (tid < Wc && n_lo + tid < NT) {
           double acc = red[tid];
           for (int w = 1; w < nwarps; ++w) acc += red[w * 16 + tid];
+          if (a.world > 1) acc = pic_xg_allreduce(a, acc, tid, lwc, it, tag, failed);
           const double sl = own_sl[tid];
           ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), own_dt[tid]));
           own_eps[tid] = __dadd_rn(own_g[tid], __dmul_rn(sl, acc));
@@ -1087,6 +1126,7 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
 #pragma unroll
               for (int u = 0; u < 4; ++u) acc += pv[u];
             }
+            if (a.world > 1) acc = pic_xg_allreduce(a, acc, ni, lwc, it, tag, failed);
             const double sl = own_sl[ni];
             ga_acc = __dadd_rn(ga_acc, __dmul_rn(__dmul_rn(sl, __dmul_rn(acc, acc)), own_dt[ni]));
             own_eps[ni] = __dadd_rn(own_g[ni], __dmul_rn(sl, acc));

@@ -90,6 +90,14 @@ struct KqSweepArgs {
   cplx* chi_out;             // [K][N] or null
   double* chi_norms_out;     // [K] or null
   int* diag_out;             // [4] copy of the status words {status, failed epoch, rounds, 0} or null
+  // objectives sharded over GPUs (world > 1): after the owner CTA of a time slice has summed
+  // the partial sums of this GPU's CTAs it writes that sum into the slice's slots of every
+  // rank's exchange buffer (peer_slots[r] + pic_xg_off, layout [4][cta][rank][2^pic_lwc],
+  // the 4 sub-buffers selected by the parities of epoch and round) and adds what the other
+  // ranks wrote into its own buffer, in rank order: identical pulses on every GPU
+  size_t pic_xg_off;         // in slots
+  size_t pic_xg_buf;         // slots per sub-buffer
+  const cplx* tau_sum;       // chis_sm with sharded objectives: sum_j w_j tau_j over ALL ranks
 };
 
 __device__ __forceinline__ void kq_store(const KqSweepArgs& a, size_t idx, cplx v) {

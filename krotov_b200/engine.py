@@ -81,7 +81,9 @@ class SweepEngine:
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self._iter_args = {}    # marshalled kq_krotov_iteration arguments
         self.epoch = 0
-        self.comm = None      # KqComm: per-time-step exchange ('exchange' mode)
+        self.comm = None      # KqComm: cross-GPU exchange (objectives sharded)
+        self.shard = None     # ShardComm owning `comm` (NCCL collectives)
+        self.K_total = cp.K   # objectives over all ranks
         self.gather = None    # dict set by ShardComm.attach_gather
         K, N, NT = cp.K, cp.N, cp.NT
         self.X = torch.empty((NT + 1, K, N), dtype=c128, device=dev)
@@ -206,9 +208,16 @@ class SweepEngine:
         # the pointer arguments repeat with the rotating buffer sets of the
         # caller: marshal them once per combination (the cache keeps the
         # tensors alive, so an id cannot be re-used by another tensor)
+        tau_sum = None
+        if kind == CHI_KINDS['sm'] and self.comm is not None:
+            # sum_j w_j tau_j over the objectives of ALL ranks (NCCL, on the
+            # compute stream; no host synchronisation)
+            w = tau_in if self.t_weights is None else tau_in * self.t_weights
+            tau_sum = self._tau_sum = w.sum().reshape(1)
+            self.shard.all_reduce_sum(tau_sum)
         tensors = (tau_in, phiT_in, guess_t, prev_guess_t, opt_t, phiT_out,
                    tau_out, self.X if store_X else None, sigma_t, Phi0, Phi1,
-                   self.g_a, diag_t)
+                   self.g_a, diag_t, tau_sum)
         key = (kind,) + tuple(map(id, tensors))
         hit = self._iter_args.get(key)
         if hit is None:
@@ -218,7 +227,7 @@ class SweepEngine:
             def ptr(t):
                 return 0 if t is None else t.data_ptr()
             hit = (tensors, (
-                self._p, kind, self.cp.K, ptr(self.t_targets),
+                self._p, kind, self.K_total, ptr(self.t_targets),
                 ptr(self.t_weights),
                 ptr(self.chi if kind < 0 else None),
                 ptr(self.chi_norms if kind < 0 else None),
@@ -228,7 +237,9 @@ class SweepEngine:
                 ptr(None if kind < 0 else self.chi),
                 ptr(None if kind < 0 else self.chi_norms),
                 ptr(sigma_t), ptr(Phi0), ptr(Phi1), ptr(self.g_a),
-                ptr(diag_t), ptr(self.workspace)))
+                ptr(diag_t),
+                None if self.comm is None else ctypes.byref(self.comm),
+                ptr(tau_sum), ptr(self.workspace)))
             self._iter_args[key] = hit
         check(self.lib.kq_krotov_iteration(
             *hit[1], self.epoch & 0xFFFFFFFF, self.raw_stream()))
@@ -237,8 +248,8 @@ class SweepEngine:
     def fused_supported(self):
         """True if :meth:`krotov_iteration` handles this problem."""
         cp = self.cp
-        return (self.comm is None and self.gather is None and cp.M == 2
-                and cp.L == 1 and 2 <= cp.N <= 4)
+        return (self.gather is None and cp.M == 2 and cp.L == 1
+                and 2 <= cp.N <= 4)
 
     def clear_fused_failure(self):
         """Reset the 'first failed epoch' status word."""

@@ -358,8 +358,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 raise ValueError("fewer objectives than GPUs")
             from ._dense import dense as _dense
             n_state = _dense(objectives[0].initial_state).size
-            shard_mode = parallel_map.choose(K_total, n_state)
-            if shard_mode == 'exchange':
+            shard_mode = parallel_map.choose(K_total, n_state, world)
+            if shard_mode in ('exchange', 'sharded'):
                 lo, hi = shard_bounds(K_total, world, rank)
     local_objectives = objectives[lo:hi]
     cp = compile_problem(local_objectives, controls, pulses_mapping[lo:hi],
@@ -371,6 +371,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     gather_comm = None
     if (hi - lo) != K_total:
         shard = ShardComm(dist, group, eng.device).attach(eng)
+        eng.K_total = K_total
     if shard_mode == 'replicate' and not (
             engine_mode is None and eng.fused_supported()):
         shard_mode = 'gather'     # outside the one-launch kernel family
@@ -385,8 +386,10 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         raise ValueError("engine_mode must be None or 'sweeps'")
     # one-launch-per-iteration kernel family (csrc/kq_picard.cuh); falls back
     # to the sweep kernels when the library declines or does not converge
-    use_fused = (engine_mode is None and shard is None
-                 and gather_comm is None and eng.fused_supported())
+    # ('sharded': the kernel itself sums over the GPUs in every round)
+    use_fused = (engine_mode is None and gather_comm is None
+                 and (shard is None or shard_mode == 'sharded')
+                 and eng.fused_supported())
     L, NT, K = cp.L, cp.NT, K_total
     has_targets = cp.targets is not None
     templates = [obj.initial_state for obj in objectives]
@@ -635,7 +638,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 if packed is not None:
                     packed.mark(ri, eng)
             except KqError as exc:
-                if 'error -3' not in str(exc):
+                if exc.status != -3:     # KQ_ERR_UNSUPPORTED
                     raise
                 use_fused = False      # outside the fused kernel family
         fetched = None

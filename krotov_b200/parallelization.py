@@ -68,6 +68,15 @@ class GPUShards:
             state vectors, where the sweep is bound by the chain of nt-1
             dependent steps and not by throughput.
 
+            ``'sharded'``: every rank owns a block of objectives for all
+            sweeps and runs the one-launch time-parallel iteration kernel
+            (``kq_krotov_iteration``) on it; in every fixed-point round of
+            that kernel the per-time-step sums over the objectives cross the
+            GPUs once (nt doubles per GPU written straight into the peers'
+            exchange buffers over NVLink, added in rank order), so all ranks
+            obtain bit-identical pulses.  Iterations the kernel family does
+            not cover fall back to ``'exchange'``.
+
             ``'replicate'``: every rank runs the complete problem with the
             one-launch time-parallel iteration kernel (``kq_krotov_iteration``)
             and no communication at all; all ranks obtain identical pulses
@@ -75,23 +84,23 @@ class GPUShards:
             family a single GPU is already latency-bound, so sharding them
             only adds exchange latency: this is the fastest correct choice.
 
-            ``'auto'`` (default): ``'replicate'`` for N <= 4 and K <= 1184
-            (falls back to ``'gather'`` if the engine declines), else
-            ``'gather'`` if ``K * N * N <= 65536``, else ``'exchange'``.
+            ``'auto'`` (default): ``'sharded'`` for N <= 4 and at most
+            1184 objectives per GPU, else ``'gather'`` if
+            ``K * N * N <= 65536``, else ``'exchange'``.
     """
 
     def __init__(self, group=None, mode='auto'):
-        if mode not in ('auto', 'exchange', 'gather', 'replicate'):
-            raise ValueError("mode must be 'auto', 'exchange', 'gather' or "
-                             "'replicate'")
+        if mode not in ('auto', 'exchange', 'gather', 'replicate', 'sharded'):
+            raise ValueError("mode must be 'auto', 'sharded', 'exchange', "
+                             "'gather' or 'replicate'")
         self.group = group
         self.mode = mode
 
-    def choose(self, K, N):
+    def choose(self, K, N, world=1):
         if self.mode != 'auto':
             return self.mode
-        if N <= 4 and K <= 1184:
-            return 'replicate'
+        if N <= 4 and -(-K // max(world, 1)) <= 1184:
+            return 'sharded'
         return 'gather' if K * N * N <= 65536 else 'exchange'
 
     def resolve(self):
@@ -144,6 +153,7 @@ class ShardComm:
                              slots=self.slots_t.data_ptr())
         if for_exchange:
             eng.comm = self.kqcomm
+            eng.shard = self
         self._eng = eng
         self._barrier_tag = 0
         self.dist.barrier(group=self.group)

@@ -20,7 +20,13 @@ def main():
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     rank, world = dist.get_rank(), dist.get_world_size()
     ok = True
-    for K, nt, chi, mode in ((37, 120, 're', 'exchange'),
+    for K, nt, chi, mode in ((128, 1000, 're', 'sharded'),
+                             (37, 120, 're', 'sharded'),
+                             (128, 300, 'sm', 'sharded'),
+                             (6, 80, 'ss', 'sharded'),
+                             (9, 200, 'hs', 'sharded'),
+                             (1031, 400, 're', 'sharded'),
+                             (37, 120, 're', 'exchange'),
                              (128, 300, 'sm', 'exchange'),
                              (6, 80, 'ss', 'exchange'),
                              (37, 120, 're', 'gather'),
@@ -47,6 +53,17 @@ def main():
             wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
             propagator=krotov.propagators.expm, chi_constructor=chi_fn,
             iter_stop=3, store_all_pulses=True)
+        if mode == 'sharded':
+            # the hook-free fast path (no host synchronisation per iteration)
+            fast = krotov.optimize_pulses(
+                wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+                propagator=krotov.propagators.expm, chi_constructor=chi_fn,
+                iter_stop=3, store_all_pulses=True,
+                parallel_map=GPUShards(mode=mode))
+            assert np.array_equal(np.array(fast.all_pulses),
+                                  np.array(res.all_pulses))
+            assert fast.fused_iterations == 3 and res.fused_iterations == 3, \
+                (fast.fused_iterations, res.fused_iterations)
         got = np.array(res.all_pulses)
         want = np.array(ref.all_pulses)
         err = np.max(np.abs(got - want)) / np.max(np.abs(want))
