@@ -86,6 +86,12 @@ typedef struct {
                          form of f*A in Hilbert space; 0: general complex */
   int32_t reserved;   /* kq_sweep_forward_update: number of time windows of the
                          time-parallel update sweep (0 = as few as fit shared memory) */
+  int32_t update_sweep; /* which fast update sweep to prefer where both apply (N = 3, 4, few
+                         objectives): 0 = library default (time-parallel fixed point),
+                         1 = delta-polynomial sequential sweep (strongly coupled problems:
+                         the fixed point needs many rounds there), 2 = fixed point.
+                         N > 4 always uses the delta-polynomial sweep if it fits. */
+  int32_t reserved2;
 } kq_problem;
 
 /* Cross-GPU exchange descriptor for the per-time-step reduction of the pulse
@@ -119,6 +125,13 @@ const char* kq_last_error(void);
  * of cudaLaunchCooperativeKernel (co-residency is still checked against the
  * occupancy limit; the kernels wait for the preceding launches before they
  * touch memory).
+ * "dpoly" (default 1): the delta-polynomial update sweep (csrc/kq_dpoly.cuh: few
+ * objectives, one control, first order; per time step ONE small matrix-vector product
+ * with a propagator that is a polynomial in this iteration's pulse update) is used
+ * where kq_problem.update_sweep / the state dimension ask for it; 0: never; 2:
+ * wherever it fits.  The sequential Taylor kernels are always queued behind it as an
+ * in-stream conditional fall-back (taken when the update exceeds the bound the
+ * polynomials were built for).
  * "time_parallel" (default 1): propagation
  * sweeps under known pulses (kq_propagate_forward, kq_sweep_backward*) are cut
  * into time segments that run concurrently (segment propagators -> boundary

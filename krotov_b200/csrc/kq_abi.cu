@@ -11,6 +11,7 @@
 #include <string>
 
 #include "kq_host.cuh"
+#include "kq_dpoly_geom.cuh"
 
 int g_kq_coop_launch = 1;
 int g_kq_pdl_launch = 0;
@@ -59,19 +60,21 @@ struct Scratch {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-Scratch g_scratch[kMaxDevices];
+Scratch g_scratch[kMaxDevices][2];   // slot 0: time-parallel propagation, 1: dpoly records
 bool g_disable_segments = false;   // kq_set_option("time_parallel", 0)
 int g_picard = 1;                  // kq_set_option("picard", 0|1|2): off / auto / forced
 int g_picard_timing = 0;
 int g_picard_history = 1;          // kq_set_option("picard_history", 0|1): update-history hint
 int g_picard_maxit = 64;           // kq_set_option("picard_maxit", n)
+int g_dpoly = 1;                   // kq_set_option("dpoly", 0|1|2): off / auto / wherever it fits
+int g_dpoly_debug = 0;             // kq_set_option("dpoly_debug", 1): no sequential kernel behind it
 constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
 constexpr int kPicMaxItCap = 1000;
 constexpr int kPicMaxWindows = 64;   // time windows of one windowed update sweep
 
-int get_scratch(int dev, size_t bytes, void** out) {
+int get_scratch(int dev, size_t bytes, void** out, int slot = 0) {
   std::lock_guard<std::mutex> lock(g_mu);
-  Scratch& sc = g_scratch[dev];
+  Scratch& sc = g_scratch[dev][slot];
   if (sc.bytes < bytes) {
     if (sc.ptr) KQ_CUDA(cudaFree(sc.ptr));   // synchronises the device
     sc.ptr = nullptr;
@@ -123,7 +126,7 @@ int device_init(int* dev_out) {
         kq_tables_upload_spec_fw3_re, kq_tables_upload_spec_fw4_re,
         kq_tables_upload_warp0,    kq_tables_upload_warp8,    kq_tables_upload_warp16,
         kq_tables_upload_warp32,   kq_tables_upload_picard2,  kq_tables_upload_picard3,
-        kq_tables_upload_picard4};
+        kq_tables_upload_picard4,  kq_tables_upload_dpoly};
     for (auto up : uploads) {
       const int rc = up(&T);
       if (rc) return rc;
@@ -287,6 +290,76 @@ bool picard_plan(const kq_problem* p, int sms, PicPlan& pp, int K_plan = 0) {
   pp.stride = (int)pic_stride(p);
   pp.smem = smem;
   return true;
+}
+
+size_t dpoly_header_offset(const kq_problem* p) {
+  size_t bytes = kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
+  if (p && p->NT > 0) {   // slots of the time-parallel fused sweep: part | eps | ga
+    bytes += (size_t)2 * kPicMaxBlocks * pic_stride(p) * sizeof(KqSlot);
+    bytes += 64 + (size_t)4 * pic_hist_ld(p) * sizeof(double);   // update history: header | ring
+  }
+  return (bytes + 63) / 64 * 64;
+}
+
+// ---- delta-polynomial update sweep (kq_dpoly.cuh): few objectives, one control ----
+struct DpPlan {
+  KqDpoly d;
+  KqDpolyGeom g;
+};
+bool dpoly_plan(const kq_problem* p, DpPlan& dp) {
+  const int K = p->K, N = p->N;
+  if (p->M != 2 || p->L != 1 || N < 2 || N > 16 || p->NT < 2) return false;
+  int Q = 1;
+  while (Q < N && Q < 8) Q <<= 1;
+  while (Q > 1 && (long long)K * (N + 1) * Q > KQ_DP_MAXLANES) Q >>= 1;
+  const int Npad = round_up(N, Q), C = Npad / Q;
+  const long long NL = (long long)K * (N + 1) * Q;   // rows of E plus the zeta row
+  if (C > KQ_DP_CMAX || NL > KQ_DP_MAXLANES) return false;
+  const size_t rec_stride = (size_t)C * NL * ((KQ_DP_JMAX + 1) | 1) + 2;
+  const size_t fixed = 2 * KQ_DP_RINGMAX * 8 + (size_t)((2 * K + 1) & ~1) * 8 + (size_t)((K * N + 1) & ~1) * 8 +
+                       (size_t)2 * K * Npad * 16;
+  if (fixed + 2 * rec_stride * 16 > kSmemBudget) return false;
+  // ring capacity: up to 16 records of the highest degree, within the shared-memory budget
+  const size_t ring = std::min<size_t>((size_t)KQ_DP_RINGMAX * rec_stride, (kSmemBudget - fixed) / 16);
+  // build kernel: one thread per matrix element, polynomial double-buffered + conj(eta)
+  const size_t per = ((size_t)2 * (KQ_DP_JMAX + 1) * N * N + N) * 16;
+  const int TPC = std::max(1, std::min(256 / (N * N), (int)(100 * 1024 / per)));
+  if ((size_t)TPC * per > kSmemBudget) return false;
+  std::memset(&dp, 0, sizeof dp);
+  dp.d.rec_stride = (int)rec_stride;
+  dp.d.NL = (int)NL;
+  dp.d.Q = Q;
+  dp.d.C = C;
+  dp.d.Npad = Npad;
+  dp.d.TPC = TPC;
+  dp.d.ring = (int)ring;
+  dp.g.nmax = N <= 4 ? 4 : (N <= 8 ? 8 : 16);
+  dp.g.smem_build = (size_t)TPC * per;
+  dp.g.smem_sweep = fixed + ring * 16;
+  return true;
+}
+// The delta-polynomial sweep is the only fast update sweep for N > 4; for N <= 4 the caller
+// asks for it (kq_problem.update_sweep = 1) when the problem is strongly coupled -- the
+// time-parallel fixed point needs many rounds there.
+bool dpoly_preferred(const kq_problem* p) {
+  if (g_dpoly == 2) return true;
+  return g_dpoly == 1 && (p->N > 4 || p->update_sweep == 1);
+}
+// plan | build | zeta | sweep on `st`; `a` is the argument block of the update sweep
+// (a.X = backward states, a.epoch set).  The caller queues the sequential kernel behind it
+// with cond_epoch = epoch, then launch_dpoly_epilogue.
+size_t dpoly_rec_bytes(const kq_problem* p, const DpPlan& dp) {
+  return ((size_t)p->NT * dp.d.rec_stride * sizeof(cplx) + 255) / 256 * 256;
+}
+int launch_dpoly(const kq_problem* p, const KqSweepArgs& a, DpPlan& dp, void* workspace, int dev,
+                 cudaStream_t st, void* rec = nullptr) {
+  if (!rec) {
+    int rc = get_scratch(dev, dpoly_rec_bytes(p, dp), &rec, 1);
+    if (rc) return rc;
+  }
+  dp.d.rec = reinterpret_cast<cplx*>(rec);
+  dp.d.hdr = reinterpret_cast<KqDpHeader*>(static_cast<char*>(workspace) + dpoly_header_offset(p));
+  return kq_launch_dpoly(a, dp.d, dp.g, st);
 }
 
 // Fill the time-parallel family's launch arguments and launch it.
@@ -538,6 +611,27 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   return launch_warp(a2, pl2, fsel, false, false, st);
 }
 
+// The sequential update/forward sweep kernels (one time step after the other).
+int launch_sequential_update(const kq_problem* p, const KqSweepArgs& a, const Plan& pl, int fsel,
+                             bool second, cudaStream_t st) {
+  if (pl.family == 0) {
+    if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
+    if (p->real_ops && !p->is_super) {
+      switch (p->N) {
+        case 2: return kq_launch_fwupd_spec2_re(a, pl, fsel, second, st);
+        case 3: return kq_launch_fwupd_spec3_re(a, pl, fsel, second, st);
+        default: return kq_launch_fwupd_spec4_re(a, pl, fsel, second, st);
+      }
+    }
+    switch (p->N) {
+      case 2: return kq_launch_fwupd_spec2(a, pl, fsel, second, st);
+      case 3: return kq_launch_fwupd_spec3(a, pl, fsel, second, st);
+      default: return kq_launch_fwupd_spec4(a, pl, fsel, second, st);
+    }
+  }
+  return launch_warp(a, pl, fsel, second, true, st);
+}
+
 // ---- boundary condition / overlaps --------------------------------------
 __global__ void k_overlaps(int K, int N, const cplx* __restrict__ a, const cplx* __restrict__ b,
                            cplx* __restrict__ out) {
@@ -621,11 +715,104 @@ __global__ void k_chi_boundary(int K, int N, int kind, int K_total, const cplx* 
   }
 }
 
+// sum_j w_j tau_j in a fixed order (chis_sm, functionals.py:225-253); one CTA
+__global__ void __launch_bounds__(256) k_tau_sum(int K, const cplx* __restrict__ tau,
+                                                 const double* __restrict__ weights,
+                                                 cplx* __restrict__ out) {
+  __shared__ double sx[8], sy[8];
+  double x = 0.0, y = 0.0;
+  for (int j = threadIdx.x; j < K; j += 256) {
+    const double w = weights ? weights[j] : 1.0;
+    x = fma(w, tau[j].x, x);
+    y = fma(w, tau[j].y, y);
+  }
+  x = warp_allreduce_sum(x);
+  y = warp_allreduce_sum(y);
+  if ((threadIdx.x & 31) == 0) {
+    sx[threadIdx.x >> 5] = x;
+    sy[threadIdx.x >> 5] = y;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      x += sx[w];
+      y += sy[w];
+    }
+    out[0] = c_make(x, y);
+  }
+}
+
+// One Krotov iteration as a sequence of launches for problems the delta-polynomial sweep
+// serves (few objectives, one control, first order): chi boundary | backward sweep |
+// plan, build, zeta, sweep | conditional sequential kernel | epilogue | tau.
+int composite_iteration(const kq_problem* p, DpPlan& dp, KqSweepArgs a, int chi_kind,
+                        int32_t K_total, const double* guess_pulses, void* workspace, int dev,
+                        cudaStream_t st) {
+  const int K = p->K, N = p->N, NT = p->NT;
+  // scratch behind the step records: X | chi | phi(T) | chi norms | tau sum
+  const size_t recb = dpoly_rec_bytes(p, dp);
+  const size_t xb = ((size_t)(NT + 1) * K * N * sizeof(cplx) + 255) / 256 * 256;
+  const size_t sb = ((size_t)K * N * sizeof(cplx) + 255) / 256 * 256;
+  const size_t nb = ((size_t)K * sizeof(double) + 255) / 256 * 256;
+  void* base = nullptr;
+  int rc = get_scratch(dev, recb + xb + 2 * sb + nb + 256, &base, 1);
+  if (rc) return rc;
+  char* cur = static_cast<char*>(base) + recb;
+  cplx* X = a.Xout ? a.Xout : reinterpret_cast<cplx*>(cur);
+  cur += xb;
+  cplx* chi = a.chi_out ? a.chi_out : reinterpret_cast<cplx*>(cur);
+  cur += sb;
+  cplx* phiT = a.stateT ? a.stateT : reinterpret_cast<cplx*>(cur);
+  cur += sb;
+  double* norms = a.chi_norms_out ? a.chi_norms_out : reinterpret_cast<double*>(cur);
+  cur += nb;
+  cplx* tsum = reinterpret_cast<cplx*>(cur);
+  if (chi_kind >= 0) {
+    if (chi_kind == KQ_CHI_SM) {
+      k_tau_sum<<<1, 256, 0, st>>>(K, a.tau_in, a.weights, tsum);
+      KQ_CUDA(cudaGetLastError());
+    }
+    const int bt = 128;
+    k_chi_boundary<<<(K + bt - 1) / bt, bt, 0, st>>>(K, N, chi_kind, K_total, a.phiT_in, a.targets,
+                                                     a.tau_in, a.weights, tsum, chi, norms);
+    KQ_CUDA(cudaGetLastError());
+  } else {
+    chi = const_cast<cplx*>(a.chiT);
+    norms = const_cast<double*>(a.chi_norms);
+  }
+  rc = run_prop(p, true, guess_pulses, reinterpret_cast<const kq_c128*>(chi), nullptr,
+                reinterpret_cast<kq_c128*>(X), st, 0, -1);
+  if (rc) return rc;
+  a.X = X;
+  a.chi_norms = norms;
+  a.stateT = phiT;
+  a.pic_bw = 0;
+  rc = launch_dpoly(p, a, dp, workspace, dev, st, base);
+  if (rc) return rc;
+  a.cond_epoch = a.epoch;
+  Plan pl;
+  rc = make_plan(p, true, false, g_dev[dev].sms, pl);
+  if (rc) return rc;
+  if (pl.grid > kMaxBlocks) return fail(KQ_ERR_UNSUPPORTED, "too many CTAs (%d)", pl.grid);
+  a.slots = reinterpret_cast<KqSlot*>(static_cast<char*>(workspace) + kStatusBytes);
+  a.tag_base = a.epoch * (uint32_t)(NT + 1);
+  rc = launch_sequential_update(p, a, pl, p->is_super ? 2 : 0, false, st);
+  if (rc) return rc;
+  rc = kq_launch_dpoly_epilogue(a, dp.d, st);
+  if (rc) return rc;
+  if (a.tau_out && a.targets) {
+    const int bt = 128;
+    k_overlaps<<<(K + bt - 1) / bt, bt, 0, st>>>(K, N, a.targets, phiT, a.tau_out);
+    KQ_CUDA(cudaGetLastError());
+  }
+  return KQ_OK;
+}
+
 }  // namespace
 
 extern "C" {
 
-int kq_version(void) { return 103; }
+int kq_version(void) { return 104; }
 
 int kq_set_option(const char* name, int value) {
   if (name && std::strcmp(name, "time_parallel") == 0) {
@@ -647,6 +834,15 @@ int kq_set_option(const char* name, int value) {
   }
   if (name && std::strcmp(name, "programmatic_launch") == 0) {
     g_kq_pdl_launch = value ? 1 : 0;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "dpoly") == 0) {
+    if (value < 0 || value > 2) return fail(KQ_ERR_ARG, "dpoly must be 0, 1 or 2");
+    g_dpoly = value;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "dpoly_debug") == 0) {
+    g_dpoly_debug = value ? 1 : 0;
     return KQ_OK;
   }
   if (name && std::strcmp(name, "picard_history") == 0) {
@@ -718,12 +914,7 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* st
 }
 
 size_t kq_workspace_bytes(const kq_problem* p) {
-  size_t bytes = kStatusBytes + (size_t)2 * kMaxBlocks * KQ_LMAX * sizeof(KqSlot);
-  if (p && p->NT > 0) {   // slots of the time-parallel fused sweep: part | eps | ga
-    bytes += (size_t)2 * kPicMaxBlocks * pic_stride(p) * sizeof(KqSlot);
-    bytes += 64 + (size_t)4 * pic_hist_ld(p) * sizeof(double);   // update history: header | ring
-  }
-  return bytes;
+  return dpoly_header_offset(p) + 64;   // ... | header of the delta-polynomial sweep
 }
 
 int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
@@ -832,7 +1023,16 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   }
   const int fsel = p->is_super ? 2 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  a.epoch = epoch;
+  a.epoch = epoch ? epoch : 1u;
+  // few objectives, one control: delta-polynomial sweep (kq_dpoly.cuh) with the sequential
+  // kernel queued behind it as an in-stream conditional fall-back
+  DpPlan dp;
+  const bool use_dpoly = !second && a.world == 1 && dpoly_preferred(p) && dpoly_plan(p, dp);
+  if (use_dpoly) {
+    rc = launch_dpoly(p, a, dp, workspace, dev, st);
+    if (rc) return rc;
+    a.cond_epoch = a.epoch;
+  }
   // time-parallel fused sweep (kq_picard.cuh), with the sequential kernel
   // queued behind it as a conditional fall-back.  The sweep may be cut into
   // time windows that are solved one after the other (each a fixed-point
@@ -841,7 +1041,7 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   // faster for strongly coupled problems, where the number of rounds grows with
   // the length of the interval (kq_problem.reserved = number of windows, 0 = as
   // few as fit).
-  if (g_picard && pl.family == 0 && pl.spec && a.world == 1 && g_dev[dev].coop) {
+  if (!use_dpoly && g_picard && pl.family == 0 && pl.spec && a.world == 1 && g_dev[dev].coop) {
     int nwin = p->reserved > 0 ? std::min(p->reserved, kPicMaxWindows) : 1;
     nwin = std::min(nwin, std::max(1, p->NT / 32));
     kq_problem pw = *p;
@@ -885,22 +1085,12 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
       a.cond_epoch = epoch ? epoch : 1u;   // the sequential kernel below runs only on request
     }
   }
-  if (pl.family == 0) {
-    if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
-    if (p->real_ops && !p->is_super) {
-      switch (p->N) {
-        case 2: return kq_launch_fwupd_spec2_re(a, pl, fsel, second, st);
-        case 3: return kq_launch_fwupd_spec3_re(a, pl, fsel, second, st);
-        default: return kq_launch_fwupd_spec4_re(a, pl, fsel, second, st);
-      }
-    }
-    switch (p->N) {
-      case 2: return kq_launch_fwupd_spec2(a, pl, fsel, second, st);
-      case 3: return kq_launch_fwupd_spec3(a, pl, fsel, second, st);
-      default: return kq_launch_fwupd_spec4(a, pl, fsel, second, st);
-    }
+  if (!(use_dpoly && g_dpoly_debug)) {
+    rc = launch_sequential_update(p, a, pl, fsel, second, st);
+    if (rc) return rc;
   }
-  return launch_warp(a, pl, fsel, second, true, st);
+  if (use_dpoly) return kq_launch_dpoly_epilogue(a, dp.d, st);
+  return KQ_OK;
 }
 
 int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
@@ -942,7 +1132,10 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   PicPlan pp;
   // all ranks use the geometry of the largest block of objectives
   const int K_plan = world > 1 ? (K_total + world - 1) / world : p->K;
-  if (!g_picard || !g_dev[dev].coop || !picard_plan(p, g_dev[dev].sms, pp, K_plan))
+  DpPlan dp;
+  const bool composite = !second && world == 1 && dpoly_preferred(p) && dpoly_plan(p, dp);
+  if (!composite &&
+      (!g_picard || !g_dev[dev].coop || !picard_plan(p, g_dev[dev].sms, pp, K_plan)))
     return fail(KQ_ERR_UNSUPPORTED, "problem is outside the time-parallel kernel family");
   KqSweepArgs a = base_args(p);
   if (world > 1) {
@@ -976,6 +1169,12 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   a.chi_out = reinterpret_cast<cplx*>(chi_out);
   a.chi_norms_out = chi_norms_out;
   a.diag_out = diag_out;
+  if (composite) {
+    a.epoch = epoch ? epoch : 1u;
+    a.status = reinterpret_cast<int*>(workspace);
+    return composite_iteration(p, dp, a, chi_kind, K_total, guess_pulses, workspace, dev,
+                               static_cast<cudaStream_t>(stream));
+  }
   return launch_picard(p, a, pp, workspace, epoch, second, static_cast<cudaStream_t>(stream));
 }
 

@@ -141,6 +141,7 @@ int kq_tables_upload_warp32(const KqTables* T);
 int kq_tables_upload_picard2(const KqTables* T);
 int kq_tables_upload_picard3(const KqTables* T);
 int kq_tables_upload_picard4(const KqTables* T);
+int kq_tables_upload_dpoly(const KqTables* T);
 
 int kq_launch_prop_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
 int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
@@ -167,6 +168,14 @@ int kq_launch_picard3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool sec
                             bool real, cudaStream_t st);
 int kq_launch_picard4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                             bool real, cudaStream_t st);
+// delta-polynomial update sweep (kq_dpoly.cuh)
+struct KqDpoly;
+struct KqDpolyGeom {
+  int nmax;             // register rows of the build kernel (4, 8, 16, 32)
+  size_t smem_build, smem_sweep;
+};
+int kq_launch_dpoly(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom& g, cudaStream_t st);
+int kq_launch_dpoly_epilogue(const KqSweepArgs& a, const KqDpoly& d, cudaStream_t st);
 int kq_launch_warp0(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
                     cudaStream_t st);
 int kq_launch_warp8(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,

@@ -242,6 +242,8 @@ template <int N, int FSEL, bool SECOND, int BTMAX>
 __global__ void __launch_bounds__(BTMAX, 1)
 k_fwupd_small(const KqSweepArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // fall-back of a faster sweep kernel queued before this one: run only if it asked for it
+  if (a.cond_epoch && *reinterpret_cast<volatile int*>(a.status + 1) != (int)a.cond_epoch) return;
   const KqTables& T = c_kq_tables;
   constexpr int NN = N * N;
   const int BT = blockDim.x, tid = threadIdx.x;

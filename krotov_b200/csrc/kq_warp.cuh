@@ -49,6 +49,10 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
   constexpr int AREG = (MODE >= 8) ? MODE : 0;
   static_assert(AREG == 0 || RPL == 1, "register rows need one row per lane");
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // fall-back of a faster update sweep queued before this one: run only if it asked for it
+  if (UPDATE && a.cond_epoch &&
+      *reinterpret_cast<volatile int*>(a.status + 1) != (int)a.cond_epoch)
+    return;
   const KqTables& T = c_kq_tables;
   const int K = a.K, N = a.N, NT = a.NT, M = a.M, L = a.L, NN = N * N;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

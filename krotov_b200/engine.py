@@ -68,6 +68,20 @@ class SweepEngine:
         self.t_psi0 = up(cp.psi0, c128)
         self.t_targets = None if cp.targets is None else up(cp.targets, c128)
         self.t_weights = None if cp.weights is None else up(cp.weights, f64)
+        # strongly coupled problems with few objectives and N = 3, 4: the
+        # time-parallel fixed point would need many rounds (their number grows
+        # with T * (S/lambda) * sum_k ||chi_k|| ||mu_k||^2), the delta-polynomial
+        # sequential sweep does not care
+        update_sweep = 0
+        if cp.M == 2 and cp.L == 1 and cp.N in (3, 4) and cp.K <= 16:
+            lam0 = float(np.asarray(lambda_vals, dtype=np.float64)[0])
+            smax = float(np.max(np.abs(np.asarray(shape_arrays[0]))))
+            mu2 = max(np.linalg.norm(np.asarray(cp.mu[k, 0]).reshape(
+                cp.N, cp.N), 2) for k in range(cp.K)) ** 2
+            coupling = float(np.sum(cp.dt)) * smax / lam0 * 0.5 * mu2
+            if coupling > 4.0:
+                update_sweep = 1
+        self.update_sweep = update_sweep
         self.problem = KqProblem(
             K=cp.K, N=cp.N, NT=cp.NT, L=cp.L, M=cp.M,
             is_super=1 if cp.is_super else 0,
@@ -75,7 +89,8 @@ class SweepEngine:
             mu=self.t_mu.data_ptr(), term2pulse=self.t_t2p.data_ptr(),
             op_norm=self.t_opn.data_ptr(), dt=self.t_dt.data_ptr(),
             shape=self.t_shape.data_ptr(), lambda_a=self.t_lambda.data_ptr(),
-            real_ops=1 if cp.real_ops else 0, reserved=0)
+            real_ops=1 if cp.real_ops else 0, reserved=0,
+            update_sweep=update_sweep, reserved2=0)
         self._p = ctypes.byref(self.problem)
         nbytes = self.lib.kq_workspace_bytes(self._p)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
@@ -248,8 +263,11 @@ class SweepEngine:
     def fused_supported(self):
         """True if :meth:`krotov_iteration` handles this problem."""
         cp = self.cp
+        # the library declines (KQ_ERR_UNSUPPORTED) what its kernel families
+        # do not cover: N <= 4 runs the time-parallel fixed-point kernel, few
+        # objectives with N >= 3 the delta-polynomial sweep (csrc/kq_dpoly.cuh)
         return (self.gather is None and cp.M == 2 and cp.L == 1
-                and 2 <= cp.N <= 4)
+                and cp.N >= 2)
 
     def clear_fused_failure(self):
         """Reset the 'first failed epoch' status word."""

@@ -51,6 +51,8 @@ class _PackedResults:
     synchronisation."""
 
     def __init__(self, torch, device, L, NT, K):
+        # K: complex numbers in the tau region (sharded objectives: the
+        # gathered phi(T) | tau blocks of all ranks)
         def up16(x):
             return (x + 15) // 16 * 16
         self.torch, self.L, self.NT, self.K = torch, L, NT, K
@@ -531,8 +533,44 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
     prev_guess_ref = None   # device pulses the previous iteration started from
     # hooked iterations: everything the host needs in one pinned copy
     packed = None
+    # objectives sharded over GPUs, one-launch kernel: every rank's
+    # phi(T) | tau block is all-gathered (ONE NCCL call per iteration, on the
+    # compute stream) straight into the packed buffer, so hooks on every rank
+    # see all objectives after the single device->host copy
+    sharded_packed = host_loop and shard is not None and use_fused
+    Kmax = -(-K_total // shard.world) if shard is not None else cp.K
     if host_loop and shard is None:
         packed = _PackedResults(torch, eng.device, L, NT, cp.K)
+    elif sharded_packed:
+        packed = _PackedResults(torch, eng.device, L, NT,
+                                shard.world * Kmax * (cp.N + 1))
+    loc_ring = [None, None, None]
+
+    def ring_loc(m):
+        """Rank-local phi(T) [Kmax, N] | tau [Kmax] of iteration m in one
+        buffer (the unit of the all-gather)."""
+        if loc_ring[m % 3] is None:
+            flat = torch.zeros(Kmax * (cp.N + 1), dtype=torch.complex128,
+                               device=eng.device)
+            loc_ring[m % 3] = dict(
+                flat=flat,
+                phiT=flat[:Kmax * cp.N].view(Kmax, cp.N)[:cp.K],
+                tau=flat[Kmax * cp.N:Kmax * cp.N + cp.K])
+        return loc_ring[m % 3]
+
+    def gather_into_packed(m):
+        shard.all_gather_flat(packed.views[m % 3]['tau'],
+                              ring_loc(m)['flat'])
+
+    def split_gathered(block):
+        """Host copy of the gathered region -> (tau [K], phi(T) [K, N])."""
+        G = np.array(block).reshape(shard.world, Kmax * (cp.N + 1))
+        taus, phis = [], []
+        for r in range(shard.world):
+            a, b = shard_bounds(K_total, shard.world, r)
+            phis.append(G[r, :Kmax * cp.N].reshape(Kmax, cp.N)[:b - a])
+            taus.append(G[r, Kmax * cp.N:Kmax * cp.N + (b - a)])
+        return np.concatenate(taus), np.concatenate(phis, axis=0)
     ri = 0
     # Hooked iterations rotate through three sets of output buffers (iteration
     # j: packed buffer, phi(T) and backward-state store number j % 3), so that
@@ -604,9 +642,13 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             ri = krotov_iteration % 3
             pv = packed.views[ri]
             opt_t = pv['pulses']
-            spare['tau'] = pv['tau']
             eng.g_a = pv['g_a']
-            spare['phiT'] = ring_phiT(krotov_iteration)
+            if sharded_packed:
+                spare['tau'] = ring_loc(krotov_iteration)['tau']
+                spare['phiT'] = ring_loc(krotov_iteration)['phiT']
+            else:
+                spare['tau'] = pv['tau']
+                spare['phiT'] = ring_phiT(krotov_iteration)
             if info_hook is not None:
                 eng.X = ring_X(krotov_iteration)
         spare_phiT = spare['phiT']
@@ -636,6 +678,8 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                 ran_fused = True
                 launch_epoch = eng.epoch
                 if packed is not None:
+                    if sharded_packed:
+                        gather_into_packed(krotov_iteration)
                     packed.mark(ri, eng)
             except KqError as exc:
                 if exc.status != -3:     # KQ_ERR_UNSUPPORTED
@@ -661,6 +705,10 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
             if chi_kind is None:
                 pass    # chi was uploaded by chi_from_host above
             new_phiT, new_tau = sweep_iteration()
+            if sharded_packed:
+                if new_phiT is not spare_phiT:
+                    spare_phiT.copy_(new_phiT)
+                gather_into_packed(krotov_iteration)
         spare['phiT'] = phiT if phiT is not None else eng.new_states()
         if has_targets:
             spare['tau'] = tau_t if tau_t is not None else torch.empty(
@@ -709,13 +757,19 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     eng.g_a = pvm['g_a']
                     if info_hook is not None:
                         eng.X = ring_X(m)
-                    phiT_m = ring_phiT(m)
-                    tau_m = pvm['tau'] if has_targets else None
+                    if sharded_packed:
+                        phiT_m = ring_loc(m)['phiT']
+                        tau_m = ring_loc(m)['tau'] if has_targets else None
+                    else:
+                        phiT_m = ring_phiT(m)
+                        tau_m = pvm['tau'] if has_targets else None
                     eng.krotov_iteration(
                         chi_kind, last['opt'], pvm['pulses'], last['phiT'],
                         last['tau'], phiT_m, tau_m,
                         store_X=info_hook is not None,
                         prev_guess_t=last['guess'], diag_t=pvm['diag'])
+                    if sharded_packed:
+                        gather_into_packed(m)
                     packed.mark(m % 3, eng)
                     last = dict(iteration=m, guess=last['opt'],
                                 opt=pvm['pulses'], phiT=phiT_m, tau=tau_m,
@@ -723,8 +777,14 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     ahead.append(last)
             optimized_pulses = [fetched[0][l].copy() for l in range(L)]
             g_a_integrals[:] = fetched[1][:L]
-            tau_vals = fetched[2].copy() if tau_t is not None \
-                else np.array([None] * K)
+            phi_host = None
+            if sharded_packed:
+                tau_all, phi_host = split_gathered(fetched[2])
+                tau_vals = tau_all if tau_t is not None \
+                    else np.array([None] * K)
+            else:
+                tau_vals = fetched[2].copy() if tau_t is not None \
+                    else np.array([None] * K)
             st = int(fetched[3][0])
         else:
             optimized_pulses = pulses_to_host(opt_t)   # synchronises
@@ -734,7 +794,13 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         if st != 0:
             raise RuntimeError("sweep kernel reported exchange failure %d"
                                % st)
-        fw_states_T = lazy_states(phiT)
+        if packed is not None and sharded_packed:
+            # the final states of all ranks came with the packed copy
+            fw_states_T = _LazyFinalStates(
+                lambda ph=phi_host: [cp.unvec(ph[k].copy(), templates[k])
+                                     for k in range(K)], K)
+        else:
+            fw_states_T = lazy_states(phiT)
         backward_states = _LazyStates(X_this, cp, eng)
         if second_order:
             forward_states = _LazyStates(Phi1, cp, eng)

@@ -257,6 +257,15 @@ class ShardComm:
                          if local.dtype.is_complex else blk)
         return torch.cat(parts, dim=0)
 
+    def all_gather_flat(self, out, local):
+        """``out[r * n : (r + 1) * n] = local of rank r`` for equally sized
+        complex vectors: one NCCL all-gather on the current stream, no
+        temporaries."""
+        v = self.torch.view_as_real
+        self.dist.all_gather_into_tensor(v(out).view(-1), v(local).view(-1),
+                                         group=self.group)
+        return out
+
     def all_reduce_sum(self, t):
         """In-place sum over ranks of a real or complex tensor."""
         v = self.torch.view_as_real(t) if t.dtype.is_complex else t

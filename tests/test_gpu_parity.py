@@ -28,6 +28,19 @@ def krotov():
     return krotov_b200
 
 
+@pytest.fixture(autouse=True, params=['dpoly_auto', 'dpoly_off'])
+def dpoly_mode(request, krotov):
+    """Every test runs twice: with the delta-polynomial update sweep
+    (csrc/kq_dpoly.cuh) where the library prefers it (few objectives, N >= 3),
+    and with it switched off, so that the time-parallel fixed-point kernels
+    and the sequential Taylor kernels stay covered for the same problems."""
+    lib = krotov._lib.load()
+    assert lib.kq_set_option(b"dpoly", 0 if request.param == 'dpoly_off'
+                             else 1) == 0
+    yield request.param
+    lib.kq_set_option(b"dpoly", 1)
+
+
 def chi_of(krotov, wl):
     if wl.chi == 'qubit_reset':
         fixed = wl.meta['chi_fixed']
@@ -876,3 +889,118 @@ def test_fused_iteration_update_history_hint(krotov, hooked):
     assert runs[0].fused_iterations == runs[1].fused_iterations == 8
     for a, b in zip(runs[0].all_pulses, runs[1].all_pulses):
         assert rel(a, b) < 1e-13
+
+
+# ---------------------------------------------------------------------------
+# Delta-polynomial update sweep (csrc/kq_dpoly.cuh)
+
+def test_dpoly_sweep_is_used_and_falls_back_in_stream(krotov, golden,
+                                                      dpoly_mode):
+    """C5 (Liouville N=16) and the transmon N=5: after the first iteration
+    (a-priori bound on the update -> possibly the sequential kernels) the
+    delta-polynomial sweep does the update; when a hook makes the update ten
+    times larger than the series was built for, the sweep notices and the
+    sequential kernels queued behind it take over -- same pulses either way."""
+    if dpoly_mode == 'dpoly_off':
+        pytest.skip("needs the delta-polynomial sweep")
+    g = golden('C5_nt500_qobj')
+    wl = krotov.workloads.dissipative_qubit_reset(nt=500)
+    res, rec = run_gpu(krotov, wl, 3)
+    check_against_golden(rec, g, 3)
+    assert res.fused_iterations == 3
+    assert res.sequential_fallback is False     # iteration 3: the fast sweep
+    # lambda_a divided by 10 after iteration 2: the update of iteration 3 is
+    # ~10x the one before, beyond the 2.5x margin of the series
+    from oracle import krotov_oracle as orc
+    wl = krotov.workloads.transmon_xgate(nstates=2, nt=1000)
+    low = wl.lowered()
+
+    def shrink(**kw):
+        if kw['iteration'] == 2:
+            kw['lambda_vals'][0] /= 10.0
+
+    res = krotov.optimize_pulses(
+        wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=4,
+        modify_params_after_iter=shrink, store_all_pulses=True)
+    rec = orc.optimize(
+        low['terms'], low['psi0'], low['targets'], low['pulses'],
+        low['shapes'], low['lambdas'], low['tlist'], orc.chis_re, iter_stop=4,
+        lambda_schedule=lambda it: [low['lambdas'][0] / 10.0] if it >= 2
+        else None)
+    for it in (1, 2, 3, 4):
+        assert rel(res.all_pulses[it],
+                   rec[it]['optimized_pulses']) < PULSE_RTOL, it
+    assert res.sequential_fallback is False     # iteration 4 adapted again
+
+
+@pytest.mark.parametrize('case', ['complex_hilbert', 'liouville_n9',
+                                  'undriven_objective'])
+def test_dpoly_sweep_variants_vs_oracle(krotov, case, dpoly_mode):
+    """Complex (non-real) Hamiltonians, a Liouvillian with N = 9 (three
+    columns per lane group, padded) and an ensemble in which one objective
+    does not contain the control, against the numpy oracle."""
+    rng = np.random.default_rng(7)
+    T, nt = 4.0, 160
+    tlist = np.linspace(0, T, nt)
+    guess = lambda t, args: 0.3 * krotov.shapes.flattop(  # noqa: E731
+        t, 0, T, 0.4, func='blackman')
+    S = lambda t: krotov.shapes.flattop(t, 0, T, 0.4, func='sinsq')  # noqa
+    opts = {guess: dict(lambda_a=0.8, update_shape=S)}
+
+    def herm(n, scale):
+        a = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
+        return scale * (a + a.conj().T) / 2
+
+    is_super = False
+    if case == 'complex_hilbert':
+        n = 6
+        H0, H1 = herm(n, 1.0), herm(n, 0.7)
+        objs = []
+        for k in range(3):
+            psi = rng.normal(size=(n, 1)) + 1j * rng.normal(size=(n, 1))
+            tgt = rng.normal(size=(n, 1)) + 1j * rng.normal(size=(n, 1))
+            objs.append(krotov.Objective(
+                initial_state=psi / np.linalg.norm(psi),
+                target=tgt / np.linalg.norm(tgt),
+                H=[H0 + 0.1 * k * np.eye(n), [H1, guess]]))
+    elif case == 'liouville_n9':
+        n, is_super = 3, True
+        H0, H1 = herm(n, 1.0), herm(n, 0.5)
+        c = 0.3 * (rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n)))
+        L = krotov.objectives.liouvillian([H0, [H1, guess]], [c])
+        rho = np.diag([0.6, 0.3, 0.1]).astype(complex)
+        tgt = np.diag([0.0, 0.0, 1.0]).astype(complex)
+        objs = [krotov.Objective(initial_state=rho, target=tgt, H=L)]
+    else:
+        n = 3
+        H0, H1 = herm(n, 1.0), herm(n, 0.7)
+        e0 = np.eye(n, dtype=complex)[:, [0]]
+        e1 = np.eye(n, dtype=complex)[:, [1]]
+        objs = [krotov.Objective(initial_state=e0, target=e1,
+                                 H=[H0, [H1, guess]]),
+                krotov.Objective(initial_state=e1, target=e0,
+                                 H=[H0 + 0.2 * H1]),
+                krotov.Objective(initial_state=e0, target=e1,
+                                 H=[0.9 * H0, [H1, guess]])]
+    res = krotov.optimize_pulses(
+        objs, opts, tlist, propagator=krotov.propagators.expm,
+        chi_constructor=krotov.functionals.chis_re, iter_stop=3,
+        store_all_pulses=True)
+    if case == 'undriven_objective':
+        from oracle import krotov_oracle as orc
+        from krotov_b200.compiler import initialize_controls
+        (_, _, pulses, _, lam, shp) = initialize_controls(objs, opts, tlist)
+        terms = [[(np.asarray(o.H[0], dtype=complex), -1)] + (
+            [(np.asarray(o.H[1][0], dtype=complex), 0)]
+            if len(o.H) > 1 else []) for o in objs]
+        rec = orc.optimize(
+            terms, [o.initial_state.ravel() for o in objs],
+            [o.target.ravel() for o in objs], pulses, shp, lam, tlist,
+            orc.chis_re, iter_stop=3)
+        want = [r['optimized_pulses'] for r in rec]
+    else:
+        want = _oracle_pulses(objs, opts, tlist, 3, is_super=is_super)
+    for it in (1, 2, 3):
+        assert rel(res.all_pulses[it], want[it]) < PULSE_RTOL, (case, it)

@@ -42,6 +42,24 @@ def _worker(rank, world, port, K, out):
         assert torch.equal(got, cfull)
         got = comm.all_gather_rows(full[lo:hi, 0].clone(), K)
         assert torch.equal(got, full[:, 0])
+        # equally sized padded blocks gathered straight into a byte buffer
+        # (the packed results of a hooked, sharded iteration)
+        kmax = -(-K // world)
+        n = kmax * 4
+        loc = torch.zeros(n, dtype=torch.complex128)
+        loc[:(hi - lo) * 3] = cfull[lo:hi].reshape(-1)
+        loc[kmax * 3:kmax * 3 + (hi - lo)] = cfull[lo:hi, 0] * 2
+        raw = torch.zeros(world * n * 16 + 32, dtype=torch.uint8)
+        region = raw[16:16 + world * n * 16].view(torch.complex128)
+        comm.all_gather_flat(region, loc)
+        G = region.numpy().reshape(world, n)
+        rows, taus = [], []
+        for r in range(world):
+            a, b = shard_bounds(K, world, r)
+            rows.append(G[r, :kmax * 3].reshape(kmax, 3)[:b - a])
+            taus.append(G[r, kmax * 3:kmax * 3 + (b - a)])
+        assert np.array_equal(np.concatenate(rows), cfull.numpy())
+        assert np.array_equal(np.concatenate(taus), 2 * cfull[:, 0].numpy())
         t = torch.tensor([complex(rank + 1, -rank)], dtype=torch.complex128)
         comm.all_reduce_sum(t)
         want = sum(complex(r + 1, -r) for r in range(world))
