@@ -125,13 +125,16 @@ const char* kq_last_error(void);
  * of cudaLaunchCooperativeKernel (co-residency is still checked against the
  * occupancy limit; the kernels wait for the preceding launches before they
  * touch memory).
- * "dpoly" (default 1): the delta-polynomial update sweep (csrc/kq_dpoly.cuh: few
+ * "dpoly" (default 1): the delta-polynomial Krotov iteration (csrc/kq_dpoly.cuh: few
  * objectives, one control, first order; per time step ONE small matrix-vector product
- * with a propagator that is a polynomial in this iteration's pulse update) is used
- * where kq_problem.update_sweep / the state dimension ask for it; 0: never; 2:
- * wherever it fits.  The sequential Taylor kernels are always queued behind it as an
- * in-stream conditional fall-back (taken when the update exceeds the bound the
- * polynomials were built for).
+ * with a step propagator that is a polynomial in the deviation of the pulse from an
+ * anchor pulse; the polynomials are kept in the workspace and rebuilt only when the
+ * pulse has drifted out of their radius; the backward sweep is a time-parallel product
+ * of the same polynomials) is used where kq_problem.update_sweep / the state dimension
+ * ask for it; 0: never; 2: wherever it fits.  kq_sweep_forward_update queues the
+ * sequential Taylor kernels behind it as an in-stream conditional fall-back;
+ * kq_krotov_iteration reports a declined iteration through diag_out / the status words
+ * (the caller repeats it with the sweep calls).
  * "time_parallel" (default 1): propagation
  * sweeps under known pulses (kq_propagate_forward, kq_sweep_backward*) are cut
  * into time segments that run concurrently (segment propagators -> boundary
@@ -159,6 +162,10 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace,
 /* Bytes of zero-initialised device workspace kq_sweep_forward_update needs
  * (status word + cross-CTA exchange slots). */
 size_t kq_workspace_bytes(const kq_problem* p);
+/* Diagnostics: byte offset in the workspace of the 64-byte header of the
+ * delta-polynomial iteration {int32 J, m, rebuild, usable, anchor_epoch, valid_epoch,
+ * builds, reuses; double radius, last_max, anchor_max, pad}. */
+size_t kq_dpoly_header_offset(const kq_problem* p);
 size_t kq_comm_slot_bytes(const kq_problem* p);
 
 /* Forward propagation over the whole grid under `pulses`:

@@ -74,6 +74,7 @@ _SIGNATURES = {
                                        ctypes.c_uint32, ctypes.c_void_p,
                                        ctypes.c_void_p]),
     'kq_workspace_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
+    'kq_dpoly_header_offset': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
     'kq_comm_slot_bytes': (ctypes.c_size_t, [ctypes.POINTER(KqProblem)]),
     'kq_propagate_forward': (ctypes.c_int, [
         ctypes.POINTER(KqProblem), ctypes.c_void_p, ctypes.c_void_p,

@@ -301,7 +301,7 @@ size_t dpoly_header_offset(const kq_problem* p) {
   return (bytes + 63) / 64 * 64;
 }
 
-// ---- delta-polynomial update sweep (kq_dpoly.cuh): few objectives, one control ----
+// ---- delta-polynomial Krotov iteration (kq_dpoly.cuh): few objectives, one control ----
 struct DpPlan {
   KqDpoly d;
   KqDpolyGeom g;
@@ -309,20 +309,38 @@ struct DpPlan {
 bool dpoly_plan(const kq_problem* p, DpPlan& dp) {
   const int K = p->K, N = p->N;
   if (p->M != 2 || p->L != 1 || N < 2 || N > 16 || p->NT < 2) return false;
-  int Q = 1;
-  while (Q < N && Q < 8) Q <<= 1;
-  while (Q > 1 && (long long)K * (N + 1) * Q > KQ_DP_MAXLANES) Q >>= 1;
-  const int Npad = round_up(N, Q), C = Npad / Q;
-  const long long NL = (long long)K * (N + 1) * Q;   // rows of E plus the zeta row
-  if (C > KQ_DP_CMAX || NL > KQ_DP_MAXLANES) return false;
+  int Npad = 2;
+  while (Npad < N) Npad <<= 1;
+  const int NR = N + 1;
+  // lanes per row Q (C = Npad / Q columns per lane): the largest Q that keeps all lanes in
+  // ONE warp (the chain then runs on shuffles alone), else the largest that fits the CTA
+  int Q = 0;
+  for (int q = std::min(Npad, 8); q >= 1; q >>= 1)
+    if (Npad / q <= KQ_DP_CMAX && (long long)K * NR * q <= 32) {
+      Q = q;
+      break;
+    }
+  if (!Q)
+    for (int q = std::min(Npad, 8); q >= 1; q >>= 1)
+      if (Npad / q <= KQ_DP_CMAX && (long long)K * NR * q <= KQ_DP_MAXLANES) {
+        Q = q;
+        break;
+      }
+  if (!Q) return false;
+  int C = Npad / Q;
+  if (C == 3) return false;   // cannot happen (powers of two)
+  const long long NL = (long long)K * NR * Q;   // rows of E plus the zeta row
   const size_t rec_stride = (size_t)C * NL * ((KQ_DP_JMAX + 1) | 1) + 2;
-  const size_t fixed = 2 * KQ_DP_RINGMAX * 8 + (size_t)((2 * K + 1) & ~1) * 8 + (size_t)((K * N + 1) & ~1) * 8 +
-                       (size_t)2 * K * Npad * 16;
-  if (fixed + 2 * rec_stride * 16 > kSmemBudget) return false;
-  // ring capacity: up to 16 records of the highest degree, within the shared-memory budget
-  const size_t ring = std::min<size_t>((size_t)KQ_DP_RINGMAX * rec_stride, (kSmemBudget - fixed) / 16);
-  // build kernel: one thread per matrix element, polynomial double-buffered + conj(eta)
-  const size_t per = ((size_t)2 * (KQ_DP_JMAX + 1) * N * N + N) * 16;
+  // sweep kernel: barriers | exchange buffers [2][XS] | first overlap | ring of record chunks
+  const size_t nlp = (size_t)round_up((int)NL, 32);
+  const size_t XS = (size_t)2 * K * Npad + 2 * K + 2 * nlp;
+  const size_t fixed = 2 * KQ_DP_RINGMAX * 8 + 2 * XS * 8 + (size_t)((K * N + 1) & ~1) * 8;
+  const size_t budget = 220 * 1024;
+  // two stages of two records of the highest degree must fit
+  if (fixed + 4 * rec_stride * 16 > budget) return false;
+  const size_t ring = (budget - fixed) / 16;
+  // build kernel: one thread per matrix element, polynomial double-buffered
+  const size_t per = (size_t)2 * (KQ_DP_JMAX + 1) * N * N * 16;
   const int TPC = std::max(1, std::min(256 / (N * N), (int)(100 * 1024 / per)));
   if ((size_t)TPC * per > kSmemBudget) return false;
   std::memset(&dp, 0, sizeof dp);
@@ -331,34 +349,75 @@ bool dpoly_plan(const kq_problem* p, DpPlan& dp) {
   dp.d.Q = Q;
   dp.d.C = C;
   dp.d.Npad = Npad;
+  dp.d.R2 = Npad;
   dp.d.TPC = TPC;
   dp.d.ring = (int)ring;
+  // backward sweep: segments of about 0.46 sqrt(NT) steps (the expand kernel chains over
+  // the later segments, then walks through its own)
+  int seg_len = std::max(4, (int)std::ceil(0.46 * std::sqrt((double)p->NT)));
+  while ((p->NT + seg_len - 1) / seg_len > KQ_DP_SEGMAX) ++seg_len;
+  dp.d.seg_len = seg_len;
+  dp.d.nseg = (p->NT + seg_len - 1) / seg_len;
   dp.g.nmax = N <= 4 ? 4 : (N <= 8 ? 8 : 16);
   dp.g.smem_build = (size_t)TPC * per;
   dp.g.smem_sweep = fixed + ring * 16;
   return true;
 }
-// The delta-polynomial sweep is the only fast update sweep for N > 4; for N <= 4 the caller
-// asks for it (kq_problem.update_sweep = 1) when the problem is strongly coupled -- the
-// time-parallel fixed point needs many rounds there.
+// The delta-polynomial iteration is the only fast path for N > 4; for N <= 4 the caller
+// asks for it (kq_problem.update_sweep = 1) when the problem is strongly coupled or has few
+// objectives -- the time-parallel fixed point needs many rounds, or leaves most of the GPU
+// idle, there.
 bool dpoly_preferred(const kq_problem* p) {
   if (g_dpoly == 2) return true;
   return g_dpoly == 1 && (p->N > 4 || p->update_sweep == 1);
 }
-// plan | build | zeta | sweep on `st`; `a` is the argument block of the update sweep
-// (a.X = backward states, a.epoch set).  The caller queues the sequential kernel behind it
-// with cond_epoch = epoch, then launch_dpoly_epilogue.
+// workspace behind the header: anchor pulse | step records (kept between calls)
+size_t dpoly_anchor_bytes(const kq_problem* p) { return ((size_t)p->NT * sizeof(double) + 63) / 64 * 64; }
 size_t dpoly_rec_bytes(const kq_problem* p, const DpPlan& dp) {
-  return ((size_t)p->NT * dp.d.rec_stride * sizeof(cplx) + 255) / 256 * 256;
+  return ((size_t)(p->NT + 2 * KQ_DP_PAD) * dp.d.rec_stride * sizeof(cplx) + 255) / 256 * 256;
 }
-int launch_dpoly(const kq_problem* p, const KqSweepArgs& a, DpPlan& dp, void* workspace, int dev,
-                 cudaStream_t st, void* rec = nullptr) {
-  if (!rec) {
-    int rc = get_scratch(dev, dpoly_rec_bytes(p, dp), &rec, 1);
-    if (rc) return rc;
-  }
-  dp.d.rec = reinterpret_cast<cplx*>(rec);
-  dp.d.hdr = reinterpret_cast<KqDpHeader*>(static_cast<char*>(workspace) + dpoly_header_offset(p));
+size_t dpoly_workspace_bytes(const kq_problem* p) {
+  DpPlan dp;
+  if (!p || p->NT < 1 || !dpoly_plan(p, dp)) return 0;
+  return dpoly_anchor_bytes(p) + dpoly_rec_bytes(p, dp);
+}
+// per-call scratch (device-global, stream-ordered): segment propagators | X | chi | phi(T) |
+// chi norms | tau sum
+struct DpScratch {
+  cplx *segP, *X, *chi, *phiT, *tsum;
+  double* norms;
+};
+int dpoly_scratch(const kq_problem* p, const DpPlan& dp, int dev, DpScratch& s) {
+  const int K = p->K, N = p->N, NT = p->NT;
+  const size_t pb = ((size_t)dp.d.nseg * K * N * N * sizeof(cplx) + 255) / 256 * 256;
+  const size_t xb = ((size_t)(NT + 1) * K * N * sizeof(cplx) + 255) / 256 * 256;
+  const size_t sb = ((size_t)K * N * sizeof(cplx) + 255) / 256 * 256;
+  const size_t nb = ((size_t)K * sizeof(double) + 255) / 256 * 256;
+  void* base = nullptr;
+  int rc = get_scratch(dev, pb + xb + 2 * sb + nb + 256, &base, 1);
+  if (rc) return rc;
+  char* cur = static_cast<char*>(base);
+  s.segP = reinterpret_cast<cplx*>(cur);
+  cur += pb;
+  s.X = reinterpret_cast<cplx*>(cur);
+  cur += xb;
+  s.chi = reinterpret_cast<cplx*>(cur);
+  cur += sb;
+  s.phiT = reinterpret_cast<cplx*>(cur);
+  cur += sb;
+  s.norms = reinterpret_cast<double*>(cur);
+  cur += nb;
+  s.tsum = reinterpret_cast<cplx*>(cur);
+  return KQ_OK;
+}
+// plan | build | (segment products) | expand | sweep on `st`.  The caller has set dp.d.chain,
+// X, chi, norms, segP; `a` is the argument block of the update sweep (a.epoch set).
+int launch_dpoly(const kq_problem* p, const KqSweepArgs& a, DpPlan& dp, void* workspace,
+                 cudaStream_t st) {
+  char* w = static_cast<char*>(workspace) + dpoly_header_offset(p);
+  dp.d.hdr = reinterpret_cast<KqDpHeader*>(w);
+  dp.d.anchor = reinterpret_cast<double*>(w + 64);
+  dp.d.rec = reinterpret_cast<cplx*>(w + 64 + dpoly_anchor_bytes(p));
   return kq_launch_dpoly(a, dp.d, dp.g, st);
 }
 
@@ -715,97 +774,33 @@ __global__ void k_chi_boundary(int K, int N, int kind, int K_total, const cplx* 
   }
 }
 
-// sum_j w_j tau_j in a fixed order (chis_sm, functionals.py:225-253); one CTA
-__global__ void __launch_bounds__(256) k_tau_sum(int K, const cplx* __restrict__ tau,
-                                                 const double* __restrict__ weights,
-                                                 cplx* __restrict__ out) {
-  __shared__ double sx[8], sy[8];
-  double x = 0.0, y = 0.0;
-  for (int j = threadIdx.x; j < K; j += 256) {
-    const double w = weights ? weights[j] : 1.0;
-    x = fma(w, tau[j].x, x);
-    y = fma(w, tau[j].y, y);
-  }
-  x = warp_allreduce_sum(x);
-  y = warp_allreduce_sum(y);
-  if ((threadIdx.x & 31) == 0) {
-    sx[threadIdx.x >> 5] = x;
-    sy[threadIdx.x >> 5] = y;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) {
-      x += sx[w];
-      y += sy[w];
-    }
-    out[0] = c_make(x, y);
-  }
-}
-
-// One Krotov iteration as a sequence of launches for problems the delta-polynomial sweep
-// serves (few objectives, one control, first order): chi boundary | backward sweep |
-// plan, build, zeta, sweep | conditional sequential kernel | epilogue | tau.
+// One Krotov iteration as a sequence of launches for problems the delta-polynomial family
+// serves (few objectives, one control, first order): plan (chi boundary) | build | segment
+// products | expand | sweep | epilogue (tau).  A declined or failed iteration is reported
+// like a fixed point that did not converge; the caller repeats it with the sweep calls.
 int composite_iteration(const kq_problem* p, DpPlan& dp, KqSweepArgs a, int chi_kind,
-                        int32_t K_total, const double* guess_pulses, void* workspace, int dev,
-                        cudaStream_t st) {
-  const int K = p->K, N = p->N, NT = p->NT;
-  // scratch behind the step records: X | chi | phi(T) | chi norms | tau sum
-  const size_t recb = dpoly_rec_bytes(p, dp);
-  const size_t xb = ((size_t)(NT + 1) * K * N * sizeof(cplx) + 255) / 256 * 256;
-  const size_t sb = ((size_t)K * N * sizeof(cplx) + 255) / 256 * 256;
-  const size_t nb = ((size_t)K * sizeof(double) + 255) / 256 * 256;
-  void* base = nullptr;
-  int rc = get_scratch(dev, recb + xb + 2 * sb + nb + 256, &base, 1);
+                        void* workspace, int dev, cudaStream_t st) {
+  DpScratch s;
+  int rc = dpoly_scratch(p, dp, dev, s);
   if (rc) return rc;
-  char* cur = static_cast<char*>(base) + recb;
-  cplx* X = a.Xout ? a.Xout : reinterpret_cast<cplx*>(cur);
-  cur += xb;
-  cplx* chi = a.chi_out ? a.chi_out : reinterpret_cast<cplx*>(cur);
-  cur += sb;
-  cplx* phiT = a.stateT ? a.stateT : reinterpret_cast<cplx*>(cur);
-  cur += sb;
-  double* norms = a.chi_norms_out ? a.chi_norms_out : reinterpret_cast<double*>(cur);
-  cur += nb;
-  cplx* tsum = reinterpret_cast<cplx*>(cur);
+  dp.d.chain = 1;
+  dp.d.segP = s.segP;
+  dp.d.X = a.Xout ? a.Xout : s.X;
+  dp.d.tsum = s.tsum;
   if (chi_kind >= 0) {
-    if (chi_kind == KQ_CHI_SM) {
-      k_tau_sum<<<1, 256, 0, st>>>(K, a.tau_in, a.weights, tsum);
-      KQ_CUDA(cudaGetLastError());
-    }
-    const int bt = 128;
-    k_chi_boundary<<<(K + bt - 1) / bt, bt, 0, st>>>(K, N, chi_kind, K_total, a.phiT_in, a.targets,
-                                                     a.tau_in, a.weights, tsum, chi, norms);
-    KQ_CUDA(cudaGetLastError());
+    dp.d.chi = a.chi_out ? a.chi_out : s.chi;
+    dp.d.norms = a.chi_norms_out ? a.chi_norms_out : s.norms;
   } else {
-    chi = const_cast<cplx*>(a.chiT);
-    norms = const_cast<double*>(a.chi_norms);
+    dp.d.chi = const_cast<cplx*>(a.chiT);
+    dp.d.norms = const_cast<double*>(a.chi_norms);
   }
-  rc = run_prop(p, true, guess_pulses, reinterpret_cast<const kq_c128*>(chi), nullptr,
-                reinterpret_cast<kq_c128*>(X), st, 0, -1);
-  if (rc) return rc;
-  a.X = X;
-  a.chi_norms = norms;
-  a.stateT = phiT;
+  if (!a.stateT) a.stateT = s.phiT;
+  a.X = dp.d.X;
+  a.chi_norms = dp.d.norms;
   a.pic_bw = 0;
-  rc = launch_dpoly(p, a, dp, workspace, dev, st, base);
+  rc = launch_dpoly(p, a, dp, workspace, st);
   if (rc) return rc;
-  a.cond_epoch = a.epoch;
-  Plan pl;
-  rc = make_plan(p, true, false, g_dev[dev].sms, pl);
-  if (rc) return rc;
-  if (pl.grid > kMaxBlocks) return fail(KQ_ERR_UNSUPPORTED, "too many CTAs (%d)", pl.grid);
-  a.slots = reinterpret_cast<KqSlot*>(static_cast<char*>(workspace) + kStatusBytes);
-  a.tag_base = a.epoch * (uint32_t)(NT + 1);
-  rc = launch_sequential_update(p, a, pl, p->is_super ? 2 : 0, false, st);
-  if (rc) return rc;
-  rc = kq_launch_dpoly_epilogue(a, dp.d, st);
-  if (rc) return rc;
-  if (a.tau_out && a.targets) {
-    const int bt = 128;
-    k_overlaps<<<(K + bt - 1) / bt, bt, 0, st>>>(K, N, a.targets, phiT, a.tau_out);
-    KQ_CUDA(cudaGetLastError());
-  }
-  return KQ_OK;
+  return kq_launch_dpoly_epilogue(a, dp.d, 0, st);
 }
 
 }  // namespace
@@ -914,8 +909,11 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* st
 }
 
 size_t kq_workspace_bytes(const kq_problem* p) {
-  return dpoly_header_offset(p) + 64;   // ... | header of the delta-polynomial sweep
+  // ... | header of the delta-polynomial iteration | its anchor pulse and step records
+  return dpoly_header_offset(p) + 64 + dpoly_workspace_bytes(p);
 }
+
+size_t kq_dpoly_header_offset(const kq_problem* p) { return dpoly_header_offset(p); }
 
 int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
             int32_t* smem_bytes) {
@@ -1029,7 +1027,18 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   DpPlan dp;
   const bool use_dpoly = !second && a.world == 1 && dpoly_preferred(p) && dpoly_plan(p, dp);
   if (use_dpoly) {
-    rc = launch_dpoly(p, a, dp, workspace, dev, st);
+    // backward states from the caller's X; chi norms as given
+    DpScratch s;
+    rc = dpoly_scratch(p, dp, dev, s);
+    if (rc) return rc;
+    dp.d.chain = 0;
+    dp.d.segP = s.segP;
+    dp.d.X = const_cast<cplx*>(a.X);
+    dp.d.chi = nullptr;
+    dp.d.norms = const_cast<double*>(chi_norms);
+    dp.d.tsum = s.tsum;
+    a.chi_kind = -1;
+    rc = launch_dpoly(p, a, dp, workspace, st);
     if (rc) return rc;
     a.cond_epoch = a.epoch;
   }
@@ -1089,7 +1098,7 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
     rc = launch_sequential_update(p, a, pl, fsel, second, st);
     if (rc) return rc;
   }
-  if (use_dpoly) return kq_launch_dpoly_epilogue(a, dp.d, st);
+  if (use_dpoly) return kq_launch_dpoly_epilogue(a, dp.d, 1, st);
   return KQ_OK;
 }
 
@@ -1172,7 +1181,7 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   if (composite) {
     a.epoch = epoch ? epoch : 1u;
     a.status = reinterpret_cast<int*>(workspace);
-    return composite_iteration(p, dp, a, chi_kind, K_total, guess_pulses, workspace, dev,
+    return composite_iteration(p, dp, a, chi_kind, workspace, dev,
                                static_cast<cudaStream_t>(stream));
   }
   return launch_picard(p, a, pp, workspace, epoch, second, static_cast<cudaStream_t>(stream));

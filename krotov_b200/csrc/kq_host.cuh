@@ -175,7 +175,8 @@ struct KqDpolyGeom {
   size_t smem_build, smem_sweep;
 };
 int kq_launch_dpoly(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom& g, cudaStream_t st);
-int kq_launch_dpoly_epilogue(const KqSweepArgs& a, const KqDpoly& d, cudaStream_t st);
+int kq_launch_dpoly_epilogue(const KqSweepArgs& a, const KqDpoly& d, int fallback_in_stream,
+                             cudaStream_t st);
 int kq_launch_warp0(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,
                     cudaStream_t st);
 int kq_launch_warp8(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second, bool update,

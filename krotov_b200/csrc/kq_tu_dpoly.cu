@@ -1,48 +1,73 @@
-// Delta-polynomial update sweep (kq_dpoly.cuh): launches.
+// Delta-polynomial Krotov iteration (kq_dpoly.cuh): launches.
 #include "kq_host.cuh"
 #include "kq_dpoly.cuh"
 
 KQ_DEFINE_TABLES_UPLOAD(kq_tables_upload_dpoly)
 
 namespace {
+int round32(int v) { return (v + 31) / 32 * 32; }
+
 template <int NMAX>
-int build_and_zeta(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom& g, cudaStream_t st) {
+int build_and_backward(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom& g,
+                       cudaStream_t st) {
   void* params[] = {(void*)&a, (void*)&d};
   KqPlan pl = {};
-  pl.grid = (a.NT + d.TPC - 1) / d.TPC;
+  pl.grid = (a.NT + 2 * KQ_DP_PAD + d.TPC - 1) / d.TPC;
   pl.grid_y = a.K;
   pl.block = d.TPC * a.N * a.N;
   pl.smem = g.smem_build;
-  return launch(k_dpoly_build<NMAX>, pl, false, st, params);
+  int rc = launch(k_dp_build<NMAX>, pl, false, st, params);
+  if (rc) return rc;
+  const int NN = a.N * a.N;
+  if (d.chain) {
+    k_dp_segprod<<<dim3(d.nseg, a.K), round32(NN), (size_t)3 * NN * sizeof(cplx), st>>>(a, d);
+    KQ_CUDA(cudaGetLastError());
+  }
+  k_dp_expand<NMAX><<<dim3(d.nseg, a.K), round32(a.N * d.R2), (size_t)3 * a.N * sizeof(cplx),
+                      st>>>(a, d);
+  KQ_CUDA(cudaGetLastError());
+  return KQ_OK;
+}
+
+template <bool QONE, bool ONEWARP, int MAXT, bool PF>
+int sweep_c(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom& g, cudaStream_t st) {
+  void* params[] = {(void*)&a, (void*)&d};
+  KqPlan pl = {};
+  pl.grid = 1;
+  pl.block = round32(d.NL) + 32;   // consumers + the producer warp
+  pl.smem = g.smem_sweep;
+  switch (d.C) {
+    case 1: return launch(k_dp_sweep<1, QONE, ONEWARP, MAXT, PF>, pl, false, st, params);
+    case 2: return launch(k_dp_sweep<2, QONE, ONEWARP, MAXT, PF>, pl, false, st, params);
+    default: return launch(k_dp_sweep<4, QONE, ONEWARP, MAXT, PF>, pl, false, st, params);
+  }
+}
+template <bool ONEWARP, int MAXT, bool PF>
+int sweep(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom& g, cudaStream_t st) {
+  return d.Q == 1 ? sweep_c<true, ONEWARP, MAXT, PF>(a, d, g, st)
+                  : sweep_c<false, ONEWARP, MAXT, PF>(a, d, g, st);
 }
 }  // namespace
 
 int kq_launch_dpoly(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom& g,
                     cudaStream_t st) {
-  k_dpoly_plan<<<1, 256, 0, st>>>(a, d);
+  k_dp_plan<<<1, 256, 0, st>>>(a, d);
   KQ_CUDA(cudaGetLastError());
   int rc;
   switch (g.nmax) {
-    case 4: rc = build_and_zeta<4>(a, d, g, st); break;
-    case 8: rc = build_and_zeta<8>(a, d, g, st); break;
-    default: rc = build_and_zeta<16>(a, d, g, st); break;
+    case 4: rc = build_and_backward<4>(a, d, g, st); break;
+    case 8: rc = build_and_backward<8>(a, d, g, st); break;
+    default: rc = build_and_backward<16>(a, d, g, st); break;
   }
   if (rc) return rc;
-  void* params[] = {(void*)&a, (void*)&d};
-  KqPlan pl = {};
-  pl.grid = 1;
-  pl.block = (d.NL + 31) / 32 * 32 + 32;   // consumers + the producer warp
-  pl.smem = g.smem_sweep;
-  switch (d.C) {
-    case 1: return launch(k_dpoly_sweep<1>, pl, false, st, params);
-    case 2: return launch(k_dpoly_sweep<2>, pl, false, st, params);
-    case 3: return launch(k_dpoly_sweep<3>, pl, false, st, params);
-    default: return launch(k_dpoly_sweep<4>, pl, false, st, params);
-  }
+  if (d.NL <= 32) return sweep<true, 64, true>(a, d, g, st);
+  if (d.NL <= 224) return sweep<false, 256, true>(a, d, g, st);
+  return sweep<false, KQ_DP_MAXLANES + 32, false>(a, d, g, st);
 }
 
-int kq_launch_dpoly_epilogue(const KqSweepArgs& a, const KqDpoly& d, cudaStream_t st) {
-  k_dpoly_epilogue<<<1, 256, 0, st>>>(a, d);
+int kq_launch_dpoly_epilogue(const KqSweepArgs& a, const KqDpoly& d, int fallback_in_stream,
+                             cudaStream_t st) {
+  k_dp_epilogue<<<1, 256, 0, st>>>(a, d, fallback_in_stream);
   KQ_CUDA(cudaGetLastError());
   return KQ_OK;
 }
