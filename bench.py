@@ -716,6 +716,8 @@ def run_ours(args):
     lib = krotov._lib.load()
     if args.picard is not None:
         krotov._lib.check(lib.kq_set_option(b"picard", args.picard))
+    if args.dpoly is not None:
+        krotov._lib.check(lib.kq_set_option(b"dpoly", args.dpoly))
     if args.picard_history is not None:
         krotov._lib.check(lib.kq_set_option(b"picard_history",
                                             args.picard_history))
@@ -1000,6 +1002,9 @@ def main():
     ap.add_argument('--picard', type=int, default=None, choices=[0, 1, 2],
                     help='time-parallel fused sweep: 0 off (sequential '
                          'kernel), 1 on (library default)')
+    ap.add_argument('--dpoly', type=int, default=None, choices=[0, 1, 2],
+                    help="delta-polynomial iteration: 0 never, 1 where the "
+                    "engine asks for it (library default), 2 wherever it fits")
     ap.add_argument('--picard-history', type=int, default=None,
                     choices=[0, 1], help='update-history first iterate of '
                     'the fixed-point kernel (library default: on)')

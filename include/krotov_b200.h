@@ -162,9 +162,9 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace,
 /* Bytes of zero-initialised device workspace kq_sweep_forward_update needs
  * (status word + cross-CTA exchange slots). */
 size_t kq_workspace_bytes(const kq_problem* p);
-/* Diagnostics: byte offset in the workspace of the 64-byte header of the
+/* Diagnostics: byte offset in the workspace of the header (128 bytes reserved) of the
  * delta-polynomial iteration {int32 J, m, rebuild, usable, anchor_epoch, valid_epoch,
- * builds, reuses; double radius, last_max, anchor_max, pad}. */
+ * builds, reuses; double radius, last_max, anchor_max, dtmax, o0, o1}. */
 size_t kq_dpoly_header_offset(const kq_problem* p);
 size_t kq_comm_slot_bytes(const kq_problem* p);
 

@@ -350,6 +350,9 @@ bool dpoly_plan(const kq_problem* p, DpPlan& dp) {
   dp.d.C = C;
   dp.d.Npad = Npad;
   dp.d.R2 = Npad;
+  dp.d.chain_bs = std::max(1, std::min(32, 1024 / (N * N)));
+  // one record of the highest degree must fit a staging buffer; small ones: about 24 KB
+  dp.d.estage_cap = std::max((KQ_DP_JMAX + 1) * N * N, 1536);
   dp.d.TPC = TPC;
   dp.d.ring = (int)ring;
   // backward sweep: segments of about 0.46 sqrt(NT) steps (the expand kernel chains over
@@ -416,8 +419,9 @@ int launch_dpoly(const kq_problem* p, const KqSweepArgs& a, DpPlan& dp, void* wo
                  cudaStream_t st) {
   char* w = static_cast<char*>(workspace) + dpoly_header_offset(p);
   dp.d.hdr = reinterpret_cast<KqDpHeader*>(w);
-  dp.d.anchor = reinterpret_cast<double*>(w + 64);
-  dp.d.rec = reinterpret_cast<cplx*>(w + 64 + dpoly_anchor_bytes(p));
+  static_assert(sizeof(KqDpHeader) <= 128, "header area");
+  dp.d.anchor = reinterpret_cast<double*>(w + 128);
+  dp.d.rec = reinterpret_cast<cplx*>(w + 128 + dpoly_anchor_bytes(p));
   return kq_launch_dpoly(a, dp.d, dp.g, st);
 }
 
@@ -910,7 +914,7 @@ int kq_comm_barrier(const kq_comm* comm, uint32_t tag, void* workspace, void* st
 
 size_t kq_workspace_bytes(const kq_problem* p) {
   // ... | header of the delta-polynomial iteration | its anchor pulse and step records
-  return dpoly_header_offset(p) + 64 + dpoly_workspace_bytes(p);
+  return dpoly_header_offset(p) + 128 + dpoly_workspace_bytes(p);
 }
 
 size_t kq_dpoly_header_offset(const kq_problem* p) { return dpoly_header_offset(p); }

@@ -137,43 +137,65 @@ __global__ void __launch_bounds__(256) k_dp_plan(const KqSweepArgs a, const KqDp
   double dtmax = 0.0, gmax = 0.0, slmax = 0.0, o0 = 0.0, o1 = 0.0, Dmax = 0.0;
   const double lam = a.lambda_a[0];
   const bool have_anchor = h->anchor_epoch != 0;
+  const bool have_last =
+      h->valid_epoch != 0 && (uint32_t)h->valid_epoch + 1u == a.epoch && h->last_max >= 0.0;
+  // dt and the operator norms belong to the problem: kept in the header after the first call
+  const bool have_const = h->dtmax > 0.0;
   bool finite = true;
-  for (int n = tid; n < NT; n += 256) {
-    const double g = a.pulses[n];
-    dtmax = fmax(dtmax, fabs(a.dt[n]));
-    gmax = fmax(gmax, fabs(g));
-    slmax = fmax(slmax, fabs(a.shape[n] / lam));
-    if (have_anchor) Dmax = fmax(Dmax, fabs(g - d.anchor[n]));
-    if (!(fabs(g) < 1e300)) finite = false;
+  // four entries per thread in flight (the loop is bound by the latency of its loads)
+  for (int n0 = tid; n0 < NT; n0 += 4 * 256) {
+    double g[4], an[4], dtv[4], sh[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = n0 + u * 256;
+      const bool in = n < NT;
+      g[u] = in ? a.pulses[n] : 0.0;
+      an[u] = (in && have_anchor) ? d.anchor[n] : g[u];
+      dtv[u] = (in && !have_const) ? a.dt[n] : 0.0;
+      sh[u] = (in && !have_last) ? a.shape[n] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dtmax = fmax(dtmax, fabs(dtv[u]));
+      gmax = fmax(gmax, fabs(g[u]));
+      slmax = fmax(slmax, fabs(sh[u] / lam));
+      Dmax = fmax(Dmax, fabs(g[u] - an[u]));
+      if (!(fabs(g[u]) < 1e300)) finite = false;
+    }
   }
   // a-priori bound of |Im sum_k <chi_k| mu |phi_k>| ||chi_k||: sum_k ||chi_k|| ||mu_k||_1 ||phi_k(0)||
-  // (unitary or contractive dynamics)
+  // (unitary or contractive dynamics); only needed while no update has been measured
   double ap = 0.0;
-  for (int k = tid; k < K; k += 256) {
-    const int t2p = a.term2pulse[k * 2 + 1];
-    if (t2p == 0) {
-      o0 = fmax(o0, a.op_norm[k * 2 + 0]);
-      o1 = fmax(o1, a.op_norm[k * 2 + 1]);
-    } else if (t2p == -1) {
-      o0 = fmax(o0, a.op_norm[k * 2 + 0] + a.op_norm[k * 2 + 1]);
-    } else {
-      o0 = fmax(o0, a.op_norm[k * 2 + 0]);
-    }
-    double mun = 0.0;
-    for (int c = 0; c < N; ++c) {
-      double cs = 0.0;
-      for (int r = 0; r < N; ++r) {
-        const cplx m = a.mu[(size_t)k * NN + c * N + r];
-        cs += fabs(m.x) + fabs(m.y);
+  if (!have_const || !have_last) {
+    for (int k = tid; k < K; k += 256) {
+      const int t2p = a.term2pulse[k * 2 + 1];
+      const double n0 = a.op_norm[k * 2 + 0], n1 = a.op_norm[k * 2 + 1];
+      if (t2p == 0) {
+        o0 = fmax(o0, n0);
+        o1 = fmax(o1, n1);
+      } else if (t2p == -1) {
+        o0 = fmax(o0, n0 + n1);
+      } else {
+        o0 = fmax(o0, n0);
       }
-      mun = fmax(mun, cs);
+      if (!have_last) {
+        double mun = 0.0;
+        for (int c = 0; c < N; ++c) {
+          double cs = 0.0;
+          for (int r = 0; r < N; ++r) {
+            const cplx m = a.mu[(size_t)k * NN + c * N + r];
+            cs += fabs(m.x) + fabs(m.y);
+          }
+          mun = fmax(mun, cs);
+        }
+        double pn = 0.0;
+        for (int r = 0; r < N; ++r) {
+          const cplx s = a.state0[(size_t)k * N + r];
+          pn += fabs(s.x) + fabs(s.y);
+        }
+        ap += d.norms[k] * mun * fmax(pn, 1.0);
+      }
     }
-    double pn = 0.0;
-    for (int r = 0; r < N; ++r) {
-      const cplx s = a.state0[(size_t)k * N + r];
-      pn += fabs(s.x) + fabs(s.y);
-    }
-    ap += d.norms[k] * mun * fmax(pn, 1.0);
   }
   double v[6] = {dtmax, gmax, slmax, o0, o1, Dmax};
 #pragma unroll
@@ -188,17 +210,24 @@ __global__ void __launch_bounds__(256) k_dp_plan(const KqSweepArgs a, const KqDp
   for (int j = 0; j < 6; ++j)
     for (int w = 1; w < 8; ++w) red[j][0] = fmax(red[j][0], red[j][w]);
   for (int w = 1; w < 8; ++w) sred[0] += sred[w];
-  dtmax = red[0][0];
   gmax = red[1][0];
   slmax = red[2][0];
-  o0 = red[3][0];
-  o1 = red[4][0];
   Dmax = red[5][0];
+  if (have_const) {
+    dtmax = h->dtmax;
+    o0 = h->o0;
+    o1 = h->o1;
+  } else {
+    dtmax = red[0][0];
+    o0 = red[3][0];
+    o1 = red[4][0];
+    h->dtmax = dtmax;
+    h->o0 = o0;
+    h->o1 = o1;
+  }
   // predicted size of this iteration's update
-  double upd = slmax * sred[0];   // strict a-priori bound
-  const bool have_last =
-      h->valid_epoch != 0 && (uint32_t)h->valid_epoch + 1u == a.epoch && h->last_max >= 0.0;
-  if (have_last) upd = fmin(upd, 2.5 * h->last_max);
+  // (a strict a-priori bound before the first measured update)
+  double upd = have_last ? 2.5 * h->last_max : slmax * sred[0];
   upd = fmax(upd, 1e-9 * fmax(gmax, 1e-3));
   bool ok = all_finite && (upd < 1e300);
   // smallest degree whose radius covers `want`: x^(J+1)/(J+1)! <= 2e-17.  With a measured
@@ -210,12 +239,15 @@ __global__ void __launch_bounds__(256) k_dp_plan(const KqSweepArgs a, const KqDp
   int J = 1;
   double radius = 1e300;
   if (x1 > 0.0) {
-    double fact = 2.0;   // (J+1)!
+    // (2e-17 (J+1)!)^(1/(J+1)) for J = 1..8
+    const double xj[KQ_DP_JMAX] = {6.324555320336759e-09, 4.9324241486609435e-06,
+                                   1.4801656089845705e-04, 1.1913578981670911e-03,
+                                   4.9324241486609416e-03, 1.3910780714804482e-02,
+                                   3.078355801572517e-02,  5.78509288716415e-02};
     for (int jj = 1; jj <= KQ_DP_JMAX; ++jj) {
       J = jj;
-      radius = pow(2e-17 * fact, 1.0 / (double)(jj + 1)) / x1;
+      radius = xj[jj - 1] / x1;
       if (radius >= want) break;
-      fact *= (double)(jj + 2);
     }
   }
   // reuse the records while the pulse stays inside their radius -- unless they carry much
@@ -367,63 +399,98 @@ __global__ void __launch_bounds__(256) k_dp_build(const KqSweepArgs a, const KqD
   if (e == 0 && k == 0 && !pad) d.anchor[n] = a.pulses[n];
 }
 
+// Stage the E coefficients of `count` records (n_first, n_first + dir, ...) of objective k into
+// shared memory, dst[(s (J+1) + j) NN + r N + c], with cp.async (16 bytes each; every thread of
+// the CTA takes part).  The caller commits / waits.
+__device__ __forceinline__ void dp_stage_records(const KqDpoly& d, cplx* dst, int k, int N, int J,
+                                                 int used, int n_first, int dir, int count) {
+  const int NN = N * N, NR = N + 1, JS = dp_js(J), per = (J + 1) * NN;
+  for (int idx = threadIdx.x; idx < count * per; idx += blockDim.x) {
+    const int sidx = idx / per, rem = idx - sidx * per;
+    const int j = rem / NN, el = rem - j * NN;
+    const int r = el / N, c = el - r * N;
+    const cplx* src =
+        d.rec + (size_t)(n_first + dir * sidx) * used + dp_rec_index(d, NR, k, r, c, JS) + j;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + idx)), "l"(src)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int NLEFT>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(NLEFT) : "memory");
+}
+
 // ---- segprod: propagators of the time segments under the guess pulse ---------------
 // grid (nseg, K), block >= N*N threads: thread = element (r, c).  P <- U_n P over the steps
-// of the segment (ascending), U_n = sum_j D_n^j E_j[n]; output row-major.
+// of the segment (ascending), U_n = sum_j D_n^j E_j[n]; output row-major.  The records come
+// through shared memory in double-buffered batches of d.estage_cap / ((J+1) N N) steps.
 __global__ void __launch_bounds__(256) k_dp_segprod(const KqSweepArgs a, const KqDpoly d) {
   extern __shared__ __align__(16) unsigned char dp_smem[];
   if (dp_declined(a)) return;
-  const int N = a.N, NN = N * N, NT = a.NT, NR = N + 1, K = a.K;
+  const int N = a.N, NN = N * N, NT = a.NT, K = a.K;
   const int k = blockIdx.y, q = blockIdx.x, e = threadIdx.x;
   const bool act = e < NN;
   const int r = act ? e / N : 0, c = act ? e - r * N : 0;
-  const int J = d.hdr->J, JS = dp_js(J), used = dp_rec_used(d, J);
+  const int J = d.hdr->J, used = dp_rec_used(d, J);
   cplx* U = reinterpret_cast<cplx*>(dp_smem);   // [NN]
   cplx* P = U + NN;                              // [2][NN]
+  cplx* Eb = P + 2 * NN;                         // [2][estage_cap]
+  double* Ds = reinterpret_cast<double*>(Eb + (size_t)2 * d.estage_cap);   // [seg_len]
   const int n0 = q * d.seg_len, n1 = min(NT, n0 + d.seg_len);
-  const size_t off = dp_rec_index(d, NR, k, r, c, JS);
+  const int per = (J + 1) * NN;
+  const int SB = max(1, d.estage_cap / per);
+  const int nb = (n1 - n0 + SB - 1) / SB;
   const bool driven = a.term2pulse[k * 2 + 1] == 0;
-  cplx E[KQ_DP_JMAX + 1];
-#pragma unroll
-  for (int j = 0; j <= KQ_DP_JMAX; ++j) E[j] = c_zero();
-  if (act) {
-    P[e] = c_make(r == c ? 1.0 : 0.0, 0.0);
-    const cplx* rp = d.rec + (size_t)n0 * used + off;
-#pragma unroll
-    for (int j = 0; j <= KQ_DP_JMAX; ++j)
-      if (j <= J) E[j] = rp[j];
-  }
+  for (int i = e; i < n1 - n0; i += blockDim.x)
+    Ds[i] = driven ? a.pulses[n0 + i] - d.anchor[n0 + i] : 0.0;
+  if (act) P[e] = c_make(r == c ? 1.0 : 0.0, 0.0);
+  dp_stage_records(d, Eb, k, N, J, used, n0, 1, min(SB, n1 - n0));
+  cp_async_commit();
   int cur = 0;
-  for (int n = n0; n < n1; ++n) {
-    const double D = driven ? a.pulses[n] - d.anchor[n] : 0.0;
-    cplx u = E[KQ_DP_JMAX];
-#pragma unroll
-    for (int j = KQ_DP_JMAX - 1; j >= 0; --j) {
-      u.x = fma(u.x, D, E[j].x);
-      u.y = fma(u.y, D, E[j].y);
+  for (int b = 0; b < nb; ++b) {
+    const int nf = n0 + b * SB, cnt = min(SB, n1 - nf);
+    if (b + 1 < nb) {
+      dp_stage_records(d, Eb + (size_t)((b + 1) & 1) * d.estage_cap, k, N, J, used, nf + SB, 1,
+                       min(SB, n1 - nf - SB));
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    if (act && n + 1 < n1) {
-      const cplx* rp = d.rec + (size_t)(n + 1) * used + off;
-#pragma unroll
-      for (int j = 0; j <= KQ_DP_JMAX; ++j)
-        if (j <= J) E[j] = rp[j];
-    }
-    if (act) U[e] = u;
     __syncthreads();
-    if (act) {
-      cplx a0 = c_zero(), a1 = c_zero();
-      const cplx* Pc = P + cur * NN + c;
-      const cplx* Ur = U + r * N;
-      int x = 0;
-      for (; x + 1 < N; x += 2) {
-        a0 = c_fma(Ur[x], Pc[x * N], a0);
-        a1 = c_fma(Ur[x + 1], Pc[(x + 1) * N], a1);
+    const cplx* Ebb = Eb + (size_t)(b & 1) * d.estage_cap;
+    for (int si = 0; si < cnt; ++si) {
+      const double D = Ds[nf + si - n0];
+      cplx u = c_zero();
+      if (act) {
+        const cplx* ep = Ebb + (size_t)si * per + e;
+        u = ep[J * NN];
+        for (int j = J - 1; j >= 0; --j) {
+          const cplx ej = ep[j * NN];
+          u.x = fma(u.x, D, ej.x);
+          u.y = fma(u.y, D, ej.y);
+        }
+        U[e] = u;
       }
-      if (x < N) a0 = c_fma(Ur[x], Pc[x * N], a0);
-      P[(cur ^ 1) * NN + e] = c_add(a0, a1);
+      __syncthreads();
+      if (act) {
+        cplx a0 = c_zero(), a1 = c_zero();
+        const cplx* Pc = P + cur * NN + c;
+        const cplx* Ur = U + r * N;
+        int x = 0;
+        for (; x + 1 < N; x += 2) {
+          a0 = c_fma(Ur[x], Pc[x * N], a0);
+          a1 = c_fma(Ur[x + 1], Pc[(x + 1) * N], a1);
+        }
+        if (x < N) a0 = c_fma(Ur[x], Pc[x * N], a0);
+        P[(cur ^ 1) * NN + e] = c_add(a0, a1);
+      }
+      __syncthreads();
+      cur ^= 1;
     }
-    __syncthreads();
-    cur ^= 1;
   }
   if (act) d.segP[((size_t)q * K + k) * NN + e] = P[cur * NN + e];
 }
@@ -432,12 +499,13 @@ __global__ void __launch_bounds__(256) k_dp_segprod(const KqSweepArgs a, const K
 // grid (nseg, K), block >= N * R2 threads: thread = (column c, row r), r fastest (R2 = N
 // rounded up to a power of two, so that a column's rows are neighbouring lanes of one warp).
 // Boundary state of the segment: chi(T) pulled back through the later segments,
-// v <- P_p^dag v for p = nseg-1 .. q+1 (thread r < N forms component r from column r of P_p,
-// prefetched one segment ahead).  Then, for n = n1-1 .. n0,
+// v <- P_p^dag v for p = nseg-1 .. q+1 (thread r < N forms component r from column r of P_p).
+// Then, for n = n1-1 .. n0,
 //   eta = mu^dag chi[n+1] ||chi||,  zeta_j[c] = sum_r E_j[n][r, c] conj(eta_r)   -> record n
 //   chi[n][c] = sum_r conj(U_n[r, c]) chi[n+1][r]                                -> X[n]
 // (sums over r: butterfly over the R2 lanes of the column).  With d.chain == 0 the backward
 // states are read from X instead (kq_sweep_forward_update: the caller propagated them).
+// Segment propagators and records come through shared memory in double-buffered batches.
 template <int NMAX>
 __global__ void __launch_bounds__(256) k_dp_expand(const KqSweepArgs a, const KqDpoly d) {
   extern __shared__ __align__(16) unsigned char dp_smem[];
@@ -449,119 +517,154 @@ __global__ void __launch_bounds__(256) k_dp_expand(const KqSweepArgs a, const Kq
   const int J = d.hdr->J, JS = dp_js(J), used = dp_rec_used(d, J);
   cplx* schi = reinterpret_cast<cplx*>(dp_smem);   // [2][N]
   cplx* seta = schi + 2 * N;                        // [N] conj(eta)
+  cplx* Pb = seta + N;                              // [2][chain_bs][NN]
+  cplx* Eb = Pb + (size_t)2 * d.chain_bs * NN;      // [2][estage_cap]
+  cplx* mus = Eb + (size_t)2 * d.estage_cap;        // [NN] mu of this objective
+  double* Ds = reinterpret_cast<double*>(mus + NN); // [seg_len] guess - anchor
   const int n0 = q * d.seg_len, n1 = min(NT, n0 + d.seg_len);
+  const int per = (J + 1) * NN;
+  const int SB = max(1, d.estage_cap / per);
+  const int nbe = (n1 - n0 + SB - 1) / SB;
   const double cnorm = d.norms[k];
+  const bool driven = a.term2pulse[k * 2 + 1] == 0;
+  const double lam = a.lambda_a[0];
+  for (int i = tid; i < NN; i += blockDim.x) mus[i] = a.mu[(size_t)k * NN + i];
+  for (int i = tid; i < n1 - n0; i += blockDim.x) {
+    const int n = n0 + i;
+    const double D = driven ? a.pulses[n] - d.anchor[n] : 0.0;
+    Ds[i] = D;
+    if (k == 0) {   // this step's scalars
+      cplx* tail = d.rec + (size_t)n * used + (size_t)d.C * d.NL * JS;
+      tail[0] = c_make(a.shape[n] / lam, a.pulses[n]);
+      tail[1] = c_make(a.dt[n], D);
+    }
+  }
+  // the first batch of records is under way while the boundary state is formed
+  dp_stage_records(d, Eb, k, N, J, used, n1 - 1, -1, min(SB, n1 - n0));
+  cp_async_commit();
   int cur = 0;
   if (d.chain) {
     if (tid < N) schi[tid] = d.chi[(size_t)k * N + tid];
     __syncthreads();
-    cplx col[NMAX];
+    const int BS = d.chain_bs, nchain = d.nseg - 1 - q;
+    const int nb = (nchain + BS - 1) / BS;
     const bool row_thread = tid < N;
-    if (row_thread && q + 1 < d.nseg) {
-      const cplx* Pp = d.segP + ((size_t)(d.nseg - 1) * K + k) * NN + tid;
-#pragma unroll
-      for (int x = 0; x < NMAX; ++x)
-        if (x < N) col[x] = Pp[x * N];
-    }
-    for (int p = d.nseg - 1; p > q; --p) {
-      cplx a0 = c_zero(), a1 = c_zero();
-      if (row_thread) {
-#pragma unroll
-        for (int x = 0; x < NMAX; x += 2) {
-          if (x < N) a0 = c_fma_conj(col[x], schi[cur * N + x], a0);
-          if (x + 1 < N) a1 = c_fma_conj(col[x + 1], schi[cur * N + x + 1], a1);
-        }
-        if (p - 1 > q) {
-          const cplx* Pp = d.segP + ((size_t)(p - 1) * K + k) * NN + tid;
-#pragma unroll
-          for (int x = 0; x < NMAX; ++x)
-            if (x < N) col[x] = Pp[x * N];
-        }
-        schi[(cur ^ 1) * N + tid] = c_add(a0, a1);
+    auto issue = [&](int b) {
+      const int cnt = min(BS, nchain - b * BS);
+      cplx* dst = Pb + (size_t)(b & 1) * BS * NN;
+      for (int e = tid; e < cnt * NN; e += blockDim.x) {
+        const int i = e / NN, el = e - i * NN;
+        const int pseg = d.nseg - 1 - (b * BS + i);
+        const cplx* src = d.segP + ((size_t)pseg * K + k) * NN + el;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + i * NN + el)),
+                     "l"(src)
+                     : "memory");
+      }
+      cp_async_commit();
+    };
+    if (nb > 0) issue(0);
+    for (int b = 0; b < nb; ++b) {
+      if (b + 1 < nb) {
+        issue(b + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
-      cur ^= 1;
+      const int cnt = min(BS, nchain - b * BS);
+      const cplx* Pbb = Pb + (size_t)(b & 1) * BS * NN;
+      for (int i = 0; i < cnt; ++i) {
+        if (row_thread) {
+          const cplx* Pp = Pbb + i * NN + tid;   // column `tid` of the row-major propagator
+          cplx a0 = c_zero(), a1 = c_zero();
+          int x = 0;
+          for (; x + 1 < N; x += 2) {
+            a0 = c_fma_conj(Pp[x * N], schi[cur * N + x], a0);
+            a1 = c_fma_conj(Pp[(x + 1) * N], schi[cur * N + x + 1], a1);
+          }
+          if (x < N) a0 = c_fma_conj(Pp[x * N], schi[cur * N + x], a0);
+          schi[(cur ^ 1) * N + tid] = c_add(a0, a1);
+        }
+        __syncthreads();
+        cur ^= 1;
+      }
     }
     if (q == d.nseg - 1 && tid < N) d.X[((size_t)NT * K + k) * N + tid] = schi[cur * N + tid];
   }
-  const size_t off = dp_rec_index(d, NR, k, act ? r : 0, act ? c : 0, JS);
-  const bool driven = a.term2pulse[k * 2 + 1] == 0;
-  const double lam = a.lambda_a[0];
-  cplx E[KQ_DP_JMAX + 1];
-#pragma unroll
-  for (int j = 0; j <= KQ_DP_JMAX; ++j) E[j] = c_zero();
-  if (act) {
-    const cplx* rp = d.rec + (size_t)(n1 - 1) * used + off;
-#pragma unroll
-    for (int j = 0; j <= KQ_DP_JMAX; ++j)
-      if (j <= J) E[j] = rp[j];
-  }
-  for (int n = n1 - 1; n >= n0; --n) {
-    if (!d.chain) {
-      if (tid < N) schi[cur * N + tid] = d.X[((size_t)(n + 1) * K + k) * N + tid];
-      __syncthreads();
-    }
-    if (tid < N) {
-      // conj(eta), eta = mu^dag chi[n+1] ||chi||; no update follows the last step
-      const double cn = (n + 1 < NT) ? cnorm : 0.0;
-      cplx acc = c_zero();
-      for (int rr = 0; rr < N; ++rr)
-        acc = c_fma_conj(a.mu[(size_t)k * NN + tid * N + rr], schi[cur * N + rr], acc);
-      seta[tid] = c_make(acc.x * cn, -acc.y * cn);
+  const int el = (act ? r : 0) * N + (act ? c : 0);
+  for (int b = 0; b < nbe; ++b) {
+    const int nf = n1 - 1 - b * SB, cnt = min(SB, nf - n0 + 1);
+    if (b + 1 < nbe) {
+      dp_stage_records(d, Eb + (size_t)((b + 1) & 1) * d.estage_cap, k, N, J, used, nf - SB, -1,
+                       min(SB, nf - SB - n0 + 1));
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    const double D = driven ? a.pulses[n] - d.anchor[n] : 0.0;
-    cplx u = E[KQ_DP_JMAX];
+    const cplx* Ebb = Eb + (size_t)(b & 1) * d.estage_cap;
+    for (int si = 0; si < cnt; ++si) {
+      const int n = nf - si;
+      if (!d.chain) {
+        if (tid < N) schi[cur * N + tid] = d.X[((size_t)(n + 1) * K + k) * N + tid];
+        __syncthreads();
+      }
+      if (tid < N) {
+        // conj(eta), eta = mu^dag chi[n+1] ||chi||; no update follows the last step
+        const double cn = (n + 1 < NT) ? cnorm : 0.0;
+        cplx acc = c_zero();
+        for (int rr = 0; rr < N; ++rr)
+          acc = c_fma_conj(mus[tid * N + rr], schi[cur * N + rr], acc);
+        seta[tid] = c_make(acc.x * cn, -acc.y * cn);
+      }
+      __syncthreads();
+      const double D = Ds[n - n0];
+      cplx E[KQ_DP_JMAX + 1];
+      const cplx* ep = Ebb + (size_t)si * per + el;
 #pragma unroll
-    for (int j = KQ_DP_JMAX - 1; j >= 0; --j) {
-      u.x = fma(u.x, D, E[j].x);
-      u.y = fma(u.y, D, E[j].y);
-    }
-    const cplx chr = act ? schi[cur * N + r] : c_zero();
-    const cplx etr = act ? seta[r] : c_zero();
-    cplx px = c_fma_conj(u, chr, c_zero());   // conj(U[r,c]) chi[r]
-    cplx pz[KQ_DP_JMAX + 1];
+      for (int j = 0; j <= KQ_DP_JMAX; ++j) E[j] = (act && j <= J) ? ep[j * NN] : c_zero();
+      cplx u = E[KQ_DP_JMAX];
 #pragma unroll
-    for (int j = 0; j <= KQ_DP_JMAX; ++j) pz[j] = c_fma(E[j], etr, c_zero());
-    if (act && n > n0) {
-      const cplx* rp = d.rec + (size_t)(n - 1) * used + off;
+      for (int j = KQ_DP_JMAX - 1; j >= 0; --j) {
+        u.x = fma(u.x, D, E[j].x);
+        u.y = fma(u.y, D, E[j].y);
+      }
+      const cplx chr = act ? schi[cur * N + r] : c_zero();
+      const cplx etr = act ? seta[r] : c_zero();
+      cplx px = c_fma_conj(u, chr, c_zero());   // conj(U[r,c]) chi[r]
+      cplx pz[KQ_DP_JMAX + 1];
 #pragma unroll
-      for (int j = 0; j <= KQ_DP_JMAX; ++j)
-        if (j <= J) E[j] = rp[j];
-    }
-    for (int o = R2 >> 1; o > 0; o >>= 1) {
-      px.x += __shfl_xor_sync(0xffffffffu, px.x, o);
-      px.y += __shfl_xor_sync(0xffffffffu, px.y, o);
+      for (int j = 0; j <= KQ_DP_JMAX; ++j) pz[j] = c_fma(E[j], etr, c_zero());
+      for (int o = R2 >> 1; o > 0; o >>= 1) {
+        px.x += __shfl_xor_sync(0xffffffffu, px.x, o);
+        px.y += __shfl_xor_sync(0xffffffffu, px.y, o);
 #pragma unroll
-      for (int j = 0; j <= KQ_DP_JMAX; ++j) {
-        if (j <= J) {
-          pz[j].x += __shfl_xor_sync(0xffffffffu, pz[j].x, o);
-          pz[j].y += __shfl_xor_sync(0xffffffffu, pz[j].y, o);
+        for (int j = 0; j <= KQ_DP_JMAX; ++j) {
+          if (j <= J) {
+            pz[j].x += __shfl_xor_sync(0xffffffffu, pz[j].x, o);
+            pz[j].y += __shfl_xor_sync(0xffffffffu, pz[j].y, o);
+          }
         }
       }
-    }
-    cplx* rec = d.rec + (size_t)n * used;
-    if (r == 0 && c < N) {
-      if (d.chain) {
-        schi[(cur ^ 1) * N + c] = px;
-        d.X[((size_t)n * K + k) * N + c] = px;
-      }
-      cplx* zp = rec + dp_rec_index(d, NR, k, N, c, JS);
+      cplx* rec = d.rec + (size_t)n * used;
+      if (r == 0 && c < N) {
+        if (d.chain) {
+          schi[(cur ^ 1) * N + c] = px;
+          d.X[((size_t)n * K + k) * N + c] = px;
+        }
+        cplx* zp = rec + dp_rec_index(d, NR, k, N, c, JS);
 #pragma unroll
-      for (int j = 0; j <= KQ_DP_JMAX; ++j)
-        if (j <= J) zp[j] = pz[j];
-      if (c < d.Npad - N) {   // padding columns of the zeta row
-        cplx* z0 = rec + dp_rec_index(d, NR, k, N, N + c, JS);
-        for (int j = 0; j <= J; ++j) z0[j] = c_zero();
+        for (int j = 0; j <= KQ_DP_JMAX; ++j)
+          if (j <= J) zp[j] = pz[j];
+        if (c < d.Npad - N) {   // padding columns of the zeta row
+          cplx* z0 = rec + dp_rec_index(d, NR, k, N, N + c, JS);
+          for (int j = 0; j <= J; ++j) z0[j] = c_zero();
+        }
       }
+      __syncthreads();
+      if (d.chain) cur ^= 1;
     }
-    if (tid == 0 && k == 0) {
-      cplx* tail = rec + (size_t)d.C * d.NL * JS;
-      tail[0] = c_make(a.shape[n] / lam, a.pulses[n]);
-      tail[1] = c_make(a.dt[n], D);
-    }
-    __syncthreads();
-    if (d.chain) cur ^= 1;
   }
   if (q == d.nseg - 1) {
     // records behind the grid: no overlap, no update
@@ -584,23 +687,8 @@ __global__ void __launch_bounds__(256) k_dp_expand(const KqSweepArgs a, const Kq
 // is the producer: its lane 0 refills the ring (waits until every consumer warp has released
 // a stage, re-arms the stage's mbarrier and issues the TMA bulk copy), so no copy is issued
 // from the dependency chain.
-// shared: [full 16][empty 16][dbuf 2 x K, padded][sred K N, padded][phi 2 x K Npad cplx][ring]
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// one non-blocking test; the result is consumed later (off the dependency chain)
-__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
 }
 __device__ __forceinline__ void dp_consumer_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
@@ -944,7 +1032,17 @@ __global__ void __launch_bounds__(256) k_dp_epilogue(const KqSweepArgs a, const 
   // the largest update of this call: predicts the next one (k_dp_plan)
   __shared__ double red[8];
   double m = 0.0;
-  for (int n = threadIdx.x; n < a.NT; n += 256) m = fmax(m, fabs(a.opt_pulses[n] - a.pulses[n]));
+  for (int n0 = threadIdx.x; n0 < a.NT; n0 += 4 * 256) {
+    double o[4], g[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int n = n0 + u * 256;
+      o[u] = n < a.NT ? a.opt_pulses[n] : 0.0;
+      g[u] = n < a.NT ? a.pulses[n] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m = fmax(m, fabs(o[u] - g[u]));
+  }
   m = warp_allreduce_max(m);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();

@@ -24,7 +24,7 @@ struct KqDpHeader {
   double radius;          // the records reproduce U_n(anchor_n + Delta) for |Delta| <= radius
   double last_max;        // largest |opt - guess| of epoch valid_epoch
   double anchor_max;      // max |anchor|
-  double pad;
+  double dtmax, o0, o1;   // problem constants (max |dt|, operator norm bounds), 0 = not yet known
 };
 
 struct KqDpoly {
@@ -37,6 +37,8 @@ struct KqDpoly {
   int nseg, seg_len;      // backward sweep: segments of seg_len steps
   int chain;              // 1: backward states from chi(T) through the records; 0: read from X
   int R2;                 // N rounded up to a power of two (expand kernel: lanes per column)
+  int chain_bs;           // expand kernel: segment propagators per shared-memory batch
+  int estage_cap;         // segprod / expand: complex numbers per record-staging buffer
   KqDpHeader* hdr;
   double* anchor;         // [NT] pulse the records are expanded around
   cplx* segP;             // [nseg][K][N*N] segment propagators (row-major)

@@ -1,4 +1,6 @@
 // Delta-polynomial Krotov iteration (kq_dpoly.cuh): launches.
+#include <algorithm>
+
 #include "kq_host.cuh"
 #include "kq_dpoly.cuh"
 
@@ -20,12 +22,22 @@ int build_and_backward(const KqSweepArgs& a, const KqDpoly& d, const KqDpolyGeom
   if (rc) return rc;
   const int NN = a.N * a.N;
   if (d.chain) {
-    k_dp_segprod<<<dim3(d.nseg, a.K), round32(NN), (size_t)3 * NN * sizeof(cplx), st>>>(a, d);
-    KQ_CUDA(cudaGetLastError());
+    KqPlan ps = {};
+    ps.grid = d.nseg;
+    ps.grid_y = a.K;
+    ps.block = std::max(128, round32(NN));   // extra threads help staging the records
+    ps.smem = ((size_t)3 * NN + (size_t)2 * d.estage_cap) * sizeof(cplx) + (size_t)d.seg_len * 8;
+    rc = launch(k_dp_segprod, ps, false, st, params);
+    if (rc) return rc;
   }
-  k_dp_expand<NMAX><<<dim3(d.nseg, a.K), round32(a.N * d.R2), (size_t)3 * a.N * sizeof(cplx),
-                      st>>>(a, d);
-  KQ_CUDA(cudaGetLastError());
+  KqPlan pe = {};
+  pe.grid = d.nseg;
+  pe.grid_y = a.K;
+  pe.block = std::max(128, round32(a.N * d.R2));
+  pe.smem = ((size_t)3 * a.N + (size_t)2 * d.chain_bs * NN + (size_t)2 * d.estage_cap + NN) * sizeof(cplx) +
+            (size_t)d.seg_len * 8;
+  rc = launch(k_dp_expand<NMAX>, pe, false, st, params);
+  if (rc) return rc;
   return KQ_OK;
 }
 

@@ -68,10 +68,13 @@ class SweepEngine:
         self.t_psi0 = up(cp.psi0, c128)
         self.t_targets = None if cp.targets is None else up(cp.targets, c128)
         self.t_weights = None if cp.weights is None else up(cp.weights, f64)
-        # strongly coupled problems with few objectives and N = 3, 4: the
-        # time-parallel fixed point would need many rounds (their number grows
-        # with T * (S/lambda) * sum_k ||chi_k|| ||mu_k||^2), the delta-polynomial
-        # sequential sweep does not care
+        # few objectives with N = 3, 4: the delta-polynomial iteration
+        # (csrc/kq_dpoly.cuh) runs its sequential chain in ONE warp when
+        # K (N + 1) <= 32 lanes and is then at least as fast as the
+        # time-parallel fixed point, which would leave most of the GPU idle;
+        # strongly coupled problems (the number of fixed-point rounds grows
+        # with T * (S/lambda) * sum_k ||chi_k|| ||mu_k||^2) prefer it up to
+        # K = 16 anyway
         update_sweep = 0
         if cp.M == 2 and cp.L == 1 and cp.N in (3, 4) and cp.K <= 16:
             lam0 = float(np.asarray(lambda_vals, dtype=np.float64)[0])
@@ -79,7 +82,7 @@ class SweepEngine:
             mu2 = max(np.linalg.norm(np.asarray(cp.mu[k, 0]).reshape(
                 cp.N, cp.N), 2) for k in range(cp.K)) ** 2
             coupling = float(np.sum(cp.dt)) * smax / lam0 * 0.5 * mu2
-            if coupling > 4.0:
+            if coupling > 4.0 or cp.K * (cp.N + 1) <= 32:
                 update_sweep = 1
         self.update_sweep = update_sweep
         self.problem = KqProblem(

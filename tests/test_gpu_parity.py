@@ -1004,3 +1004,49 @@ def test_dpoly_sweep_variants_vs_oracle(krotov, case, dpoly_mode):
         want = _oracle_pulses(objs, opts, tlist, 3, is_super=is_super)
     for it in (1, 2, 3):
         assert rel(res.all_pulses[it], want[it]) < PULSE_RTOL, (case, it)
+
+
+def test_dpoly_records_are_reused_across_iterations(krotov, dpoly_mode):
+    """The step polynomials of the delta-polynomial iteration are anchored at
+    a pulse of an EARLIER Krotov iteration and kept in the workspace: over 12
+    iterations of the transmon X gate (N = 3) most iterations must reuse them
+    (plan header: builds + reuses == iterations, reuses > builds) and the
+    pulses must still match the oracle, iteration by iteration."""
+    if dpoly_mode == 'dpoly_off':
+        pytest.skip("needs the delta-polynomial iteration")
+    import ctypes
+    import torch
+    from oracle import krotov_oracle as orc
+    from krotov_b200.compiler import compile_problem, initialize_controls
+    from krotov_b200.engine import SweepEngine
+    lib = krotov._lib.load()
+    wl = krotov.workloads.transmon_xgate(nt=400)
+    low = wl.lowered()
+    n_it = 12
+    rec = orc.optimize(low['terms'], low['psi0'], low['targets'],
+                       low['pulses'], low['shapes'], low['lambdas'],
+                       low['tlist'], orc.chis_re, iter_stop=n_it)
+    objectives = wl.objectives(krotov.Objective)
+    controls, _, guess, mapping, lam, shp = initialize_controls(
+        objectives, wl.pulse_options, wl.tlist)
+    cp = compile_problem(objectives, controls, mapping, wl.tlist)
+    eng = SweepEngine(cp, shp, lam)
+    assert eng.update_sweep == 1
+    g = eng.pulses_to_device(guess)
+    o = g.clone()
+    phiT = eng.propagate_forward(g)
+    tau = eng.overlaps(eng.t_targets, phiT)
+    diag = torch.zeros(4, dtype=torch.int32, device=eng.device)
+    for it in range(1, n_it + 1):
+        p2, t2 = eng.new_states(), torch.empty_like(tau)
+        eng.krotov_iteration('re', g, o, phiT, tau, p2, t2, diag_t=diag)
+        torch.cuda.synchronize()
+        assert diag.cpu().numpy().tolist() == [0, 0, 0, 0], it
+        assert rel(o.cpu().numpy(), rec[it]['optimized_pulses']) < PULSE_RTOL, it
+        phiT, tau = p2, t2
+        g, o = o, g
+    off = lib.kq_dpoly_header_offset(eng._p)
+    hdr = eng.workspace[off:off + 32].cpu().numpy().view(np.int32)
+    builds, reuses = int(hdr[6]), int(hdr[7])
+    assert builds + reuses == n_it
+    assert reuses > builds, (builds, reuses)
