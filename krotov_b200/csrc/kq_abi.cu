@@ -774,7 +774,9 @@ __global__ void k_chi_boundary(int K, int N, int kind, int K_total, const cplx* 
   norms[k] = nrm;
   for (int i = 0; i < N; ++i) {
     cplx v = chi[(size_t)k * N + i];
-    chi[(size_t)k * N + i] = c_make(v.x / nrm, v.y / nrm);
+    // a target reached exactly gives chi = 0: keep it zero instead of 0/0 (the reference
+    // divides by zero there, optimize.py:410)
+    chi[(size_t)k * N + i] = nrm > 0.0 ? c_make(v.x / nrm, v.y / nrm) : c_zero();
   }
 }
 

@@ -96,9 +96,13 @@ __device__ __forceinline__ void taylor_plan(const KqTables& T, double x, int& s,
                                             double& xs) {
   s = 1;
   xs = x;
-  if (x > 1.0) {
-    double sd = ceil(x);
-    sd = fmin(sd, 1.0e6);
+  if (!(x <= 1.0e6)) {
+    // non-finite (NaN pulses, e.g. from a zero chi norm) or absurdly large: the result is
+    // garbage either way (the host checks the pulses for finiteness) -- keep the work
+    // bounded instead of scaling a million times per step
+    xs = 1.0;
+  } else if (x > 1.0) {
+    const double sd = ceil(x);
     s = (int)sd;
     xs = x / sd;
   }

@@ -126,10 +126,9 @@ __global__ void __launch_bounds__(256) k_dp_plan(const KqSweepArgs a, const KqDp
       }
       const double nrm = sqrt(nrm2);
       d.norms[k] = nrm;
-      const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;   // a perfect target gives chi = 0, not NaN
-      for (int i = 0; i < N; ++i) {
+      for (int i = 0; i < N; ++i) {   // a target reached exactly gives chi = 0, not 0/0
         const cplx v = d.chi[(size_t)k * N + i];
-        d.chi[(size_t)k * N + i] = nrm > 0.0 ? c_make(v.x / nrm, v.y / nrm) : c_make(v.x * inv, v.y * inv);
+        d.chi[(size_t)k * N + i] = nrm > 0.0 ? c_make(v.x / nrm, v.y / nrm) : c_zero();
       }
     }
     __syncthreads();

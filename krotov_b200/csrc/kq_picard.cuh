@@ -725,7 +725,8 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       }
       cnorm = sqrt(nrm2);
 #pragma unroll
-      for (int i = 0; i < N; ++i) chiT[i] = c_make(chiT[i].x / cnorm, chiT[i].y / cnorm);
+      for (int i = 0; i < N; ++i)
+        chiT[i] = cnorm > 0.0 ? c_make(chiT[i].x / cnorm, chiT[i].y / cnorm) : c_zero();
     }
     if (g.t == 0 && valid) {
       if (a.chi_out) {
@@ -961,9 +962,14 @@ __global__ void __launch_bounds__(KQ_PIC_BT, 1) k_krotov_picard(const KqSweepArg
       // error of eps_it: the last change, or -- while the iteration contracts --
       // its extrapolation rho/(1-rho) * change with rho = ratio of the last two
       // changes (stops one exchange round earlier)
+      // A small change alone does not bound the error of a map whose resolvent norm can be
+      // ~e^{CT} (strong coupling, long T): it is accepted only while the iteration
+      // contracts (the change shrank), or when two consecutive changes were both small
+      // (rounding level: their ratio is noise).
       const double rho = (dm_prev < kInf && dm_prev > 0.0) ? dmax / dm_prev : 1.0;
-      const bool small = (dmax <= a.pic_rtol * emax) ||
-                         (rho < 0.25 && dmax * rho <= (1.0 - rho) * 0.2 * a.pic_rtol * emax);
+      const double tol = a.pic_rtol * emax;
+      const bool small = (dmax <= tol && (rho < 1.0 || dm_prev <= tol)) ||
+                         (rho < 0.25 && dmax * rho <= (1.0 - rho) * 0.2 * tol);
       dm_prev = dmax;
       converged = !exch_fail && resolved && small;
       stop = converged || exch_fail || it >= a.pic_maxit;

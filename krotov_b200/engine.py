@@ -310,8 +310,8 @@ class SweepEngine:
         arr = np.asarray(chi_vectors, dtype=np.complex128).reshape(
             self.cp.K, self.cp.N)
         norms = np.sqrt((arr.real ** 2 + arr.imag ** 2).sum(axis=1))
-        with np.errstate(divide='ignore', invalid='ignore'):
-            arr = arr / norms[:, None]
+        # a zero chi (target reached exactly) stays zero instead of 0/0
+        arr = arr / np.where(norms > 0, norms, 1.0)[:, None]
         self.chi.copy_(self.torch.as_tensor(arr))
         self.chi_norms.copy_(self.torch.as_tensor(norms))
         self.h2d_bytes += arr.nbytes + norms.nbytes

@@ -279,6 +279,16 @@ def _restore_from_previous_result(result, objectives, tlist, store_all_pulses):
     return guess_controls, [control_onto_interval(c) for c in guess_controls]
 
 
+def _check_finite(pulses, iteration):
+    """The kernels never hang on non-finite input, but their output is then
+    meaningless: say so instead of returning NaN pulses (e.g. a
+    chi_constructor that returned NaN, or a lambda_a of zero)."""
+    if not all(np.all(np.isfinite(p)) for p in pulses):
+        raise FloatingPointError(
+            "non-finite pulse values after Krotov iteration %d (check "
+            "lambda_a, the update shapes and the chi_constructor)" % iteration)
+
+
 def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
                     chi_constructor, mu=None, sigma=None, iter_start=0,
                     iter_stop=5000, check_convergence=None, info_hook=None,
@@ -794,6 +804,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         if st != 0:
             raise RuntimeError("sweep kernel reported exchange failure %d"
                                % st)
+        _check_finite(optimized_pulses, krotov_iteration)
         if packed is not None and sharded_packed:
             # the final states of all ranks came with the packed copy
             fw_states_T = _LazyFinalStates(
@@ -919,6 +930,7 @@ def optimize_pulses(objectives, pulse_options, tlist, *, propagator,
         # after the swap at the end of the loop the optimized pulses of the
         # last iteration are in guess_t
         optimized_pulses = pulses_to_host(guess_t)
+        _check_finite(optimized_pulses, deferred[-1][0])
         result.optimized_controls = optimized_pulses
         result.states = states_to_host(phiT)
 

@@ -363,3 +363,130 @@ def test_convergence_specs_follow_reference():
         r3).startswith('Loss of monotonic')
     with pytest.raises(ValueError):
         cv.dump_result('x', every=0)
+
+
+def test_import_krotov_alias_package():
+    """`import krotov` resolves to the engine when compat/ is on the path: the
+    reference's package, submodule and top-level names
+    (/root/reference/src/krotov/__init__.py:40-65)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import krotov, krotov_b200\n"
+        "import krotov.propagators as P\n"
+        "from krotov.functionals import chis_re, J_T_re\n"
+        "from krotov.objectives import Objective, gate_objectives\n"
+        "from krotov.convergence import check_monotonic_error, value_below\n"
+        "from krotov.info_hooks import print_table, chain\n"
+        "from krotov.shapes import flattop, blackman\n"
+        "from krotov.second_order import numerical_estimate_A\n"
+        "from krotov.conversions import pulse_onto_tlist\n"
+        "from krotov.parallelization import parallel_map\n"
+        "assert krotov.optimize_pulses is krotov_b200.optimize_pulses\n"
+        "assert krotov.Objective is krotov_b200.Objective\n"
+        "assert krotov.result.Result is krotov.Result\n"
+        "assert P.expm is krotov_b200.propagators.expm\n"
+        "assert callable(krotov.mu.derivative_wrt_pulse)\n"
+        "print('ok')\n")
+    env = dict(os.environ)
+    env['PYTHONPATH'] = os.pathsep.join(
+        [os.path.join(root, 'compat'), root, env.get('PYTHONPATH', '')])
+    out = subprocess.run([sys.executable, '-c', code], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == 'ok'
+
+
+def test_print_table_api_matches_reference():
+    """print_table: keyword-only signature with J_T_prev, validation of
+    col_formats / col_headers (/root/reference/tests/test_infohooks.py:78-127),
+    default and custom layouts (rows of tests/test_infohooks/
+    custom_format_out.txt and of the SciPost example in the docstring,
+    info_hooks.py:366-372), '*' markers, J_T_prev from info_vals."""
+    import io
+    from krotov_b200.info_hooks import print_table
+    J_T = lambda **kwargs: 1.0  # noqa: E731
+    for bad, msg in (((".2e"), '8 elements'), ("eeeeeeee", 'percent format string'),
+                     ((".2e", ".2e"), '8 elements'),
+                     (('%d', '%.2', '%.2e', '%.2e', '%.2e', '%.2e', '%.2e', '%d'),
+                      'Invalid col_formats')):
+        with pytest.raises(ValueError) as exc:
+            print_table(J_T=J_T, col_formats=bad)
+        assert msg in str(exc.value)
+    for bad in ("header", ("header", "header")):
+        with pytest.raises(ValueError) as exc:
+            print_table(J_T=J_T, col_headers=bad)
+        assert '8 elements' in str(exc.value)
+    with pytest.raises(ValueError) as exc:
+        print_table(J_T=J_T, show_g_a_int_per_pulse=True, col_headers=(
+            "it", "J_T", "∫gₐ(ϵ{i})dt", "∑∫gₐ(t)dt", "J", "ΔJ_T", "ΔJ", "secs"))
+    assert "must support '.format(l=l)'" in str(exc.value)
+    with pytest.raises(TypeError):
+        print_table(J_T)          # keyword-only, like the reference
+
+    def rows(hook, vals, g_as, n_pulses=1, info_vals=None):
+        info_vals = [] if info_vals is None else info_vals
+        for it, (v, g) in enumerate(zip(vals, g_as)):
+            info_vals.append(hook(
+                iteration=it, g_a_integrals=np.atleast_1d(g),
+                guess_pulses=[None] * n_pulses, iter_stop=10, start_time=0.0,
+                stop_time=float(it), info_vals=info_vals, value=v))
+    out = io.StringIO()
+    hook = print_table(J_T=lambda **kw: kw['value'], out=out)
+    rows(hook, [1.0, 0.765, 0.556], [0.0, 2.33e-2, 2.07e-2])
+    assert out.getvalue().splitlines() == [
+        "iter.      J_T    ∫gₐ(t)dt          J       ΔJ_T         ΔJ  secs",
+        "0     1.00e+00    0.00e+00   1.00e+00        n/a        n/a     0",
+        "1     7.65e-01    2.33e-02   7.88e-01  -2.35e-01  -2.12e-01     1",
+        "2     5.56e-01    2.07e-02   5.77e-01  -2.09e-01  -1.88e-01     2"]
+    out = io.StringIO()
+    hook = print_table(
+        J_T=lambda **kw: kw['value'], out=out,
+        col_formats=('%8d', '%12.4e', '%12.4e', '%12.4e', '%12.4e', '%12.4e', '%12.4e',
+                     '%05d'))
+    rows(hook, [1.0, 0.76485], [0.0, 0.11758])
+    assert out.getvalue().splitlines() == [
+        "iter.              J_T     ∫gₐ(t)dt            J         ΔJ_T"
+        "           ΔJ  secs",
+        "       0    1.0000e+00   0.0000e+00   1.0000e+00          n/a"
+        "          n/a 00000",
+        "       1    7.6485e-01   1.1758e-01   8.8243e-01  -2.3515e-01"
+        "  -1.1757e-01 00001"]
+    # two pulses, per-pulse columns, loss of monotonic convergence marked
+    out = io.StringIO()
+    hook = print_table(J_T=lambda **kw: kw['value'], out=out,
+                       show_g_a_int_per_pulse=True, unicode=False)
+    rows(hook, [1.0, 1.1], [[0.0, 0.0], [1e-2, 2e-2]], n_pulses=2)
+    lines = out.getvalue().splitlines()
+    assert lines[0].split() == ["iter.", "J_T", "g_a_int_1", "g_a_int_2",
+                                "g_a_int", "J", "Delta", "J_T", "Delta", "J",
+                                "secs"]
+    assert lines[2].endswith(" **")
+    assert lines[2].split()[:5] == ['1', '1.10e+00', '1.00e-02', '2.00e-02',
+                                    '3.00e-02']
+    # custom headers (tests/test_infohooks/custom_header_out.txt of the reference)
+    out = io.StringIO()
+    hook = print_table(
+        J_T=lambda **kw: kw['value'], out=out, show_g_a_int_per_pulse=True,
+        col_headers=('iteration', ' final time functional',
+                     ' running cost (pulse {l})', ' total running cost',
+                     ' total functional', ' change in final time functional',
+                     ' change in total functional', ' seconds for iteration'))
+    rows(hook, [1.0, 0.76485], [0.0, 0.11758])
+    assert out.getvalue().splitlines() == [
+        "iteration   final time functional  total running cost  total functional"
+        "  change in final time functional  change in total functional"
+        "  seconds for iteration",
+        "0                        1.00e+00            0.00e+00          1.00e+00"
+        "                              n/a                         n/a"
+        "                      0",
+        "1                        7.65e-01            1.18e-01          8.82e-01"
+        "                        -2.35e-01                   -1.18e-01"
+        "                      1"]
+    # continuation: the first printed row uses info_vals[-1] (or J_T_prev)
+    out = io.StringIO()
+    hook = print_table(J_T=lambda **kw: 0.5, out=out)
+    hook(iteration=4, g_a_integrals=np.array([0.1]), guess_pulses=[None],
+         iter_stop=10, start_time=0.0, stop_time=0.0, info_vals=[0.75])
+    assert "-2.50e-01  -1.50e-01" in out.getvalue()
