@@ -66,6 +66,30 @@ typedef enum {
   KQ_ERR_EXCHANGE = -4    /* cross-CTA / cross-GPU exchange timed out */
 } kq_status;
 
+/* Sparse (CSR) form of the generator terms, their adjoints and the mu matrices, for large
+ * state vectors (64 < N <= 1024: Liouville space of notebook 06, N = 625).  Matrix i has
+ * rows row_ptr[i*(N+1) .. i*(N+1)+N] (offsets relative to mat_off[i]) into col / val.
+ * Numbering: ops[k][m] -> k*M + m;  ops_adj[k][m] -> K*M + k*M + m;
+ * mu[k][l] -> 2*K*M + k*L + l.  All arrays are DEVICE pointers. */
+typedef struct kq_sparse {
+  const int32_t* row_ptr;
+  const int64_t* mat_off;
+  const int32_t* col;
+  const kq_c128* val;
+  /* optional dictionary-coded copy (NULL / 0 if absent): val[p] = dict[code16[p]],
+   * col16[p] = col[p]; n_dict <= 65536.  Liouvillians repeat few distinct values, so a
+   * CTA can keep all matrices of its objective in shared memory (4 bytes per non-zero). */
+  const uint16_t* col16;
+  const uint16_t* code16;
+  const kq_c128* dict;
+  int32_t n_dict;
+  /* HOST-side hints: the largest number of non-zeros one CTA would stage, over the
+   * objectives: generator terms + mu (update sweep) / generator or adjoint terms
+   * (propagation sweeps).  0 = do not stage. */
+  int32_t stage_nnz_update;
+  int32_t stage_nnz_prop;
+} kq_sparse;
+
 typedef struct {
   int32_t K;          /* objectives held by this rank */
   int32_t N;          /* state length */
@@ -92,6 +116,8 @@ typedef struct {
                          the fixed point needs many rounds there), 2 = fixed point.
                          N > 4 always uses the delta-polynomial sweep if it fits. */
   int32_t reserved2;
+  const struct kq_sparse* sparse;  /* NULL, or the CSR form of all matrices: required for
+                         N > 64 (then ops / ops_adj / mu may be NULL), ignored otherwise */
 } kq_problem;
 
 /* Cross-GPU exchange descriptor for the per-time-step reduction of the pulse

@@ -50,7 +50,18 @@ class KqProblem(ctypes.Structure):
         ('shape', ctypes.c_void_p), ('lambda_a', ctypes.c_void_p),
         ('real_ops', ctypes.c_int32), ('reserved', ctypes.c_int32),
         ('update_sweep', ctypes.c_int32), ('reserved2', ctypes.c_int32),
+        ('sparse', ctypes.c_void_p),
     ]
+
+
+class KqSparse(ctypes.Structure):
+    """Mirror of ``kq_sparse``."""
+    _fields_ = [('row_ptr', ctypes.c_void_p), ('mat_off', ctypes.c_void_p),
+                ('col', ctypes.c_void_p), ('val', ctypes.c_void_p),
+                ('col16', ctypes.c_void_p), ('code16', ctypes.c_void_p),
+                ('dict', ctypes.c_void_p), ('n_dict', ctypes.c_int32),
+                ('stage_nnz_update', ctypes.c_int32),
+                ('stage_nnz_prop', ctypes.c_int32)]
 
 
 class KqComm(ctypes.Structure):

@@ -107,6 +107,7 @@ class CompiledProblem:
         self.is_super = False
         self.real_ops = False
         self.ops = self.ops_adj = self.mu = None      # complex128 arrays
+        self.sparse = None      # CSR bundle instead, for N > DENSE_NMAX
         self.term2pulse = self.op_norm = None
         self.psi0 = self.targets = None               # [K,N]
         self.weights = None
@@ -247,10 +248,28 @@ def compile_problem(objectives, controls, mapping, tlist, mu=None,
         else:
             for l, op in terms:
                 mu_tab[k, l] = (1j * op) if is_super else op
-    # column-major storage: element (r,c) at c*N + r
-    cp.ops = np.ascontiguousarray(np.swapaxes(ops, 2, 3))
-    cp.ops_adj = np.ascontiguousarray(np.swapaxes(ops_adj, 2, 3))
-    cp.mu = np.ascontiguousarray(np.swapaxes(mu_tab, 2, 3))
+    if N > DENSE_NMAX:
+        # large state vectors (Liouville space of notebook 06: N = 625): the
+        # kernels take the matrices in CSR form (include/krotov_b200.h,
+        # kq_sparse; numbering: terms | adjoint terms | mu)
+        cp.sparse = _csr_bundle(
+            [ops[k, m] for k in range(K) for m in range(M)]
+            + [ops_adj[k, m] for k in range(K) for m in range(M)]
+            + [mu_tab[k, l] for k in range(K) for l in range(max(L, 1))], N)
+        # the most non-zeros one CTA works with: terms + mu / terms or adjoints
+        per = np.diff(cp.sparse['mat_off'])
+        Lm = max(L, 1)
+        fw = per[:K * M].reshape(K, M).sum(axis=1)
+        bw = per[K * M:2 * K * M].reshape(K, M).sum(axis=1)
+        mu_n = per[2 * K * M:].reshape(K, Lm).sum(axis=1)
+        cp.sparse['stage_nnz_update'] = int(np.max(fw + mu_n))
+        cp.sparse['stage_nnz_prop'] = int(max(np.max(fw), np.max(bw)))
+        cp.ops = cp.ops_adj = cp.mu = None
+    else:
+        # column-major storage: element (r,c) at c*N + r
+        cp.ops = np.ascontiguousarray(np.swapaxes(ops, 2, 3))
+        cp.ops_adj = np.ascontiguousarray(np.swapaxes(ops_adj, 2, 3))
+        cp.mu = np.ascontiguousarray(np.swapaxes(mu_tab, 2, 3))
 
     cp.state_templates = [obj.initial_state for obj in objectives]
     cp.psi0 = np.array([cp.vec(obj.initial_state) for obj in objectives])
@@ -269,6 +288,61 @@ def compile_problem(objectives, controls, mapping, tlist, mu=None,
         cp.weights = np.array(
             [float(getattr(obj, 'weight', 1.0)) for obj in objectives])
     return cp
+
+
+DENSE_NMAX = 64   # largest state length the dense kernel families take
+
+
+def _csr_bundle(mats, N):
+    """CSR of a list of N x N matrices in the layout of ``kq_sparse``:
+    row_ptr [n_mat, N+1] (relative to the matrix' offset), mat_off [n_mat+1],
+    col, val; exact zeros are dropped."""
+    import scipy.sparse
+    row_ptr = np.zeros((len(mats), N + 1), dtype=np.int32)
+    mat_off = np.zeros(len(mats) + 1, dtype=np.int64)
+    cols, vals = [], []
+    for i, a in enumerate(mats):
+        c = scipy.sparse.csr_matrix(np.asarray(a, dtype=np.complex128))
+        c.eliminate_zeros()
+        c.sort_indices()
+        row_ptr[i] = c.indptr
+        mat_off[i + 1] = mat_off[i] + c.nnz
+        cols.append(c.indices.astype(np.int32))
+        vals.append(c.data.astype(np.complex128))
+    col = np.concatenate(cols) if cols else np.zeros(0, np.int32)
+    val = np.concatenate(vals) if vals else np.zeros(0, np.complex128)
+    if col.size == 0:      # keep the device arrays non-empty
+        col, val = np.zeros(1, np.int32), np.zeros(1, np.complex128)
+    out = dict(row_ptr=row_ptr, mat_off=mat_off, col=col, val=val,
+               nnz=int(mat_off[-1]), col16=None, code16=None, dict=None)
+    # dictionary coding: a Liouvillian repeats few distinct values (bit-exact
+    # comparison), so a non-zero shrinks to a 16-bit column + a 16-bit code and
+    # the matrices of one objective fit the shared memory of its CTA
+    # Codes are numbered by first appearance in the order the kernel touches the
+    # non-zeros -- matrix by matrix, the p-th entry of every row, rows (= lanes)
+    # fastest -- so that neighbouring lanes mostly read neighbouring dictionary
+    # entries (no shared-memory bank conflicts).
+    nnz_tot = int(mat_off[-1])
+    if nnz_tot > 0:
+        mat_of = np.repeat(np.arange(len(mats)), np.diff(mat_off))
+        row_of = np.concatenate([
+            np.repeat(np.arange(N), np.diff(row_ptr[i])) for i in range(len(mats))])
+        pos_of = np.arange(nnz_tot) - (mat_off[mat_of] + row_ptr[mat_of, row_of])
+        order = np.lexsort((row_of, pos_of, mat_of))
+        uniq, first, inv = np.unique(
+            val[order].view(np.float64).reshape(-1, 2), axis=0,
+            return_index=True, return_inverse=True)
+        if len(uniq) <= 65536 and N <= 65536:
+            rank = np.empty(len(uniq), dtype=np.int64)
+            rank[np.argsort(first, kind='stable')] = np.arange(len(uniq))
+            codes = np.empty(nnz_tot, dtype=np.int64)
+            codes[order] = rank[inv.ravel()]
+            table = np.empty((len(uniq), 2), dtype=np.float64)
+            table[rank] = uniq
+            out['dict'] = table.view(np.complex128).ravel()
+            out['code16'] = codes.astype(np.uint16)
+            out['col16'] = col.astype(np.uint16)
+    return out
 
 
 def _probe_mu(mu, objectives, k, pulses, mapping, l, cp):

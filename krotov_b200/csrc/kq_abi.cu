@@ -12,6 +12,7 @@
 
 #include "kq_host.cuh"
 #include "kq_dpoly_geom.cuh"
+#include "kq_csr.cuh"
 
 int g_kq_coop_launch = 1;
 int g_kq_pdl_launch = 0;
@@ -126,7 +127,7 @@ int device_init(int* dev_out) {
         kq_tables_upload_spec_fw3_re, kq_tables_upload_spec_fw4_re,
         kq_tables_upload_warp0,    kq_tables_upload_warp8,    kq_tables_upload_warp16,
         kq_tables_upload_warp32,   kq_tables_upload_picard2,  kq_tables_upload_picard3,
-        kq_tables_upload_picard4,  kq_tables_upload_dpoly};
+        kq_tables_upload_picard4,  kq_tables_upload_dpoly,    kq_tables_upload_csr};
     for (auto up : uploads) {
       const int rc = up(&T);
       if (rc) return rc;
@@ -145,8 +146,16 @@ int check_problem(const kq_problem* p) {
   if (p->K < 1 || p->N < 1 || p->NT < 1 || p->L < 0 || p->M < 1)
     return fail(KQ_ERR_ARG, "invalid sizes K=%d N=%d NT=%d L=%d M=%d", p->K, p->N, p->NT, p->L, p->M);
   if (p->L > KQ_LMAX) return fail(KQ_ERR_UNSUPPORTED, "L=%d pulses > %d", p->L, KQ_LMAX);
-  if (p->N > 64)
-    return fail(KQ_ERR_UNSUPPORTED, "state length N=%d > 64 is not built yet", p->N);
+  if (p->N > 1024)
+    return fail(KQ_ERR_UNSUPPORTED, "state length N=%d > 1024 is not built", p->N);
+  if (p->N > 64) {
+    if (!p->sparse || !p->sparse->row_ptr || !p->sparse->mat_off || !p->sparse->col || !p->sparse->val)
+      return fail(KQ_ERR_ARG, "N=%d > 64 needs the sparse form of the matrices (kq_problem.sparse)",
+                  p->N);
+    if (!p->term2pulse || !p->op_norm || !p->dt)
+      return fail(KQ_ERR_ARG, "problem has NULL time / mapping arrays");
+    return KQ_OK;
+  }
   if (!p->ops || !p->ops_adj || !p->term2pulse || !p->op_norm || !p->dt)
     return fail(KQ_ERR_ARG, "problem has NULL operator/time arrays");
   return KQ_OK;
@@ -159,6 +168,17 @@ int round_up(int v, int q) { return (v + q - 1) / q * q; }
 int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) {
   const int K = p->K, N = p->N, M = p->M, L = p->L, NN = N * N;
   std::memset(&pl, 0, sizeof pl);
+  if (N > 64) {
+    // row-per-thread CSR family (kq_csr.cuh): one CTA per objective
+    pl.family = 2;
+    pl.block = round_up(N, 32);
+    pl.grid = K;
+    pl.smem = (size_t)(2 * KQ_LMAX * 32 + 2 * KQ_LMAX + ((M + 1) & ~1)) * sizeof(double) +
+              (size_t)2 * N * sizeof(cplx);
+    (void)second;
+    (void)sms;
+    return KQ_OK;
+  }
   if (N <= 4 && M <= KQ_MMAX_SMALL) {
     pl.family = 0;
     pl.spec = (N >= 2 && M == 2 && (!update || L == 1)) ? 1 : 0;
@@ -570,6 +590,29 @@ __global__ void k_seg_chain_rows(const KqSweepArgs a, int nseg) {
   }
 }
 
+KqCsr csr_of(const kq_problem* p) {
+  KqCsr s;
+  s.row_ptr = p->sparse->row_ptr;
+  s.mat_off = reinterpret_cast<const long long*>(p->sparse->mat_off);
+  s.col = p->sparse->col;
+  s.val = reinterpret_cast<const cplx*>(p->sparse->val);
+  s.col16 = p->sparse->col16;
+  s.code16 = p->sparse->code16;
+  s.dict = reinterpret_cast<const cplx*>(p->sparse->dict);
+  s.n_dict = p->sparse->n_dict;
+  return s;
+}
+// Shared memory of the staged variant (dictionary + row pointers + packed non-zeros behind
+// the plan's base size); 0 if the matrices of one objective do not fit.
+size_t csr_stage_bytes(const kq_problem* p, bool update, size_t base) {
+  const kq_sparse* sp = p->sparse;
+  const int nnz = update ? sp->stage_nnz_update : sp->stage_nnz_prop;
+  if (!sp->col16 || !sp->code16 || !sp->dict || sp->n_dict < 1 || nnz < 1) return 0;
+  const int nloc = update ? p->M + p->L : p->M;
+  const size_t extra = (size_t)sp->n_dict * sizeof(cplx) + (size_t)nloc * (p->N + 1) * 4 + (size_t)nnz * 4;
+  return base + extra <= (size_t)220 * 1024 ? extra : 0;
+}
+
 int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_c128* state0,
              kq_c128* stateT, kq_c128* store, void* stream, int k_lo = 0, int k_cnt = -1) {
   int rc = check_problem(p);
@@ -599,6 +642,12 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   a.backward = backward ? 1 : 0;
   const int fsel = p->is_super ? 2 : (backward ? 1 : 0);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pl.family == 2) {
+    pl.grid = k_cnt;
+    const size_t extra = csr_stage_bytes(p, false, pl.smem);
+    pl.smem += extra;
+    return kq_launch_csr(a, csr_of(p), pl, fsel, false, extra > 0, st);
+  }
   if (pl.family == 0) {
     if (!pl.spec) return kq_launch_prop_small(a, pl, fsel, st);
     // time-parallel propagation: segments of seg_len steps run concurrently
@@ -677,6 +726,14 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
 // The sequential update/forward sweep kernels (one time step after the other).
 int launch_sequential_update(const kq_problem* p, const KqSweepArgs& a, const Plan& pl, int fsel,
                              bool second, cudaStream_t st) {
+  if (pl.family == 2) {
+    if (second) return fail(KQ_ERR_UNSUPPORTED, "second order is not built for N > 64");
+    if (a.world > 1) return fail(KQ_ERR_UNSUPPORTED, "N > 64 is single-GPU");
+    Plan pls = pl;
+    const size_t extra = csr_stage_bytes(p, true, pl.smem);
+    pls.smem += extra;
+    return kq_launch_csr(a, csr_of(p), pls, fsel, true, extra > 0, st);
+  }
   if (pl.family == 0) {
     if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
     if (p->real_ops && !p->is_super) {
@@ -992,7 +1049,8 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   if (rc) return rc;
   if (!guess_pulses || !opt_pulses || !X || !chi_norms || !phi0 || !g_a || !workspace)
     return fail(KQ_ERR_ARG, "NULL argument to kq_sweep_forward_update");
-  if (!p->mu || !p->shape || !p->lambda_a) return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
+  if ((!p->mu && p->N <= 64) || !p->shape || !p->lambda_a)
+    return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
   if (p->L < 1) return fail(KQ_ERR_ARG, "no pulses to update");
   const bool second = sigma != nullptr;
   if (second && !Phi0) return fail(KQ_ERR_ARG, "second order needs Phi0");
@@ -1121,7 +1179,8 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   if (rc) return rc;
   if (!guess_pulses || !opt_pulses || !phi0 || !g_a || !workspace)
     return fail(KQ_ERR_ARG, "NULL argument to kq_krotov_iteration");
-  if (!p->mu || !p->shape || !p->lambda_a) return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
+  if ((!p->mu && p->N <= 64) || !p->shape || !p->lambda_a)
+    return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
   if (chi_kind < -1 || chi_kind > KQ_CHI_HS) return fail(KQ_ERR_ARG, "unknown chi kind %d", chi_kind);
   if (chi_kind < 0 && (!chiT || !chi_norms)) return fail(KQ_ERR_ARG, "chiT/chi_norms are NULL");
   if (chi_kind >= 0 && !targets) return fail(KQ_ERR_ARG, "built-in chi needs targets");

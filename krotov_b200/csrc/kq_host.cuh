@@ -142,6 +142,7 @@ int kq_tables_upload_picard2(const KqTables* T);
 int kq_tables_upload_picard3(const KqTables* T);
 int kq_tables_upload_picard4(const KqTables* T);
 int kq_tables_upload_dpoly(const KqTables* T);
+int kq_tables_upload_csr(const KqTables* T);
 
 int kq_launch_prop_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
 int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
@@ -168,6 +169,10 @@ int kq_launch_picard3(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool sec
                             bool real, cudaStream_t st);
 int kq_launch_picard4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
                             bool real, cudaStream_t st);
+// row-per-thread CSR kernels for 64 < N <= 1024 (kq_csr.cuh)
+struct KqCsr;
+int kq_launch_csr(const KqSweepArgs& a, const KqCsr& s, const KqPlan& pl, int fsel, bool update,
+                  bool staged, cudaStream_t st);
 // delta-polynomial update sweep (kq_dpoly.cuh)
 struct KqDpoly;
 struct KqDpolyGeom {

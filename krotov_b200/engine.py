@@ -12,7 +12,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import EngineUnavailable, KqComm, KqProblem, check
+from ._lib import EngineUnavailable, KqComm, KqProblem, KqSparse, check
 
 __all__ = ['SweepEngine', 'CHI_KINDS']
 
@@ -56,9 +56,30 @@ class SweepEngine:
             self.h2d_bytes += t.numel() * t.element_size()
             return t
 
-        self.t_ops = up(cp.ops, c128)
-        self.t_ops_adj = up(cp.ops_adj, c128)
-        self.t_mu = up(cp.mu, c128)
+        self._sparse = None
+        if cp.sparse is not None:
+            # N > 64: CSR matrices (csrc/kq_csr.cuh); no dense copies
+            self.t_ops = self.t_ops_adj = self.t_mu = None
+            sp = cp.sparse
+            self.t_csr = [up(sp['row_ptr'], torch.int32),
+                          up(sp['mat_off'], torch.int64),
+                          up(sp['col'], torch.int32), up(sp['val'], c128)]
+            coded = sp['dict'] is not None
+            if coded:
+                # uint16 arrays travel as int16 bit patterns
+                self.t_csr += [
+                    up(sp['col16'].view(np.int16), torch.int16),
+                    up(sp['code16'].view(np.int16), torch.int16),
+                    up(sp['dict'], c128)]
+            ptrs = [t.data_ptr() for t in self.t_csr] + [0] * (
+                0 if coded else 3)
+            self._sparse = KqSparse(
+                *ptrs, len(sp['dict']) if coded else 0,
+                sp['stage_nnz_update'], sp['stage_nnz_prop'])
+        else:
+            self.t_ops = up(cp.ops, c128)
+            self.t_ops_adj = up(cp.ops_adj, c128)
+            self.t_mu = up(cp.mu, c128)
         self.t_t2p = up(cp.term2pulse, torch.int32)
         self.t_opn = up(cp.op_norm, f64)
         self.t_dt = up(cp.dt, f64)
@@ -88,12 +109,16 @@ class SweepEngine:
         self.problem = KqProblem(
             K=cp.K, N=cp.N, NT=cp.NT, L=cp.L, M=cp.M,
             is_super=1 if cp.is_super else 0,
-            ops=self.t_ops.data_ptr(), ops_adj=self.t_ops_adj.data_ptr(),
-            mu=self.t_mu.data_ptr(), term2pulse=self.t_t2p.data_ptr(),
+            ops=0 if self.t_ops is None else self.t_ops.data_ptr(),
+            ops_adj=0 if self.t_ops_adj is None else self.t_ops_adj.data_ptr(),
+            mu=0 if self.t_mu is None else self.t_mu.data_ptr(),
+            term2pulse=self.t_t2p.data_ptr(),
             op_norm=self.t_opn.data_ptr(), dt=self.t_dt.data_ptr(),
             shape=self.t_shape.data_ptr(), lambda_a=self.t_lambda.data_ptr(),
             real_ops=1 if cp.real_ops else 0, reserved=0,
-            update_sweep=update_sweep, reserved2=0)
+            update_sweep=update_sweep, reserved2=0,
+            sparse=0 if self._sparse is None else ctypes.addressof(
+                self._sparse))
         self._p = ctypes.byref(self.problem)
         nbytes = self.lib.kq_workspace_bytes(self._p)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
@@ -270,7 +295,7 @@ class SweepEngine:
         # do not cover: N <= 4 runs the time-parallel fixed-point kernel, few
         # objectives with N >= 3 the delta-polynomial sweep (csrc/kq_dpoly.cuh)
         return (self.gather is None and cp.M == 2 and cp.L == 1
-                and cp.N >= 2)
+                and 2 <= cp.N <= 16)
 
     def clear_fused_failure(self):
         """Reset the 'first failed epoch' status word."""

@@ -393,6 +393,63 @@ def tls_shared_controls(nt=100, T=2.0):
     )
 
 
+# --- large Liouville space (notebook 06) ------------------------------------
+
+def two_transmon_gate(n_qubit=5, nt=2000, T=400.0, lambda_a=1.0):
+    """Two coupled transmons with decay and dephasing in Liouville space, after
+    docs/notebooks/06_example_3states.ipynb of the reference (cells 5-32):
+    density matrices (n_qubit^2) x (n_qubit^2) -- super-operators 625 x 625
+    for the notebook's n_qubit = 5 -- two real controls (the second one starts
+    at zero), the three states of ``liouville_states_set='3states'`` as
+    objectives, sqrt(iSWAP) as the target gate, ``chis_re``.  Units: GHz / ns
+    with 2 pi folded into the frequencies."""
+    from .objectives import gate_objectives, liouvillian
+    GHz, MHz, ns = 2 * np.pi, 2 * np.pi * 1e-3, 1.0
+    w1, w2, wd = 4.3796 * GHz, 4.6137 * GHz, 4.4985 * GHz
+    d1, d2, J = -239.3 * MHz, -242.8 * MHz, -2.3 * MHz
+    q1T1, q2T1, q1T2, q2T2 = 38.0e3 * ns, 32.0e3 * ns, 29.5e3 * ns, 16.0e3 * ns
+    n = n_qubit
+    b = np.diag(np.sqrt(np.arange(1, n)), 1).astype(np.complex128)
+    I = np.identity(n)
+    b1, b2 = np.kron(I, b), np.kron(b, I)
+    n1, n2 = b1.conj().T @ b1, b2.conj().T @ b2
+    H0 = ((w1 - wd - d1 / 2) * n1 + (d1 / 2) * n1 @ n1
+          + (w2 - wd - d2 / 2) * n2 + (d2 / 2) * n2 @ n2
+          + J * (b1.conj().T @ b2 + b1 @ b2.conj().T))
+    H1_re = 0.5 * (b1 + b1.conj().T + b2 + b2.conj().T)
+    H1_im = 0.5j * (b1.conj().T - b1 + b2.conj().T - b2)
+    S = partial(shapes.flattop, t_start=0, t_stop=T, t_rise=20 * ns,
+                t_fall=20 * ns, func='sinsq')
+    omega = lambda t, args: 35.0 * MHz * S(t)  # noqa: E731
+    zero = lambda t, args: 0.0  # noqa: E731
+    c_ops = [np.sqrt(1 / q1T1) * b1, np.sqrt(1 / q2T1) * b2,
+             np.sqrt(1 / q1T2) * n1, np.sqrt(1 / q2T2) * n2]
+    L = liouvillian([H0, [H1_re, omega], [H1_im, zero]], c_ops)
+
+    def ket(i, j):
+        v = np.zeros((n * n, 1), dtype=np.complex128)
+        v[i * n + j] = 1.0
+        return v
+    basis = [ket(0, 0), ket(0, 1), ket(1, 0), ket(1, 1)]
+    sqrt_iswap = np.array([[1, 0, 0, 0],
+                           [0, 1 / np.sqrt(2), 1j / np.sqrt(2), 0],
+                           [0, 1j / np.sqrt(2), 1 / np.sqrt(2), 0],
+                           [0, 0, 0, 1]], dtype=np.complex128)
+    weights = np.array([20, 1, 1], dtype=np.float64)
+    weights *= len(weights) / np.sum(weights)
+    objs = gate_objectives(basis, sqrt_iswap, L, liouville_states_set='3states',
+                           weights=weights, normalize_weights=False)
+    return Workload(
+        name='two_transmon_gate_N%d' % (n * n) ** 2,
+        Hs=[o.H for o in objs], initial_states=[o.initial_state for o in objs],
+        targets=[o.target for o in objs],
+        pulse_options={omega: dict(lambda_a=lambda_a, update_shape=S),
+                       zero: dict(lambda_a=lambda_a, update_shape=S)},
+        tlist=np.linspace(0, T, nt), chi='re', is_super=True,
+        weights=[float(o.weight) for o in objs],
+    )
+
+
 def by_name(name, **kwargs):
     """Workload from its BASELINE label ('C1'..'C5')."""
     table = {

@@ -110,10 +110,11 @@ def run_reference(wl, iters, path, keep_states, sigma=None, modify=None):
     krotov.Objective.type_checking = (path == 'qobj')
     wrap = (lambda a: qutip.Qobj(a)) if path == 'qobj' else None
     if wl.is_super and path == 'qobj':
+        d = wl.initial_states[0].shape[0]
+
         def wrap(a):  # noqa: F811
-            d2 = a.shape[0]
-            if a.shape == (16, 16):
-                return qutip.Qobj(a, dims=[[[4], [4]], [[4], [4]]])
+            if a.shape == (d * d, d * d) and d > 1:
+                return qutip.Qobj(a, dims=[[[d], [d]], [[d], [d]]])
             return qutip.Qobj(a)
     objectives = wl.objectives(krotov.Objective, wrap=wrap)
     if wl.chi == 'qubit_reset':
@@ -312,9 +313,23 @@ def case_infohook_kat():
          g_a=np.array(rec.g_a))
 
 
+def case_large_liouville():
+    """Row f3: the two-transmon Liouville problem of notebook 06 (three
+    weighted objectives, two controls, chis_re) with three levels per transmon
+    (super-operators 81 x 81) and with the notebook's five (625 x 625) on a
+    short grid."""
+    wl = workloads.two_transmon_gate(n_qubit=3, nt=60, T=12.0)
+    save('two_transmon_N81_qobj', **run_reference(wl, 2, 'qobj',
+                                                   keep_states=True))
+    wl = workloads.two_transmon_gate(n_qubit=5, nt=9, T=1.8)
+    save('two_transmon_N625_qobj', **run_reference(wl, 1, 'qobj',
+                                                    keep_states=False))
+
+
 CASES = dict(tls_fixture=case_tls_fixture, c1=case_c1, c2=case_c2,
              c3=case_c3, c4=case_c4, c5=case_c5, kat=case_infohook_kat,
-             multi=case_multi_control, full=case_full_size)
+             multi=case_multi_control, full=case_full_size,
+             large=case_large_liouville)
 
 if __name__ == '__main__':
     names = sys.argv[1:] or list(CASES)
