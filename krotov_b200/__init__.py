@@ -12,8 +12,8 @@ There is no CPU fallback: without the built library and a CUDA device
 ``optimize_pulses`` raises :class:`EngineUnavailable`.  See DESIGN.md.
 """
 from . import (conversions, convergence, functionals, info_hooks, mu,  # noqa
-               objectives, propagators, result, second_order, shapes,
-               workloads)
+               objectives, perfect_entanglers, propagators, result,
+               second_order, shapes, workloads)
 from ._lib import EngineUnavailable, KqError  # noqa: F401
 from .objectives import (Objective, ensemble_objectives,  # noqa: F401
                          gate_objectives, liouvillian)
@@ -25,6 +25,7 @@ __version__ = '0.1.0'
 __all__ = [
     'Objective', 'Result', 'conversions', 'convergence', 'ensemble_objectives',
     'functionals', 'gate_objectives', 'info_hooks', 'liouvillian', 'mu',
-    'objectives', 'optimize_pulses', 'propagators', 'result', 'second_order',
+    'objectives', 'optimize_pulses', 'perfect_entanglers', 'propagators',
+    'result', 'second_order',
     'shapes', 'workloads', 'EngineUnavailable', 'KqError',
 ]

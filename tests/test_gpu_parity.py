@@ -417,6 +417,62 @@ def test_large_liouville_csr_family(krotov, golden):
         assert rel(rec_u.pulses[it], rec.pulses[it]) < 1e-13
 
 
+# ---- row f4: perfect-entangler functional (notebook 07) -----------------------
+
+def test_perfect_entangler_optimisation(krotov):
+    """Notebook 07 through the engine: gate_objectives(basis, 'PE', H) (targets
+    are the string 'PE': no tau), krotov_b200.perfect_entanglers'
+    chi_constructor as a host callback, second order with A re-estimated from
+    Delta F_PE after every iteration (cell 30).  Pulses against the oracle
+    driven by the same functional, iteration by iteration; F_PE of the guess as
+    printed by the notebook; a perfect entangler after 8 iterations."""
+    from test_oracle import run_pe_oracle
+    from krotov_b200 import perfect_entanglers as pe
+    wl, rec, F_orc = run_pe_oracle(8)
+    basis = [np.eye(4, dtype=complex)[:, [i]] for i in range(4)]
+    H = wl.Hs[0]
+    objectives = krotov.gate_objectives(basis, 'PE', H)
+    assert all(o.target == 'PE' for o in objectives)
+    chi_constructor = pe.make_PE_krotov_chi_constructor(basis)
+
+    def print_fidelity(**args):
+        U = pe.gate(basis, args['fw_states_T'])
+        assert np.all(np.asarray(args['tau_vals']) == None)  # noqa: E711
+        return pe.F_PE(*pe.g1g2g3(U)), None
+
+    class Sigma(krotov.second_order.Sigma):
+        def __init__(self, A):
+            self.A = A
+
+        def __call__(self, t):
+            return -max(0.0, 2 * self.A)
+
+        def refresh(self, forward_states, forward_states0, chi_states,
+                    chi_norms, optimized_pulses, guess_pulses, objectives,
+                    result):
+            try:
+                dJ = result.info_vals[-1][0] - result.info_vals[-2][0]
+            except IndexError:
+                dJ = 0
+            self.A = krotov.second_order.numerical_estimate_A(
+                forward_states, forward_states0, chi_states, chi_norms, dJ)
+
+    res = krotov.optimize_pulses(
+        objectives, wl.pulse_options, wl.tlist,
+        propagator=krotov.propagators.expm, chi_constructor=chi_constructor,
+        info_hook=print_fidelity, sigma=Sigma(0.0), iter_stop=8,
+        check_convergence=lambda r: ("achieved perfect entangler"
+                                     if r.info_vals[-1][0] <= 0 else None),
+        store_all_pulses=True)
+    F = [v[0] for v in res.info_vals]
+    assert '%.6f' % F[0] == '1.447335'
+    assert "perfect entangler" in res.message and len(F) == 9
+    assert F[7] > 0 > F[8]
+    for it in range(1, 9):
+        assert rel(res.all_pulses[it], rec[it]['optimized_pulses']) < PULSE_RTOL
+        assert abs(F[it] - F_orc[it]) < 1e-9
+
+
 # ---- continuation (optimize.py:707-803, tests/test_krotov.py:166-432) --------
 
 def test_continue_from_dumped_result(krotov, tmp_path):

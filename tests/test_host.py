@@ -490,3 +490,48 @@ def test_print_table_api_matches_reference():
     hook(iteration=4, g_a_integrals=np.array([0.1]), guess_pulses=[None],
          iter_stop=10, start_time=0.0, stop_time=0.0, info_vals=[0.75])
     assert "-2.50e-01  -1.50e-01" in out.getvalue()
+
+
+def test_perfect_entangler_functional():
+    """krotov_b200.perfect_entanglers (restatement of what notebook 07 takes
+    from the absent `weylchamber`): local invariants of known gates, F_PE of
+    notebook 07's guess (cell 39: 1.447335), Wirtinger gradient against
+    central differences, chi constructor = -dF/d<phi| in the Bell basis of
+    gate_objectives(..., 'PE')."""
+    from krotov_b200 import perfect_entanglers as pe
+    import krotov_b200 as krotov
+    cnot = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]])
+    swap = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])
+    for U, want in ((np.eye(4), (1, 0, 3)), (cnot, (0, 0, 1)),
+                    (swap, (-1, 0, -3)),
+                    (np.exp(0.7j) * cnot, (0, 0, 1))):    # any global phase
+        assert np.allclose(pe.g1g2g3(U), want, atol=1e-14)
+    assert abs(pe.F_PE(*pe.g1g2g3(cnot))) < 1e-14
+    rng = np.random.default_rng(3)
+    q, _ = np.linalg.qr(rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))
+    a = q + 0.05 * (rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4)))
+    F, dFc = pe.F_PE_gradient(a)
+
+    def F_of(b):
+        return pe.F_PE_gradient(b)[0]
+    h = 1e-6
+    for k in range(4):
+        for l in range(4):
+            e = np.zeros((4, 4), dtype=complex)
+            e[k, l] = 1
+            num = 0.5 * ((F_of(a + h * e) - F_of(a - h * e)) / (2 * h)
+                         + 1j * (F_of(a + 1j * h * e) - F_of(a - 1j * h * e))
+                         / (2 * h))
+            assert abs(num - dFc[k, l]) < 1e-9
+    # Bell basis of the objectives = columns of MAGIC; chi = -dF/d<phi|
+    basis = [np.eye(4, dtype=complex)[:, [i]] for i in range(4)]
+    objs = krotov.gate_objectives(basis, 'PE', [np.eye(4)])
+    bell = np.array([o.initial_state.ravel() for o in objs])
+    assert np.allclose(bell, pe.MAGIC.T)
+    states = [(q @ b.reshape(4, 1)) for b in bell]
+    chis = pe.make_PE_krotov_chi_constructor(basis)(states, objs, None)
+    a_q = bell.conj() @ np.array([s.ravel() for s in states]).T
+    _, d = pe.F_PE_gradient(a_q)
+    for l in range(4):
+        assert chis[l].shape == (4, 1)
+        assert np.allclose(chis[l].ravel(), -(d[:, l] @ bell))
