@@ -45,7 +45,7 @@ import numpy as np
 
 from ._dense import dense
 
-__all__ = ['gate', 'to_magic', 'g1g2g3', 'F_PE', 'F_PE_gradient',
+__all__ = ['gate', 'to_magic', 'from_magic', 'g1g2g3', 'F_PE', 'F_PE_gradient',
            'make_PE_krotov_chi_constructor']
 
 # columns = the Bell states of objectives.py:1044-1047 in the canonical basis
@@ -69,6 +69,11 @@ def gate(basis, states):
 def to_magic(U):
     """Q^dag U Q: the gate in the Bell basis."""
     return MAGIC.conj().T @ np.asarray(U, dtype=np.complex128) @ MAGIC
+
+
+def from_magic(UB):
+    """Q UB Q^dag: a gate given in the Bell basis, back in the canonical one."""
+    return MAGIC @ np.asarray(UB, dtype=np.complex128) @ MAGIC.conj().T
 
 
 def _invariants(a):
