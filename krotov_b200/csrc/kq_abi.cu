@@ -67,8 +67,10 @@ int g_picard = 1;                  // kq_set_option("picard", 0|1|2): off / auto
 int g_picard_timing = 0;
 int g_picard_history = 1;          // kq_set_option("picard_history", 0|1): update-history hint
 int g_picard_maxit = 64;           // kq_set_option("picard_maxit", n)
+int g_picard_rtol_e15 = 20;        // kq_set_option("picard_rtol_e15", v): fixed point accepted at v * 1e-15
 int g_dpoly = 1;                   // kq_set_option("dpoly", 0|1|2): off / auto / wherever it fits
-int g_dpoly_debug = 0;             // kq_set_option("dpoly_debug", 1): no sequential kernel behind it
+int g_dpoly_debug = 0;
+int g_small_rows = 0;               // kq_set_option("small_rows", 0): thread-per-objective kernels for few generic objectives too             // kq_set_option("dpoly_debug", 1): no sequential kernel behind it
 constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
 constexpr int kPicMaxItCap = 1000;
 constexpr int kPicMaxWindows = 64;   // time windows of one windowed update sweep
@@ -148,7 +150,7 @@ int check_problem(const kq_problem* p) {
   if (p->L > KQ_LMAX) return fail(KQ_ERR_UNSUPPORTED, "L=%d pulses > %d", p->L, KQ_LMAX);
   if (p->N > 1024)
     return fail(KQ_ERR_UNSUPPORTED, "state length N=%d > 1024 is not built", p->N);
-  if (p->N > 64) {
+  if (p->N > 64 || (p->sparse && !p->ops)) {
     if (!p->sparse || !p->sparse->row_ptr || !p->sparse->mat_off || !p->sparse->col || !p->sparse->val)
       return fail(KQ_ERR_ARG, "N=%d > 64 needs the sparse form of the matrices (kq_problem.sparse)",
                   p->N);
@@ -168,7 +170,7 @@ int round_up(int v, int q) { return (v + q - 1) / q * q; }
 int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) {
   const int K = p->K, N = p->N, M = p->M, L = p->L, NN = N * N;
   std::memset(&pl, 0, sizeof pl);
-  if (N > 64) {
+  if (N > 64 || (p->sparse && !p->ops)) {
     // row-per-thread CSR family (kq_csr.cuh): one CTA per objective
     pl.family = 2;
     pl.block = round_up(N, 32);
@@ -179,7 +181,11 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
     (void)sms;
     return KQ_OK;
   }
-  if (N <= 4 && M <= KQ_MMAX_SMALL) {
+  // Few objectives with several terms / controls (the Lambda systems of notebooks 02/03/08:
+  // K = 1..5, N = 3, four controls): the thread-per-objective kernels would run one thread
+  // per CTA; the lane-per-row family spreads rows and keeps its row of A in registers.
+  const bool few_generic = (N <= 4 && !(M == 2 && (!update || L == 1)) && K <= 8 && g_small_rows);
+  if (N <= 4 && M <= KQ_MMAX_SMALL && !few_generic) {
     pl.family = 0;
     pl.spec = (N >= 2 && M == 2 && (!update || L == 1)) ? 1 : 0;
     size_t per_thread = (size_t)(M + (update ? L : 0)) * NN * sizeof(cplx);
@@ -458,7 +464,7 @@ int launch_picard(const kq_problem* p, KqSweepArgs b, const PicPlan& pp, void* w
   b.pic_lwc = pp.lwc;
   b.pic_stride = pp.stride;
   b.pic_maxit = std::min(g_picard_maxit, p->NT + 1);
-  b.pic_rtol = 2e-14;
+  b.pic_rtol = (double)g_picard_rtol_e15 * 1e-15;
   b.pic_timing = g_picard_timing;
   // one tag range per (call, time window)
   b.tag_base = (epoch * (uint32_t)kPicMaxWindows + (uint32_t)window) * (uint32_t)(kPicMaxItCap + 2);
@@ -903,8 +909,17 @@ int kq_set_option(const char* name, int value) {
     g_dpoly_debug = value ? 1 : 0;
     return KQ_OK;
   }
+  if (name && std::strcmp(name, "small_rows") == 0) {
+    g_small_rows = value ? 1 : 0;
+    return KQ_OK;
+  }
   if (name && std::strcmp(name, "picard_history") == 0) {
     g_picard_history = value ? 1 : 0;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "picard_rtol_e15") == 0) {
+    if (value < 1 || value > 1000000) return fail(KQ_ERR_ARG, "picard_rtol_e15 out of range");
+    g_picard_rtol_e15 = value;
     return KQ_OK;
   }
   if (name && std::strcmp(name, "picard_maxit") == 0) {
@@ -1049,7 +1064,7 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses, dou
   if (rc) return rc;
   if (!guess_pulses || !opt_pulses || !X || !chi_norms || !phi0 || !g_a || !workspace)
     return fail(KQ_ERR_ARG, "NULL argument to kq_sweep_forward_update");
-  if ((!p->mu && p->N <= 64) || !p->shape || !p->lambda_a)
+  if ((!p->mu && !p->sparse) || !p->shape || !p->lambda_a)
     return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
   if (p->L < 1) return fail(KQ_ERR_ARG, "no pulses to update");
   const bool second = sigma != nullptr;
@@ -1179,7 +1194,7 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   if (rc) return rc;
   if (!guess_pulses || !opt_pulses || !phi0 || !g_a || !workspace)
     return fail(KQ_ERR_ARG, "NULL argument to kq_krotov_iteration");
-  if ((!p->mu && p->N <= 64) || !p->shape || !p->lambda_a)
+  if ((!p->mu && !p->sparse) || !p->shape || !p->lambda_a)
     return fail(KQ_ERR_ARG, "problem lacks mu/shape/lambda_a");
   if (chi_kind < -1 || chi_kind > KQ_CHI_HS) return fail(KQ_ERR_ARG, "unknown chi kind %d", chi_kind);
   if (chi_kind < 0 && (!chiT || !chi_norms)) return fail(KQ_ERR_ARG, "chiT/chi_norms are NULL");
