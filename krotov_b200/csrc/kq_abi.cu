@@ -13,6 +13,7 @@
 #include "kq_host.cuh"
 #include "kq_dpoly_geom.cuh"
 #include "kq_csr.cuh"
+#include "kq_lanes_geom.cuh"
 
 int g_kq_coop_launch = 1;
 int g_kq_pdl_launch = 0;
@@ -61,7 +62,8 @@ struct Scratch {
   void* ptr = nullptr;
   size_t bytes = 0;
 };
-Scratch g_scratch[kMaxDevices][2];   // slot 0: time-parallel propagation, 1: dpoly records
+Scratch g_scratch[kMaxDevices][3];   // slot 0: time-parallel propagation, 1: dpoly records,
+                                     // 2: records of the one-warp update sweep (kq_lanes.cuh)
 bool g_disable_segments = false;   // kq_set_option("time_parallel", 0)
 int g_picard = 1;                  // kq_set_option("picard", 0|1|2): off / auto / forced
 int g_picard_timing = 0;
@@ -70,6 +72,7 @@ int g_picard_maxit = 64;           // kq_set_option("picard_maxit", n)
 int g_picard_rtol_e15 = 20;        // kq_set_option("picard_rtol_e15", v): fixed point accepted at v * 1e-15
 int g_dpoly = 1;                   // kq_set_option("dpoly", 0|1|2): off / auto / wherever it fits
 int g_dpoly_debug = 0;
+int g_lanes = 1;                    // kq_set_option("lanes", 0): without the one-warp update sweep (kq_lanes.cuh)
 int g_small_rows = 0;               // kq_set_option("small_rows", 0): thread-per-objective kernels for few generic objectives too             // kq_set_option("dpoly_debug", 1): no sequential kernel behind it
 constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
 constexpr int kPicMaxItCap = 1000;
@@ -129,7 +132,8 @@ int device_init(int* dev_out) {
         kq_tables_upload_spec_fw3_re, kq_tables_upload_spec_fw4_re,
         kq_tables_upload_warp0,    kq_tables_upload_warp8,    kq_tables_upload_warp16,
         kq_tables_upload_warp32,   kq_tables_upload_picard2,  kq_tables_upload_picard3,
-        kq_tables_upload_picard4,  kq_tables_upload_dpoly,    kq_tables_upload_csr};
+        kq_tables_upload_picard4,  kq_tables_upload_dpoly,    kq_tables_upload_csr,
+        kq_tables_upload_lanes};
     for (auto up : uploads) {
       const int rc = up(&T);
       if (rc) return rc;
@@ -167,7 +171,8 @@ int round_up(int v, int q) { return (v + q - 1) / q * q; }
 
 // update = fused sweep (objectives should share a CTA); otherwise spread
 // independent objectives over the SMs.
-int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) {
+int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl,
+              bool force_rows = false) {
   const int K = p->K, N = p->N, M = p->M, L = p->L, NN = N * N;
   std::memset(&pl, 0, sizeof pl);
   if (N > 64 || (p->sparse && !p->ops)) {
@@ -184,7 +189,8 @@ int make_plan(const kq_problem* p, bool update, bool second, int sms, Plan& pl) 
   // Few objectives with several terms / controls (the Lambda systems of notebooks 02/03/08:
   // K = 1..5, N = 3, four controls): the thread-per-objective kernels would run one thread
   // per CTA; the lane-per-row family spreads rows and keeps its row of A in registers.
-  const bool few_generic = (N <= 4 && !(M == 2 && (!update || L == 1)) && K <= 8 && g_small_rows);
+  const bool few_generic =
+      force_rows || (N <= 4 && !(M == 2 && (!update || L == 1)) && K <= 8 && g_small_rows);
   if (N <= 4 && M <= KQ_MMAX_SMALL && !few_generic) {
     pl.family = 0;
     pl.spec = (N >= 2 && M == 2 && (!update || L == 1)) ? 1 : 0;
@@ -654,6 +660,16 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
     pl.smem += extra;
     return kq_launch_csr(a, csr_of(p), pl, fsel, false, extra > 0, st);
   }
+  // few generic objectives (several terms): the thread-per-objective kernel would walk
+  // through the grid with one thread; the lane-per-row family propagates segments of the
+  // grid concurrently instead
+  bool rows = false;
+  if (pl.family == 0 && !pl.spec && g_lanes && p->N >= 2 && k_cnt * (p->N + 1) <= 64 &&
+      p->NT >= 64 && !g_disable_segments) {
+    rows = true;
+    rc = make_plan(&sub, false, false, g_dev[dev].sms, pl, true);
+    if (rc) return rc;
+  }
   if (pl.family == 0) {
     if (!pl.spec) return kq_launch_prop_small(a, pl, fsel, st);
     // time-parallel propagation: segments of seg_len steps run concurrently
@@ -678,12 +694,12 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   // the segmented sweep does N + 1 times the work)
   Plan plmax;                    // the largest CTA the kernels take: tasks per wave
   sub.K = 1 << 20;
-  rc = make_plan(&sub, false, false, g_dev[dev].sms, plmax);
+  rc = make_plan(&sub, false, false, g_dev[dev].sms, plmax, rows);
   if (rc) return rc;
   const int capacity = g_dev[dev].sms * (plmax.block / 32) * plmax.geom.G;
   int nseg = 1;
   if (!g_disable_segments && p->NT >= 64)
-    nseg = std::min(128, std::min(p->NT / 16, capacity / (k_cnt * (p->N + 1))));
+    nseg = std::min(128, std::min(p->NT / (rows ? 8 : 16), capacity / (k_cnt * (p->N + 1))));
   if (nseg < 4) return launch_warp(a, pl, fsel, false, false, st);
   a.seg_len = (p->NT + nseg - 1) / nseg;
   nseg = (p->NT + a.seg_len - 1) / a.seg_len;
@@ -703,7 +719,7 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   a1.stateT = nullptr;
   Plan pl1;
   sub.K = k_cnt * nseg * p->N;
-  rc = make_plan(&sub, false, false, g_dev[dev].sms, pl1);
+  rc = make_plan(&sub, false, false, g_dev[dev].sms, pl1, rows);
   if (rc) return rc;
   rc = launch_warp(a1, pl1, fsel, false, false, st);
   if (rc) return rc;
@@ -724,9 +740,26 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   a2.seg_pass = 2;
   Plan pl2;
   sub.K = k_cnt * nseg;
-  rc = make_plan(&sub, false, false, g_dev[dev].sms, pl2);
+  rc = make_plan(&sub, false, false, g_dev[dev].sms, pl2, rows);
   if (rc) return rc;
   return launch_warp(a2, pl2, fsel, false, false, st);
+}
+
+// One warp, lane = (objective, row): few objectives with several controls or terms
+// (kq_lanes.cuh); first order, one GPU.
+bool lanes_plan(const kq_problem* p, const KqSweepArgs& a, KqLanes& ln) {
+  if (!g_lanes || a.world > 1 || p->N < 2 || p->N > 4 || p->L < 1 || p->L > KQ_LN_LMAX ||
+      p->M > KQ_MMAX_SMALL)
+    return false;
+  const int NP = p->N == 3 ? 4 : p->N;
+  if ((long long)p->K * NP > 32) return false;
+  int span = 1;
+  while (span < p->K * NP) span <<= 1;
+  ln.NP = NP;
+  ln.span = span;
+  ln.zeta = nullptr;
+  ln.scal = nullptr;
+  return true;
 }
 
 // The sequential update/forward sweep kernels (one time step after the other).
@@ -741,7 +774,21 @@ int launch_sequential_update(const kq_problem* p, const KqSweepArgs& a, const Pl
     return kq_launch_csr(a, csr_of(p), pls, fsel, true, extra > 0, st);
   }
   if (pl.family == 0) {
-    if (!pl.spec) return kq_launch_fwupd_small(a, pl, fsel, second, st);
+    if (!pl.spec) {
+      KqLanes ln;
+      if (!second && lanes_plan(p, a, ln)) {
+        int dev = 0;
+        KQ_CUDA(cudaGetDevice(&dev));
+        const size_t zb = ((size_t)p->NT * p->L * 32 * sizeof(cplx) + 255) / 256 * 256;
+        void* base = nullptr;
+        const int rc = get_scratch(dev, zb + (size_t)p->NT * KQ_LN_SC * sizeof(double), &base, 2);
+        if (rc) return rc;
+        ln.zeta = reinterpret_cast<cplx*>(base);
+        ln.scal = reinterpret_cast<double*>(static_cast<char*>(base) + zb);
+        return kq_launch_lanes(a, ln, fsel, st);
+      }
+      return kq_launch_fwupd_small(a, pl, fsel, second, st);
+    }
     if (p->real_ops && !p->is_super) {
       switch (p->N) {
         case 2: return kq_launch_fwupd_spec2_re(a, pl, fsel, second, st);
@@ -907,6 +954,10 @@ int kq_set_option(const char* name, int value) {
   }
   if (name && std::strcmp(name, "dpoly_debug") == 0) {
     g_dpoly_debug = value ? 1 : 0;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "lanes") == 0) {
+    g_lanes = value ? 1 : 0;
     return KQ_OK;
   }
   if (name && std::strcmp(name, "small_rows") == 0) {

@@ -143,6 +143,7 @@ int kq_tables_upload_picard3(const KqTables* T);
 int kq_tables_upload_picard4(const KqTables* T);
 int kq_tables_upload_dpoly(const KqTables* T);
 int kq_tables_upload_csr(const KqTables* T);
+int kq_tables_upload_lanes(const KqTables* T);
 
 int kq_launch_prop_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
 int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
@@ -173,6 +174,10 @@ int kq_launch_picard4(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool sec
 struct KqCsr;
 int kq_launch_csr(const KqSweepArgs& a, const KqCsr& s, const KqPlan& pl, int fsel, bool update,
                   bool staged, cudaStream_t st);
+// one-warp update sweep for few objectives with several controls (kq_lanes.cuh):
+// pre-pass + chain
+struct KqLanes;
+int kq_launch_lanes(const KqSweepArgs& a, const KqLanes& d, int fsel, cudaStream_t st);
 // delta-polynomial update sweep (kq_dpoly.cuh)
 struct KqDpoly;
 struct KqDpolyGeom {

@@ -18,7 +18,10 @@ CASES = [
     ('transmon_xgate N=17 (nb 05: K=2, nt=1000)', lambda: W.transmon_xgate(nstates=8, nt=1000)),
 ]
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+only = sys.argv[2] if len(sys.argv) > 2 else ''   # substring filter on the case name
 for name, make in CASES:
+    if only not in name:
+        continue
     wl = make()
     chi = getattr(krotov.functionals, 'chis_' + wl.chi)
     def run(n):
