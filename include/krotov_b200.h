@@ -105,8 +105,8 @@ typedef struct {
   const double*  dt;
   const double*  shape;
   const double*  lambda_a;
-  int32_t real_ops;   /* 1: every matrix in ops/ops_adj has zero imaginary part
-                         (real Hamiltonians): kernels use the purely imaginary
+  int32_t real_ops;   /* 1: every matrix in ops/ops_adj AND mu has zero imaginary
+                         part (real Hamiltonians): kernels use the purely imaginary
                          form of f*A in Hilbert space; 0: general complex */
   int32_t reserved;   /* kq_sweep_forward_update: number of time windows of the
                          time-parallel update sweep (0 = as few as fit shared memory) */

@@ -248,6 +248,8 @@ def compile_problem(objectives, controls, mapping, tlist, mu=None,
         else:
             for l, op in terms:
                 mu_tab[k, l] = (1j * op) if is_super else op
+    # (a custom mu with imaginary parts takes the problem out of the real family)
+    cp.real_ops = cp.real_ops and bool(np.all(mu_tab.imag == 0.0))
     # sparse generators beyond the delta-polynomial family's reach (N > 16, e.g. the
     # 17-level transmon of notebook 05: tridiagonal drive, diagonal drift) also go
     # through the CSR kernels: a handful of non-zeros per row instead of N

@@ -73,6 +73,7 @@ int g_picard_rtol_e15 = 20;        // kq_set_option("picard_rtol_e15", v): fixed
 int g_dpoly = 1;                   // kq_set_option("dpoly", 0|1|2): off / auto / wherever it fits
 int g_dpoly_debug = 0;
 int g_lanes = 1;                    // kq_set_option("lanes", 0): without the one-warp update sweep (kq_lanes.cuh)
+int g_sat = 1;                      // kq_set_option("sat", 0): without the many-objective update sweep (kq_sat.cuh)
 int g_small_rows = 0;               // kq_set_option("small_rows", 0): thread-per-objective kernels for few generic objectives too             // kq_set_option("dpoly_debug", 1): no sequential kernel behind it
 constexpr int kPicMaxBlocks = 148;   // CTAs of the time-parallel fused sweep (one per SM)
 constexpr int kPicMaxItCap = 1000;
@@ -133,7 +134,7 @@ int device_init(int* dev_out) {
         kq_tables_upload_warp0,    kq_tables_upload_warp8,    kq_tables_upload_warp16,
         kq_tables_upload_warp32,   kq_tables_upload_picard2,  kq_tables_upload_picard3,
         kq_tables_upload_picard4,  kq_tables_upload_dpoly,    kq_tables_upload_csr,
-        kq_tables_upload_lanes};
+        kq_tables_upload_lanes,    kq_tables_upload_sat};
     for (auto up : uploads) {
       const int rc = up(&T);
       if (rc) return rc;
@@ -674,8 +675,10 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
     if (!pl.spec) return kq_launch_prop_small(a, pl, fsel, st);
     // time-parallel propagation: segments of seg_len steps run concurrently
     // (pass 1: segment propagators, chain, pass 2: states), SURVEY.md §5.7
+    // (with many objectives the sweep is bound by throughput, not by the chain: segments would
+    // only multiply the work by N + 1)
     int nseg = 1;
-    if (p->NT >= 64 && !g_disable_segments) {
+    if (p->NT >= 64 && !g_disable_segments && k_cnt <= 16384) {
       a.seg_len = std::max(16, (p->NT + 63) / 64);
       nseg = (p->NT + a.seg_len - 1) / a.seg_len;
       const size_t nP = (size_t)nseg * p->K * p->N * p->N, nB = (size_t)(nseg + 1) * p->K * p->N;
@@ -790,6 +793,17 @@ int launch_sequential_update(const kq_problem* p, const KqSweepArgs& a, const Pl
       return kq_launch_fwupd_small(a, pl, fsel, second, st);
     }
     if (p->real_ops && !p->is_super) {
+      // many two-level objectives (more than one CTA of the sequential kernel holds): the
+      // kernel built around the grid-wide reduction (kq_sat.cuh)
+      if (g_sat && p->N == 2 && !second && a.world == 1 && pl.grid > 1) {
+        int dev = 0;
+        KQ_CUDA(cudaGetDevice(&dev));
+        if (g_dev[dev].coop && kq_sat_kpc(p->K, g_dev[dev].sms)) {
+          KqSweepArgs b = a;
+          b.pic_timing = g_picard_timing;
+          return kq_launch_sat(b, g_dev[dev].sms, st);
+        }
+      }
       switch (p->N) {
         case 2: return kq_launch_fwupd_spec2_re(a, pl, fsel, second, st);
         case 3: return kq_launch_fwupd_spec3_re(a, pl, fsel, second, st);
@@ -958,6 +972,10 @@ int kq_set_option(const char* name, int value) {
   }
   if (name && std::strcmp(name, "lanes") == 0) {
     g_lanes = value ? 1 : 0;
+    return KQ_OK;
+  }
+  if (name && std::strcmp(name, "sat") == 0) {
+    g_sat = value ? 1 : 0;
     return KQ_OK;
   }
   if (name && std::strcmp(name, "small_rows") == 0) {

@@ -144,6 +144,7 @@ int kq_tables_upload_picard4(const KqTables* T);
 int kq_tables_upload_dpoly(const KqTables* T);
 int kq_tables_upload_csr(const KqTables* T);
 int kq_tables_upload_lanes(const KqTables* T);
+int kq_tables_upload_sat(const KqTables* T);
 
 int kq_launch_prop_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, cudaStream_t st);
 int kq_launch_fwupd_small(const KqSweepArgs& a, const KqPlan& pl, int fsel, bool second,
@@ -178,6 +179,9 @@ int kq_launch_csr(const KqSweepArgs& a, const KqCsr& s, const KqPlan& pl, int fs
 // pre-pass + chain
 struct KqLanes;
 int kq_launch_lanes(const KqSweepArgs& a, const KqLanes& d, int fsel, cudaStream_t st);
+// update sweep for many two-level objectives with a real generator (kq_sat.cuh)
+int kq_sat_kpc(int K, int sms);
+int kq_launch_sat(const KqSweepArgs& a, int sms, cudaStream_t st);
 // delta-polynomial update sweep (kq_dpoly.cuh)
 struct KqDpoly;
 struct KqDpolyGeom {

@@ -1,0 +1,439 @@
+// Update / forward sweep (optimize.py:449-500 of the reference) for MANY two-level objectives
+// with a real generator (the detuning ensemble of BASELINE configs[3] scaled up: K = 131 072
+// objectives, backward-state store 4.2 GB): the regime where the sweep streams from HBM.
+//
+// Every time step needs the sum over ALL objectives before any of them can move on
+// (optimize.py:454-470), so a step costs one grid-wide all-reduce whatever else is done; the
+// kernel is built around making that reduction short and keeping everything else off it:
+//   * one CTA per SM (co-resident grid); warps 2..15 are CONSUMERS with TWO objectives per
+//     thread (14 warps instead of 32 at the CTA barriers of a step, 128 registers per thread
+//     -- the 1024-thread kernel of kq_spec.cuh spills at 64 --, two independent chains per
+//     thread); warp 0 owns no objectives: it reduces the warps' partial sums, publishes the
+//     CTA's sum and gathers the other CTAs' (objectives in the exchange warp would put their
+//     work on the critical path); warp 1 issues the TMA copies (measured: a bulk-copy issue
+//     holds its warp, and the warp's next shared-memory access, for 500-3000 cycles -- from the
+//     exchange warp that delay lands on every CTA of the grid);
+//   * the backward states of a time step are one contiguous row per CTA (time-major
+//     [nt][K][N] layout) streamed HBM -> shared memory by TMA bulk copies, KQ_SAT_RING steps
+//     ahead of their use; eta = mu^dag chi ||chi|| of the next step is formed while the
+//     reduction of this one is under way;
+//   * CTAs exchange their partial sums through flag-tagged 16-byte slots in L2 (kq_common.cuh):
+//     every CTA PUSHES its sum into a mailbox per CTA, so that a mailbox's lines are polled by
+//     one CTA only; warp 0 polls all slots of its mailbox with the loads in flight together
+//     (one L2 round trip per poll instead of one per slot) and every CTA adds them in the same
+//     order: identical pulses in every CTA, no atomics;
+//   * the step itself is the closed form of exp(iR) for a real 2 x 2 generator (kq_spec.cuh),
+//     its series degree planned from the guess pulse and verified after the update; B200
+//     issues 58 DFMA per clock and SM, so the loop body is kept to about 50 FP64 operations
+//     per objective and step (mu is real for these problems: kq_problem.real_ops).
+#pragma once
+#include "kq_spec.cuh"
+
+#define KQ_SAT_BT 448       // consumer threads (warps 2..15); warp 0: exchange, warp 1: TMA
+#define KQ_SAT_THREADS (KQ_SAT_BT + 64)
+#define KQ_SAT_OPT 2
+#define KQ_SAT_RING 4
+#define KQ_SAT_NB 5       // slots polled per lane and batch (32 * NB CTAs per batch)
+
+// All slots of a batch with their loads in flight together; returns the number of polls.
+template <int NB>
+__device__ __forceinline__ int sat_wait_batch(const KqSlot* const (&p)[NB], const bool (&act)[NB],
+                                              uint32_t tag, double (&v)[NB], bool& failed) {
+#pragma unroll
+  for (int u = 0; u < NB; ++u) v[u] = 0.0;
+  if (failed) return 0;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    uint32_t lo[NB], t0[NB], hi[NB], t1[NB];
+#pragma unroll
+    for (int u = 0; u < NB; ++u)
+      asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u])
+                   : "l"(p[u])
+                   : "memory");
+    bool all = true;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+      const bool ok = !act[u] || (t0[u] == tag && t1[u] == tag);
+      all = all && ok;
+      if (act[u]) v[u] = __hiloint2double((int)hi[u], (int)lo[u]);
+    }
+    if (__all_sync(0xffffffffu, all)) return spin + 1;
+  }
+  failed = true;
+  return 0;
+}
+__device__ __forceinline__ void sat_slot_store(KqSlot* p, double v, uint32_t tag) {
+  uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag),
+               "r"(hi), "r"(tag)
+               : "memory");
+}
+
+__device__ __forceinline__ void sat_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// barrier A / staging barrier: consumers + exchange warp (the producer warp runs on its own)
+__device__ __forceinline__ void sat_bar_a() {
+  asm volatile("bar.sync 3, %0;" ::"n"(KQ_SAT_BT + 32) : "memory");
+}
+
+// One objective: R = h T0f + heps T1f (real 2 x 2, column-major [[a, b], [c, d]]) enters the
+// closed form through dl = (a - d) / 2, b, c and t = (a + d) / 2, each affine in the pulse.
+struct SatObj {
+  cplx phi[2], eta[2];
+  double d0, d1, b0, b1, c0, c1, t0, t1;
+  double fixed;    // coefficient of term 1 when no pulse drives it
+  bool driven;
+};
+
+// rare path, out of line: sin and cos of the trace phase (by value: the objectives must stay
+// in registers)
+static __device__ __noinline__ double2 sat_phase(double t) {
+  double st, ct;
+  sincos(t, &st, &ct);
+  return make_double2(st, ct);
+}
+
+// phi <- exp(i R)^s phi for the thread's objectives TOGETHER: straight-line code with the
+// series degree as a template parameter (coefficients are immediates, the independent chains
+// of the objectives interleave); h is the step already divided by s.
+template <int P>
+__device__ __forceinline__ void sat_step(SatObj (&o)[KQ_SAT_OPT], double h, double heps_new, int s) {
+  double dl[KQ_SAT_OPT], b[KQ_SAT_OPT], c[KQ_SAT_OPT], t[KQ_SAT_OPT], z[KQ_SAT_OPT];
+  double C[KQ_SAT_OPT], S[KQ_SAT_OPT];
+#pragma unroll
+  for (int q = 0; q < KQ_SAT_OPT; ++q) {
+    const double heps = o[q].driven ? heps_new : h * o[q].fixed;
+    dl[q] = fma(heps, o[q].d1, h * o[q].d0);
+    b[q] = fma(heps, o[q].b1, h * o[q].b0);
+    c[q] = fma(heps, o[q].c1, h * o[q].c0);
+    t[q] = fma(heps, o[q].t1, h * o[q].t0);
+    z[q] = fma(dl[q], dl[q], b[q] * c[q]);
+    C[q] = kq_inv_fact(2 * (P - 1));
+    S[q] = kq_inv_fact(2 * (P - 1) + 1);
+  }
+#pragma unroll
+  for (int j = P - 2; j >= 0; --j) {
+#pragma unroll
+    for (int q = 0; q < KQ_SAT_OPT; ++q) {
+      C[q] = fma(-z[q], C[q], kq_inv_fact(2 * j));
+      S[q] = fma(-z[q], S[q], kq_inv_fact(2 * j + 1));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < KQ_SAT_OPT; ++q) {
+    const double Sd = S[q] * dl[q], Sb = S[q] * b[q], Sc = S[q] * c[q], Cq = C[q];
+    double st = 0.0, ct = 1.0;
+    if (t[q] != 0.0) {   // traceless generators (two-level systems) skip the phase
+      const double2 sc = sat_phase(t[q]);
+      st = sc.x;
+      ct = sc.y;
+    }
+    cplx v0 = o[q].phi[0], v1 = o[q].phi[1];
+#pragma unroll 1
+    for (int rep = 0; rep < s; ++rep) {
+      cplx u0 = make_double2(fma(-Sd, v0.y, fma(-Sb, v1.y, Cq * v0.x)),
+                             fma(Sd, v0.x, fma(Sb, v1.x, Cq * v0.y)));
+      cplx u1 = make_double2(fma(Sd, v1.y, fma(-Sc, v0.y, Cq * v1.x)),
+                             fma(-Sd, v1.x, fma(Sc, v0.x, Cq * v1.y)));
+      if (t[q] != 0.0) {
+        u0 = make_double2(fma(-st, u0.y, ct * u0.x), fma(st, u0.x, ct * u0.y));
+        u1 = make_double2(fma(-st, u1.y, ct * u1.x), fma(st, u1.x, ct * u1.y));
+      }
+      v0 = u0;
+      v1 = u1;
+    }
+    o[q].phi[0] = v0;
+    o[q].phi[1] = v1;
+  }
+}
+
+// CTA = warp 0 (exchange) + warp 1 (TMA producer) + KQ_SAT_BT consumer threads.
+// shared: red [2][16] | tot [2] (+ pad) | mbar [RING] | empty [RING] | sdt, sg, ssl, sbound [KQ_NTC] |
+//         splan [KQ_NTC] | ring [RING][kpc][2] | M [kpc][4] (||chi|| mu^T, real)
+__global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepArgs a, int kpc) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (a.cond_epoch && *reinterpret_cast<volatile int*>(a.status + 1) != (int)a.cond_epoch) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NCW = KQ_SAT_BT / 32;   // consumer warps
+  const int K = a.K, NT = a.NT, nblk = gridDim.x;
+  const int k0 = blockIdx.x * kpc;
+  const int kcta = max(0, min(kpc, K - k0));   // objectives of this CTA (0 for idle CTAs)
+  double* red = reinterpret_cast<double*>(smem_raw);            // [2][16]
+  double* tot = red + 32;                                       // [2] (+ pad to 40 doubles)
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 40);       // [RING] row has landed
+  uint64_t* empty = mbar + KQ_SAT_RING;                         // [RING] row has been read
+  double* sdt = reinterpret_cast<double*>(empty + KQ_SAT_RING);
+  double* sg = sdt + KQ_NTC;
+  double* ssl = sg + KQ_NTC;
+  double* sbound = ssl + KQ_NTC;
+  unsigned char* splan = reinterpret_cast<unsigned char*>(sbound + KQ_NTC);
+  cplx* ring = reinterpret_cast<cplx*>(splan + KQ_NTC);
+  const size_t stage = (size_t)kpc * 2;
+  double* sM = reinterpret_cast<double*>(ring + (size_t)KQ_SAT_RING * stage);
+  const uint32_t row_bytes = (uint32_t)kcta * 2 * sizeof(cplx);
+  const bool xwarp = warp < 2;                 // exchange / producer warp: no objectives
+  const int ctid = tid - 64;                   // consumer index
+  bool failed = false;
+
+  if (tid == 0) {
+    for (int st = 0; st < KQ_SAT_RING; ++st) {
+      mbar_init(&mbar[st], 1);
+      mbar_init(&empty[st], (uint32_t)NCW);   // lane 0 of every consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // idle CTAs never fill the ring: their (weight-zero) threads must still read finite numbers
+  if (kcta == 0)
+    for (size_t i = tid; i < (size_t)KQ_SAT_RING * stage; i += KQ_SAT_THREADS) ring[i] = c_zero();
+  __syncthreads();
+  // backward states chi(t_r), r = 0..NT: step n needs row n (its overlap) -- row NT only feeds
+  // the (unused) overlap prepared behind the last step, so that the loop has no tail
+  auto issue_row = [&](int r) {
+    const int st = r % KQ_SAT_RING;
+    mbar_expect_tx(&mbar[st], row_bytes);
+    bulk_g2s(ring + st * stage, a.X + ((size_t)r * K + k0) * 2, row_bytes, &mbar[st]);
+  };
+  if (tid == 0 && kcta > 0)
+    for (int r = 0; r < KQ_SAT_RING && r <= NT; ++r) issue_row(r);
+
+  // ---- this thread's objectives: local indices ctid and ctid + BT (padding threads shadow
+  // objective 0 of the CTA with weight zero)
+  SatObj o[KQ_SAT_OPT];
+  int kl[KQ_SAT_OPT];
+  double O0 = 0.0, O1 = 0.0, Oc = 0.0;
+#pragma unroll
+  for (int q = 0; q < KQ_SAT_OPT; ++q) {
+    const int l = ctid + q * KQ_SAT_BT;
+    const bool valid = !xwarp && l < kcta;
+    kl[q] = valid ? l : 0;
+    const int k = min(k0 + kl[q], K - 1);
+    double T0[4], T1[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      T0[e] = -a.ops[((size_t)k * 2 + 0) * 4 + e].x;   // f = -i: exp(i R), R = -H dt
+      T1[e] = -a.ops[((size_t)k * 2 + 1) * 4 + e].x;
+    }
+    o[q].d0 = 0.5 * (T0[0] - T0[3]);
+    o[q].d1 = 0.5 * (T1[0] - T1[3]);
+    o[q].t0 = 0.5 * (T0[0] + T0[3]);
+    o[q].t1 = 0.5 * (T1[0] + T1[3]);
+    o[q].c0 = T0[1];
+    o[q].c1 = T1[1];
+    o[q].b0 = T0[2];
+    o[q].b1 = T1[2];
+    const double cnorm = valid ? a.chi_norms[k] : 0.0;
+    o[q].phi[0] = a.state0[(size_t)k * 2 + 0];
+    o[q].phi[1] = a.state0[(size_t)k * 2 + 1];
+    if (valid)
+      for (int e = 0; e < 4; ++e) sM[(size_t)l * 4 + e] = cnorm * a.mu[(size_t)k * 4 + e].x;
+    const int t2p = a.term2pulse[k * 2 + 1];
+    o[q].driven = (t2p == 0);
+    o[q].fixed = (t2p == -1) ? 1.0 : 0.0;
+    if (valid) {
+      O0 = fmax(O0, a.op_norm[k * 2 + 0]);
+      O1 = fmax(O1, o[q].driven ? a.op_norm[k * 2 + 1] : 0.0);
+      Oc = fmax(Oc, o[q].driven ? 0.0 : o[q].fixed * a.op_norm[k * 2 + 1]);
+    }
+  }
+  // weight-zero threads of a CTA with objectives read objective 0's matrix; idle CTAs zeros
+  if (kcta == 0 && tid < 4) sM[tid] = 0.0;
+  O0 = block_max(O0, red);
+  O1 = block_max(O1, red);
+  Oc = block_max(Oc, red);
+  const double lam = a.lambda_a[0];
+  // eta = mu^dag chi ||chi|| of the row in ring stage `st`; padding threads (q-th objective
+  // beyond kcta) get zero through `w`
+  double w[KQ_SAT_OPT];
+#pragma unroll
+  for (int q = 0; q < KQ_SAT_OPT; ++q) w[q] = (!xwarp && ctid + q * KQ_SAT_BT < kcta) ? 1.0 : 0.0;
+  auto make_eta = [&](int st, cplx (&dst)[KQ_SAT_OPT][2]) {
+#pragma unroll
+    for (int q = 0; q < KQ_SAT_OPT; ++q) {
+      const cplx* row = ring + st * stage + (size_t)kl[q] * 2;
+      const cplx x0 = row[0], x1 = row[1];
+      const double2 m0 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4);
+      const double2 m1 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4 + 2);
+      // eta_c = sum_r M[c][r] chi_r (element (r, c) of mu at c * 2 + r)
+      dst[q][0] = make_double2(w[q] * fma(m0.x, x0.x, m0.y * x1.x), w[q] * fma(m0.x, x0.y, m0.y * x1.y));
+      dst[q][1] = make_double2(w[q] * fma(m1.x, x0.x, m1.y * x1.x), w[q] * fma(m1.x, x0.y, m1.y * x1.y));
+    }
+  };
+  if (warp == 1) {
+    // ---- producer warp: row r goes into stage r % RING as soon as every consumer warp has
+    // released the row that was there (data-driven: no barrier shared with the other warps)
+    if (lane == 0 && kcta > 0) {
+      for (int r = KQ_SAT_RING; r <= NT; ++r) {
+        const int st = r % KQ_SAT_RING, use = r / KQ_SAT_RING;
+        mbar_wait(&empty[st], (uint32_t)((use - 1) & 1));
+        issue_row(r);
+      }
+    }
+    return;
+  }
+  if (kcta > 0) mbar_wait(&mbar[0], 0);
+  {
+    cplx e0[KQ_SAT_OPT][2];
+    make_eta(0, e0);
+#pragma unroll
+    for (int q = 0; q < KQ_SAT_OPT; ++q) {
+      o[q].eta[0] = e0[q][0];
+      o[q].eta[1] = e0[q][1];
+    }
+    __syncwarp();
+    if (warp >= 2 && lane == 0) sat_mbar_arrive(&empty[0]);
+  }
+  double ga = 0.0;
+  // optional per-phase cycle counts, kq_set_option("picard_timing", 1): thread 0 (exchange
+  // warp) and thread 64 (first consumer) of CTA 0
+  const bool timing = a.pic_timing && blockIdx.x == 0 && (tid == 0 || tid == 64);
+  long long tacc[4] = {0, 0, 0, 0}, tprev = 0, npoll = 0;
+#define KQ_SAT_TICK(i)                  \
+  if (timing) {                         \
+    const long long now_ = clock64();   \
+    tacc[i] += now_ - tprev;            \
+    tprev = now_;                       \
+  }
+
+  for (int base = 0; base < NT; base += KQ_NTC) {
+    const int len = min(KQ_NTC, NT - base);
+    sat_bar_a();
+    for (int i = (warp == 0 ? tid : tid - 32); i < len; i += KQ_SAT_BT + 32) {
+      const double dti = a.dt[base + i], gi = a.pulses[base + i];
+      sdt[i] = dti;
+      sg[i] = gi;
+      ssl[i] = a.shape[base + i] / lam;   // S/lambda as in optimize.py:474
+      int s, m;
+      double bound;
+      plan_bound(dti * (fma(fabs(gi), O1, O0) + Oc), s, m, bound);
+      sbound[i] = bound;
+      splan[i] = (s == 1) ? (unsigned char)m : (unsigned char)0;
+    }
+    sat_bar_a();
+    if (timing) tprev = clock64();
+    if (warp == 0) {
+      // ---- exchange warp ------------------------------------------------------------
+      for (int j = 0; j < len; ++j) {
+        const int n = base + j, par = n & 1;
+        sat_bar_a();   // barrier A: the consumer warps' partial sums are in red[par]
+        KQ_SAT_TICK(0)
+        double acc = (lane < NCW) ? red[par * 16 + lane] : 0.0;
+        acc = warp_allreduce_sum(acc);
+        if (nblk > 1) {
+          const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
+          // push: this CTA's sum goes into the mailbox of every CTA (lines of a mailbox are
+          // polled by their owner only -- a slot array read by all CTAs serialises 148 readers
+          // on every line), then the own mailbox [par][me][writer] is gathered
+          KqSlot* box = a.slots + (size_t)par * nblk * nblk;
+          for (int r = lane; r < nblk; r += 32)
+            sat_slot_store(box + (size_t)r * nblk + blockIdx.x, acc, tag);
+          KQ_SAT_TICK(1)
+          const KqSlot* sl0 = box + (size_t)blockIdx.x * nblk;
+          double g2 = 0.0;
+          for (int q0 = 0; q0 < nblk; q0 += 32 * KQ_SAT_NB) {
+            const KqSlot* p[KQ_SAT_NB];
+            bool act[KQ_SAT_NB];
+            double v[KQ_SAT_NB];
+#pragma unroll
+            for (int u = 0; u < KQ_SAT_NB; ++u) {
+              const int q = q0 + u * 32 + lane;
+              act[u] = q < nblk;
+              p[u] = sl0 + (act[u] ? q : 0);
+            }
+            npoll += sat_wait_batch<KQ_SAT_NB>(p, act, tag, v, failed);
+#pragma unroll
+            for (int u = 0; u < KQ_SAT_NB; ++u) g2 += act[u] ? v[u] : 0.0;
+          }
+          acc = warp_allreduce_sum(g2);
+        }
+        if (lane == 0) tot[par] = acc;
+        // barrier B: release the consumers (this warp does not wait)
+        asm volatile("bar.arrive 1, %0;" ::"n"(KQ_SAT_BT + 32) : "memory");
+        KQ_SAT_TICK(2)
+        if (lane == 0) {
+          if (blockIdx.x == 0) {   // pulse update (optimize.py:471-477)
+            const double sl = ssl[j], d1 = acc;
+            a.opt_pulses[n] = __dadd_rn(sg[j], __dmul_rn(sl, d1));
+            ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), sdt[j]));
+          }
+        }
+        __syncwarp();
+        KQ_SAT_TICK(3)
+      }
+      continue;
+    }
+    // ---- consumers --------------------------------------------------------------------
+    for (int j = 0; j < len; ++j) {
+      const int n = base + j, par = n & 1;
+      // Im <chi| mu |phi> ||chi|| of this thread's objectives
+      double val = 0.0;
+#pragma unroll
+      for (int q = 0; q < KQ_SAT_OPT; ++q)
+        val += c_im_conj_mul(o[q].eta[0], o[q].phi[0]) + c_im_conj_mul(o[q].eta[1], o[q].phi[1]);
+      val = warp_allreduce_sum(val);
+      if (lane == 0) red[par * 16 + warp - 2] = val;
+      sat_bar_a();   // barrier A
+      KQ_SAT_TICK(0)
+      // the next backward states are in shared memory by now: eta of the next step is formed
+      // while the exchange warp gathers the sum
+      {
+        const int r = n + 1, st = r % KQ_SAT_RING;
+        if (kcta > 0) mbar_wait(&mbar[st], (uint32_t)((r / KQ_SAT_RING) & 1));
+      }
+      cplx eta_next[KQ_SAT_OPT][2];
+      make_eta((n + 1) % KQ_SAT_RING, eta_next);
+      __syncwarp();
+      if (lane == 0) sat_mbar_arrive(&empty[(n + 1) % KQ_SAT_RING]);   // row n + 1 is consumed
+      KQ_SAT_TICK(1)
+      asm volatile("bar.sync 1, %0;" ::"n"(KQ_SAT_BT + 32) : "memory");   // barrier B
+      KQ_SAT_TICK(2)
+      const double d1 = tot[par];
+      const double dt_cur = sdt[j];
+      const double eps_new = __dadd_rn(sg[j], __dmul_rn(ssl[j], d1));
+      // forward step under the updated pulse (series degree planned from the guess pulse,
+      // verified against the updated one)
+      const double x_new = dt_cur * (fma(fabs(eps_new), O1, O0) + Oc);
+      int s = 1, m = splan[j];
+      if (m == 0 || !(x_new <= sbound[j])) {
+        double bound;
+        plan_bound(x_new, s, m, bound);
+      }
+      const int P = max(2, (m + 4) >> 1);   // 2P >= m + 3; P > 12 (scaled norm close to 1) runs 18
+      const double h = (s == 1) ? dt_cur : dt_cur / (double)s;
+      const double heps = h * eps_new;
+      // a few degrees only (more terms than needed cost two DFMA each; every variant is
+      // straight-line code in the loop body, and the loop has to stay in the instruction cache)
+      if (P <= 3) sat_step<3>(o, h, heps, s);
+      else if (P <= 5) sat_step<5>(o, h, heps, s);
+      else if (P <= 8) sat_step<8>(o, h, heps, s);
+      else if (P <= 12) sat_step<12>(o, h, heps, s);
+      else sat_step<18>(o, h, heps, s);
+#pragma unroll
+      for (int q = 0; q < KQ_SAT_OPT; ++q) {
+        o[q].eta[0] = eta_next[q][0];
+        o[q].eta[1] = eta_next[q][1];
+      }
+      KQ_SAT_TICK(3)
+    }
+  }
+  if (timing) {
+    long long* out = reinterpret_cast<long long*>(a.status + 16) + (tid == 0 ? 0 : 5);
+    for (int i = 0; i < 4; ++i) out[i] = tacc[i];
+    out[4] = npoll;
+  }
+  if (xwarp) {
+    if (blockIdx.x == 0 && tid == 0) a.g_a[0] = ga;
+    if (failed) atomicExch(a.status, (int)-4);
+    return;
+  }
+  if (a.stateT) {
+#pragma unroll
+    for (int q = 0; q < KQ_SAT_OPT; ++q) {
+      const int l = ctid + q * KQ_SAT_BT;
+      if (l < kcta) {
+        a.stateT[(size_t)(k0 + l) * 2 + 0] = o[q].phi[0];
+        a.stateT[(size_t)(k0 + l) * 2 + 1] = o[q].phi[1];
+      }
+    }
+  }
+}

@@ -733,6 +733,61 @@ def test_two_level_kernel_variants_vs_oracle(krotov, case):
     assert rel(results[0].all_pulses[2], results[1].all_pulses[2]) < 1e-13
 
 
+@pytest.mark.parametrize('case', ['real_traceless', 'real_with_trace'])
+def test_many_objectives_kernel_vs_oracle(krotov, case):
+    """More two-level objectives than one CTA of the sequential kernel holds
+    run the kernel built around the grid-wide reduction (csrc/kq_sat.cuh: two
+    objectives per thread, partially filled last CTA, batched slot polling):
+    against the oracle and against the sequential kernel it replaces."""
+    from oracle import krotov_oracle as orc
+    sx = np.array([[0, 1], [1, 0]], dtype=complex)
+    sz = np.array([[1, 0], [0, -1]], dtype=complex)
+    H0, H1 = {
+        'real_traceless': (-0.5 * sz, sx),
+        'real_with_trace': (np.diag([0.3, 1.7]).astype(complex) + 0.1 * sx,
+                            sx + 0.2 * np.diag([1.0, 0.0])),
+    }[case]
+    K = 2500
+    from functools import partial
+    T, nt = 5.0, 40
+    guess = lambda t, args: 0.3 * krotov.shapes.flattop(  # noqa: E731
+        t, t_start=0, t_stop=T, t_rise=0.5, func='blackman')
+    S = partial(krotov.shapes.flattop, t_start=0, t_stop=T, t_rise=0.5,
+                func='sinsq')
+    psi0 = np.array([[1], [0]], dtype=complex)
+    psi1 = np.array([[0], [1]], dtype=complex)
+    objs = [krotov.Objective(initial_state=psi0, target=psi1,
+                             H=[H0 * (1 + 0.2 * k / K), [H1, guess]])
+            for k in range(K)]
+    opts = {guess: dict(lambda_a=2.0, update_shape=S)}
+    tlist = np.linspace(0, T, nt)
+    lib = krotov._lib.load()
+    results = []
+    for sat in (1, 0):
+        assert lib.kq_set_option(b"sat", sat) == 0
+        results.append(krotov.optimize_pulses(
+            objs, opts, tlist, propagator=krotov.propagators.expm,
+            chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+            store_all_pulses=True))
+    lib.kq_set_option(b"sat", 1)
+    from krotov_b200.compiler import initialize_controls
+    (controls, _, pulses, mapping, lam, shp) = initialize_controls(
+        objs, opts, tlist)
+    terms = [[(np.asarray(o.H[0]), -1), (np.asarray(o.H[1][0]), 0)]
+             for o in objs]
+    rec = orc.optimize(
+        terms, [o.initial_state.ravel() for o in objs],
+        [o.target.ravel() for o in objs], pulses, shp, lam, tlist,
+        orc.chis_re, iter_stop=2)
+    for res in results:
+        for it in (1, 2):
+            assert rel(res.all_pulses[it],
+                       rec[it]['optimized_pulses']) < PULSE_RTOL, case
+    assert rel(results[0].all_pulses[2], results[1].all_pulses[2]) < 1e-12
+    assert np.allclose(results[0].tau_vals[-1], results[1].tau_vals[-1],
+                       rtol=0, atol=1e-12)
+
+
 # ---------------------------------------------------------------------------
 # One-launch-per-iteration kernel family (csrc/kq_picard.cuh)
 
