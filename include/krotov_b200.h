@@ -115,7 +115,10 @@ typedef struct {
                          1 = delta-polynomial sequential sweep (strongly coupled problems:
                          the fixed point needs many rounds there), 2 = fixed point.
                          N > 4 always uses the delta-polynomial sweep if it fits. */
-  int32_t reserved2;
+  int32_t row_nnz;    /* 0 = unknown (dense rows), else the largest number of non-zero
+                         columns in a row of the union pattern of one objective's terms,
+                         the diagonal included: rows with <= 4 entries (Lambda systems,
+                         transmon ladders) select the entries-in-registers update sweep */
   const struct kq_sparse* sparse;  /* NULL, or the CSR form of all matrices: required for
                          N > 64; for smaller N it selects the row-per-thread CSR kernels if
                          ops is NULL (sparse generators beyond the delta-polynomial family,

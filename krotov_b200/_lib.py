@@ -49,7 +49,7 @@ class KqProblem(ctypes.Structure):
         ('op_norm', ctypes.c_void_p), ('dt', ctypes.c_void_p),
         ('shape', ctypes.c_void_p), ('lambda_a', ctypes.c_void_p),
         ('real_ops', ctypes.c_int32), ('reserved', ctypes.c_int32),
-        ('update_sweep', ctypes.c_int32), ('reserved2', ctypes.c_int32),
+        ('update_sweep', ctypes.c_int32), ('row_nnz', ctypes.c_int32),
         ('sparse', ctypes.c_void_p),
     ]
 

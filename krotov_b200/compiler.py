@@ -109,6 +109,7 @@ class CompiledProblem:
         self.ops = self.ops_adj = self.mu = None      # complex128 arrays
         self.sparse = None      # CSR bundle instead, for N > DENSE_NMAX
         self.term2pulse = self.op_norm = None
+        self.row_nnz = 0
         self.psi0 = self.targets = None               # [K,N]
         self.weights = None
         self.dt = None
@@ -233,6 +234,10 @@ def compile_problem(objectives, controls, mapping, tlist, mu=None,
             t2p[k, m] = l
     cp.term2pulse = t2p
     cp.op_norm = np.abs(ops).sum(axis=2).max(axis=2)  # 1-norm per term
+    # most non-zero columns in a row of an objective's terms taken together
+    # (diagonal included): sparse rows select the entries-in-registers sweep
+    pattern = np.any(ops != 0.0, axis=1) | np.eye(N, dtype=bool)[None]
+    cp.row_nnz = int(pattern.sum(axis=2).max())
     # real Hamiltonians: f*A is purely imaginary, kernels halve the multiplies
     cp.real_ops = bool(np.all(ops.imag == 0.0))
     ops_adj = np.conj(np.swapaxes(ops, 2, 3))

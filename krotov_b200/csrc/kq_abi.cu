@@ -748,21 +748,47 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
   return launch_warp(a2, pl2, fsel, false, false, st);
 }
 
-// One warp, lane = (objective, row): few objectives with several controls or terms
-// (kq_lanes.cuh); first order, one GPU.
+// lane = (objective, row), a few entries per row in registers: few objectives with small or
+// sparse generators (kq_lanes.cuh); first order, one GPU.  kq_problem.row_nnz (0 = unknown:
+// dense rows) is the largest number of non-zero columns in a row of the union pattern of an
+// objective's terms, the diagonal included.
 bool lanes_plan(const kq_problem* p, const KqSweepArgs& a, KqLanes& ln) {
-  if (!g_lanes || a.world > 1 || p->N < 2 || p->N > 4 || p->L < 1 || p->L > KQ_LN_LMAX ||
-      p->M > KQ_MMAX_SMALL)
+  if (!g_lanes || a.world > 1 || p->N < 2 || p->N > 32 || p->L < 1 || p->L > KQ_LN_LMAX ||
+      p->M > KQ_MMAX_SMALL || !p->ops || !p->mu)
     return false;
-  const int NP = p->N == 3 ? 4 : p->N;
-  if ((long long)p->K * NP > 32) return false;
-  int span = 1;
-  while (span < p->K * NP) span <<= 1;
+  const int nnz = p->row_nnz > 0 ? p->row_nnz : p->N;
+  if (nnz > KQ_LN_NZMAX) return false;
+  int NP = 2;
+  while (NP < p->N) NP <<= 1;
+  const int G = 32 / NP, W = (p->K + G - 1) / G;
+  if (W > KQ_LN_WMAX) return false;
   ln.NP = NP;
+  ln.G = G;
+  ln.W = W;
+  ln.NZ = nnz < 2 ? 2 : nnz;
+  int span = NP;
+  if (W > 1) {
+    span = 32;
+  } else {
+    while (span < p->K * NP) span <<= 1;
+  }
   ln.span = span;
   ln.zeta = nullptr;
   ln.scal = nullptr;
   return true;
+}
+int launch_lanes_update(const kq_problem* p, const KqSweepArgs& a, KqLanes& ln, int fsel,
+                        cudaStream_t st) {
+  int dev = 0;
+  KQ_CUDA(cudaGetDevice(&dev));
+  const size_t zb =
+      ((size_t)p->NT * (p->L + 1) * ln.W * 32 * sizeof(cplx) + 255) / 256 * 256;
+  void* base = nullptr;
+  const int rc = get_scratch(dev, zb + (size_t)p->NT * KQ_LN_SC * sizeof(double), &base, 2);
+  if (rc) return rc;
+  ln.zeta = reinterpret_cast<cplx*>(base);
+  ln.scal = reinterpret_cast<double*>(static_cast<char*>(base) + zb);
+  return kq_launch_lanes(a, ln, fsel, st);
 }
 
 // The sequential update/forward sweep kernels (one time step after the other).
@@ -779,17 +805,7 @@ int launch_sequential_update(const kq_problem* p, const KqSweepArgs& a, const Pl
   if (pl.family == 0) {
     if (!pl.spec) {
       KqLanes ln;
-      if (!second && lanes_plan(p, a, ln)) {
-        int dev = 0;
-        KQ_CUDA(cudaGetDevice(&dev));
-        const size_t zb = ((size_t)p->NT * p->L * 32 * sizeof(cplx) + 255) / 256 * 256;
-        void* base = nullptr;
-        const int rc = get_scratch(dev, zb + (size_t)p->NT * KQ_LN_SC * sizeof(double), &base, 2);
-        if (rc) return rc;
-        ln.zeta = reinterpret_cast<cplx*>(base);
-        ln.scal = reinterpret_cast<double*>(static_cast<char*>(base) + zb);
-        return kq_launch_lanes(a, ln, fsel, st);
-      }
+      if (!second && lanes_plan(p, a, ln)) return launch_lanes_update(p, a, ln, fsel, st);
       return kq_launch_fwupd_small(a, pl, fsel, second, st);
     }
     if (p->real_ops && !p->is_super) {
@@ -815,6 +831,12 @@ int launch_sequential_update(const kq_problem* p, const KqSweepArgs& a, const Pl
       case 3: return kq_launch_fwupd_spec3(a, pl, fsel, second, st);
       default: return kq_launch_fwupd_spec4(a, pl, fsel, second, st);
     }
+  }
+  {
+    // N >= 5 with sparse rows (the transmon of notebook 05: N = 17, three entries per row)
+    KqLanes ln;
+    if (!second && p->row_nnz > 0 && lanes_plan(p, a, ln))
+      return launch_lanes_update(p, a, ln, fsel, st);
   }
   return launch_warp(a, pl, fsel, second, true, st);
 }

@@ -116,7 +116,8 @@ class SweepEngine:
             op_norm=self.t_opn.data_ptr(), dt=self.t_dt.data_ptr(),
             shape=self.t_shape.data_ptr(), lambda_a=self.t_lambda.data_ptr(),
             real_ops=1 if cp.real_ops else 0, reserved=0,
-            update_sweep=update_sweep, reserved2=0,
+            update_sweep=update_sweep,
+            row_nnz=int(getattr(cp, 'row_nnz', 0) or 0),
             sparse=0 if self._sparse is None else ctypes.addressof(
                 self._sparse))
         self._p = ctypes.byref(self.problem)
