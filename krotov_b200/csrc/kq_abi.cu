@@ -626,6 +626,25 @@ size_t csr_stage_bytes(const kq_problem* p, bool update, size_t base) {
   return base + extra <= (size_t)220 * 1024 ? extra : 0;
 }
 
+// Geometry of the entries-in-registers propagation kernels (kq_lanes.cuh): N <= 32, at most
+// KQ_LN_NZMAX non-zeros per row (kq_problem.row_nnz; 0 = unknown: dense rows).
+bool prop_lanes_plan(const kq_problem* p, KqLanes& ln) {
+  if (!g_lanes || p->N < 2 || p->N > 32 || p->L > KQ_LN_LMAX || p->M > KQ_MMAX_SMALL || !p->ops ||
+      !p->ops_adj)
+    return false;
+  const int nnz = p->row_nnz > 0 ? p->row_nnz : p->N;
+  if (nnz > KQ_LN_NZMAX) return false;
+  int NP = 2;
+  while (NP < p->N) NP <<= 1;
+  std::memset(&ln, 0, sizeof ln);
+  ln.NP = NP;
+  ln.G = 32 / NP;
+  ln.W = KQ_LN_WMAX;
+  ln.NZ = nnz < 2 ? 2 : nnz;
+  ln.span = 32;
+  return true;
+}
+
 int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_c128* state0,
              kq_c128* stateT, kq_c128* store, void* stream, int k_lo = 0, int k_cnt = -1) {
   int rc = check_problem(p);
@@ -660,6 +679,55 @@ int run_prop(const kq_problem* p, bool backward, const double* pulses, const kq_
     const size_t extra = csr_stage_bytes(p, false, pl.smem);
     pl.smem += extra;
     return kq_launch_csr(a, csr_of(p), pl, fsel, false, extra > 0, st);
+  }
+  // few objectives with small or sparse generators: entries-in-registers kernels
+  // (kq_lanes.cuh), time-parallel over segments of the grid
+  {
+    KqLanes ln;
+    if (!(pl.family == 0 && pl.spec) && pl.family != 2 && k_cnt <= 64 && prop_lanes_plan(p, ln)) {
+      const int capacity = g_dev[dev].sms * KQ_LN_WMAX * ln.G;   // tasks of one wave
+      int nseg = 1;
+      if (!g_disable_segments && p->NT >= 64)
+        nseg = std::min(128, std::min(p->NT / 8, capacity / (k_cnt * (p->N + 1))));
+      auto warps_for = [&](int n_task) {
+        return std::max(1, std::min(KQ_LN_WMAX, (n_task + ln.G - 1) / ln.G));
+      };
+      if (nseg < 4) {
+        ln.W = warps_for(k_cnt);
+        return kq_launch_prop_lanes(a, ln, fsel, k_cnt, st);
+      }
+      a.seg_len = (p->NT + nseg - 1) / nseg;
+      nseg = (p->NT + a.seg_len - 1) / a.seg_len;
+      a.seg_count = nseg;
+      const size_t nP = (size_t)nseg * p->K * p->N * p->N, nB = (size_t)(nseg + 1) * p->K * p->N;
+      void* scratch = nullptr;
+      rc = get_scratch(dev, (nP + nB) * sizeof(cplx), &scratch);
+      if (rc) return rc;
+      a.seg_P = reinterpret_cast<cplx*>(scratch);
+      a.seg_B = a.seg_P + nP;
+      // pass 1: the N basis vectors through every segment -> segment propagators
+      KqSweepArgs a1 = a;
+      a1.seg_pass = 1;
+      a1.store = nullptr;
+      a1.stateT = nullptr;
+      ln.W = warps_for(k_cnt * nseg * p->N);
+      rc = kq_launch_prop_lanes(a1, ln, fsel, k_cnt * nseg * p->N, st);
+      if (rc) return rc;
+      {   // boundary states of the segments (sweep order)
+        const int bt = round_up(p->N, 32);
+        const size_t sm = (size_t)2 * p->N * sizeof(cplx);
+        if (p->N <= 16)
+          k_seg_chain_rows<16><<<k_cnt, bt, sm, st>>>(a, nseg);
+        else
+          k_seg_chain_rows<32><<<k_cnt, bt, sm, st>>>(a, nseg);
+        KQ_CUDA(cudaGetLastError());
+      }
+      // pass 2: every segment from its boundary state, all states stored
+      KqSweepArgs a2 = a;
+      a2.seg_pass = 2;
+      ln.W = warps_for(k_cnt * nseg);
+      return kq_launch_prop_lanes(a2, ln, fsel, k_cnt * nseg, st);
+    }
   }
   // few generic objectives (several terms): the thread-per-objective kernel would walk
   // through the grid with one thread; the lane-per-row family propagates segments of the

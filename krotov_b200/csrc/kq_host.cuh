@@ -179,6 +179,8 @@ int kq_launch_csr(const KqSweepArgs& a, const KqCsr& s, const KqPlan& pl, int fs
 // pre-pass + chain
 struct KqLanes;
 int kq_launch_lanes(const KqSweepArgs& a, const KqLanes& d, int fsel, cudaStream_t st);
+int kq_launch_prop_lanes(const KqSweepArgs& a, const KqLanes& d, int fsel, int n_task,
+                         cudaStream_t st);
 // update sweep for many two-level objectives with a real generator (kq_sat.cuh)
 int kq_sat_kpc(int K, int sms);
 int kq_launch_sat(const KqSweepArgs& a, int sms, cudaStream_t st);

@@ -132,11 +132,121 @@ struct LnState {
   int t2p[KQ_MMAX_SMALL];
 };
 
+// Entries of row q.r of objective q.k: the non-zero columns (union over the terms, and the
+// diagonal), f * T_m at those columns, the first drift term shifted by - c0 on the diagonal.
+// Uniform control flow -- padding lanes shadow a real row and take nothing -- so that the warp
+// provably stays converged for the shuffles of the time loop.  Returns true if the row has
+// more than NZ entries.
+template <int NZ, int FSEL>
+__device__ __forceinline__ bool ln_setup(const KqSweepArgs& a, const LnLane& q, cplx c0,
+                                         LnState<NZ>& S) {
+  const int K = a.K, N = a.N, M = a.M, NN = N * N;
+#pragma unroll
+  for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
+    S.t2p[m] = (m < M && q.act) ? a.term2pulse[q.k * M + m] : -2;
+#pragma unroll
+    for (int z = 0; z < NZ; ++z) S.T[m][z] = c_zero();
+  }
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) S.src[z] = threadIdx.x & 31;
+  int cnt = 0;
+  bool shifted = false, overflow = false;
+  const int kk = min(q.k, K - 1), rr = min(q.r, N - 1);
+  for (int c = 0; c < N; ++c) {
+    cplx t[KQ_MMAX_SMALL];
+    bool nz = (c == rr);
+#pragma unroll
+    for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
+      t[m] = c_zero();
+      if (m < M) {
+        t[m] = a.ops[((size_t)kk * M + m) * NN + (size_t)c * N + rr];
+        nz = nz || t[m].x != 0.0 || t[m].y != 0.0;
+      }
+    }
+    nz = nz && q.act;
+    const bool take = nz && cnt < NZ;
+    overflow = overflow || (nz && cnt >= NZ);
+#pragma unroll
+    for (int z = 0; z < NZ; ++z) {
+      const bool here = take && z == cnt;
+      S.src[z] = here ? q.base + c : S.src[z];
+#pragma unroll
+      for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
+        cplx v = apply_f<FSEL>(t[m]);
+        const bool sh = here && c == rr && !shifted && S.t2p[m] == -1;
+        if (sh) v = c_sub(v, c0);
+        shifted = shifted || sh;
+        S.T[m][z] = here ? v : S.T[m][z];
+      }
+    }
+    cnt += take ? 1 : 0;
+  }
+  return overflow;
+}
+
+// Row of f A - c0 (times h) under the pulse values eps, Taylor plan from its largest absolute
+// row sum in the warp, the Taylor/Horner recurrence on the lane's component, exp(c0 dt).
+template <int NZ>
+__device__ __forceinline__ cplx ln_propagate(const LnState<NZ>& S, cplx y0,
+                                             const double (&eps)[KQ_LN_LMAX], double dtn,
+                                             cplx phase, int M) {
+  const KqTables& T = c_kq_tables;
+  cplx A[NZ];
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) A[z] = c_zero();
+#pragma unroll
+  for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
+    if (m < M) {
+      const int t = S.t2p[m];
+      double coef = (t == -1) ? 1.0 : 0.0;
+#pragma unroll
+      for (int l = 0; l < KQ_LN_LMAX; ++l) coef = (t == l) ? eps[l] : coef;
+#pragma unroll
+      for (int z = 0; z < NZ; ++z) A[z] = c_fma_real(coef, S.T[m][z], A[z]);
+    }
+  }
+  double x = 0.0;
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) x += fabs(A[z].x) + fabs(A[z].y);
+  x *= fabs(dtn);
+  {
+    // one Taylor plan per warp: the largest row sum of its objectives (rounded up)
+    const int hi = __reduce_max_sync(0xffffffffu, __double2hiint(x));
+    x = __hiloint2double(hi, (int)0xffffffff);
+  }
+  int s, mdeg;
+  double xs;
+  taylor_plan(T, x, s, mdeg, xs);
+  const double h = (s == 1) ? dtn : dtn / (double)s;
+#pragma unroll
+  for (int z = 0; z < NZ; ++z) A[z] = c_make(h * A[z].x, h * A[z].y);
+  cplx yc = y0;
+  for (int rep = 0; rep < s; ++rep) {
+    const cplx v = yc;
+    cplx y = v;
+    for (int j = mdeg; j >= 1; --j) {
+      const double cj = T.inv[j];   // consumed at the end of the term: its latency is hidden
+      cplx w0 = c_zero(), w1 = c_zero();
+#pragma unroll
+      for (int z = 0; z < NZ; ++z) {
+        cplx yz;
+        yz.x = __shfl_sync(0xffffffffu, y.x, S.src[z]);
+        yz.y = __shfl_sync(0xffffffffu, y.y, S.src[z]);
+        if (z & 1) w1 = c_fma(A[z], yz, w1);
+        else w0 = c_fma(A[z], yz, w0);
+      }
+      const cplx w = (NZ > 1) ? c_add(w0, w1) : w0;
+      y = c_fma_real(cj, w, v);
+    }
+    yc = y;
+  }
+  return c_make(phase.x * yc.x - phase.y * yc.y, phase.x * yc.y + phase.y * yc.x);
+}
+
 template <int NZ, bool MULTI>
 __device__ __forceinline__ void ln_step(const KqSweepArgs& a, const KqLanes& d, const LnRec& R,
                                         LnState<NZ>& S, double (*red)[KQ_LN_LMAX][8], int n,
                                         int L, int M) {
-  const KqTables& T = c_kq_tables;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double sl[KQ_LN_LMAX] = {R.s[0].x, R.s[0].y, R.s[1].x, R.s[1].y};
   const double g[KQ_LN_LMAX] = {R.s[2].x, R.s[2].y, R.s[3].x, R.s[3].y};
@@ -176,114 +286,20 @@ __device__ __forceinline__ void ln_step(const KqSweepArgs& a, const KqLanes& d, 
     S.ga[l] = __dadd_rn(S.ga[l], __dmul_rn(__dmul_rn(sl[l], __dmul_rn(o[l], o[l])), dtn));
     if (threadIdx.x == 0 && l < L) a.opt_pulses[(size_t)l * a.NT + n] = eps[l];
   }
-  // ---- this lane's entries of f A - c0 under the updated pulses; ||.||_inf bound
-  cplx A[NZ];
-#pragma unroll
-  for (int z = 0; z < NZ; ++z) A[z] = c_zero();
-#pragma unroll
-  for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
-    if (m < M) {
-      const int t = S.t2p[m];
-      double coef = (t == -1) ? 1.0 : 0.0;
-#pragma unroll
-      for (int l = 0; l < KQ_LN_LMAX; ++l) coef = (t == l) ? eps[l] : coef;
-#pragma unroll
-      for (int z = 0; z < NZ; ++z) A[z] = c_fma_real(coef, S.T[m][z], A[z]);
-    }
-  }
-  double x = 0.0;
-#pragma unroll
-  for (int z = 0; z < NZ; ++z) x += fabs(A[z].x) + fabs(A[z].y);
-  x *= fabs(dtn);
-  {
-    // one Taylor plan per warp: the largest row sum of its objectives (rounded up)
-    const int hi = __reduce_max_sync(0xffffffffu, __double2hiint(x));
-    x = __hiloint2double(hi, (int)0xffffffff);
-  }
-  int s, mdeg;
-  double xs;
-  taylor_plan(T, x, s, mdeg, xs);
-  const double h = (s == 1) ? dtn : dtn / (double)s;
-#pragma unroll
-  for (int z = 0; z < NZ; ++z) A[z] = c_make(h * A[z].x, h * A[z].y);
-  for (int rep = 0; rep < s; ++rep) {
-    const cplx v = S.y;
-    cplx y = v;
-    for (int j = mdeg; j >= 1; --j) {
-      const double cj = T.inv[j];   // consumed at the end of the term: its latency is hidden
-      cplx w0 = c_zero(), w1 = c_zero();
-#pragma unroll
-      for (int z = 0; z < NZ; ++z) {
-        cplx yz;
-        yz.x = __shfl_sync(0xffffffffu, y.x, S.src[z]);
-        yz.y = __shfl_sync(0xffffffffu, y.y, S.src[z]);
-        if (z & 1) w1 = c_fma(A[z], yz, w1);
-        else w0 = c_fma(A[z], yz, w0);
-      }
-      const cplx w = (NZ > 1) ? c_add(w0, w1) : w0;
-      y = c_fma_real(cj, w, v);
-    }
-    S.y = y;
-  }
-  // exp(c0 dt) of the shift
-  S.y = c_make(R.ph.x * S.y.x - R.ph.y * S.y.y, R.ph.x * S.y.y + R.ph.y * S.y.x);
+  // ---- forward step under the updated pulses
+  S.y = ln_propagate<NZ>(S, S.y, eps, dtn, R.ph, M);
 }
 
 template <int NZ, int FSEL, bool MULTI>
 __global__ void __launch_bounds__(256, 1) k_fwupd_rows(const KqSweepArgs a, const KqLanes d) {
   __shared__ double red[2][KQ_LN_LMAX][8];
   if (a.cond_epoch && *reinterpret_cast<volatile int*>(a.status + 1) != (int)a.cond_epoch) return;
-  const int K = a.K, N = a.N, NT = a.NT, M = a.M, L = a.L, NN = N * N;
+  const int K = a.K, N = a.N, NT = a.NT, M = a.M, L = a.L;
   const int BT = blockDim.x;
   const LnLane q = ln_lane(d, K, N);
   const cplx c0 = ln_shift<FSEL>(a, d, q);
   LnState<NZ> S;
-#pragma unroll
-  for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
-    S.t2p[m] = (m < M && q.act) ? a.term2pulse[q.k * M + m] : -2;
-#pragma unroll
-    for (int z = 0; z < NZ; ++z) S.T[m][z] = c_zero();
-  }
-#pragma unroll
-  for (int z = 0; z < NZ; ++z) S.src[z] = threadIdx.x & 31;
-  // the non-zero columns of this row (union over the terms, and the diagonal); uniform control
-  // flow -- padding lanes shadow a real row and take nothing -- so that the warp provably
-  // stays converged for the shuffles of the time loop
-  int cnt = 0;
-  bool shifted = false, overflow = false;
-  {
-    const int kk = min(q.k, K - 1), rr = min(q.r, N - 1);
-    for (int c = 0; c < N; ++c) {
-      cplx t[KQ_MMAX_SMALL];
-      bool nz = (c == rr);
-#pragma unroll
-      for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
-        t[m] = c_zero();
-        if (m < M) {
-          t[m] = a.ops[((size_t)kk * M + m) * NN + (size_t)c * N + rr];
-          nz = nz || t[m].x != 0.0 || t[m].y != 0.0;
-        }
-      }
-      nz = nz && q.act;
-      const bool take = nz && cnt < NZ;
-      overflow = overflow || (nz && cnt >= NZ);
-#pragma unroll
-      for (int z = 0; z < NZ; ++z) {
-        const bool here = take && z == cnt;
-        S.src[z] = here ? q.base + c : S.src[z];
-#pragma unroll
-        for (int m = 0; m < KQ_MMAX_SMALL; ++m) {
-          cplx v = apply_f<FSEL>(t[m]);
-          // the first drift term carries - c0 on the diagonal
-          const bool sh = here && c == rr && !shifted && S.t2p[m] == -1;
-          if (sh) v = c_sub(v, c0);
-          shifted = shifted || sh;
-          S.T[m][z] = here ? v : S.T[m][z];
-        }
-      }
-      cnt += take ? 1 : 0;
-    }
-  }
+  const bool overflow = ln_setup<NZ, FSEL>(a, q, c0, S);
   // kq_problem.row_nnz promised <= NZ entries per row: a violation is reported through the
   // status word (the host raises); no early exit, the warp stays whole
   if (overflow) atomicExch(a.status, (int)-5);
@@ -308,5 +324,96 @@ __global__ void __launch_bounds__(256, 1) k_fwupd_rows(const KqSweepArgs a, cons
 #pragma unroll
     for (int l = 0; l < KQ_LN_LMAX; ++l)
       if (l < L) a.g_a[l] = S.ga[l];
+  }
+}
+
+// ---- propagation sweeps without update (optimize.py:806-886) for the same problems -------
+// Tasks as in k_sweep_warp (kq_warp.cuh): one per objective, or -- time-parallel propagation,
+// a.seg_pass 1 / 2 -- one per (objective, segment[, basis vector]); a task is a group of NP
+// lanes, G tasks per warp.  The pulse values, dt and the phase of the shift are evaluated one
+// step ahead of their use.
+template <int NZ, int FSEL>
+__global__ void __launch_bounds__(256, 1) k_prop_rows(const KqSweepArgs a, const KqLanes d) {
+  const int K = a.K, N = a.N, NT = a.NT, M = a.M, L = a.L, NN = N * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int seg_pass = a.seg_pass;
+  const int n_task = seg_pass ? a.k_cnt * a.seg_count * (seg_pass == 1 ? N : 1) : a.k_cnt;
+  const int g = lane / d.NP;
+  int task = (blockIdx.x * nwarps + warp) * d.G + g;
+  const bool valid = task < n_task;
+  if (!valid) task = n_task - 1;
+  int seg = 0, vec = 0;
+  if (seg_pass) {
+    const int rest = task / a.k_cnt;
+    task -= rest * a.k_cnt;
+    seg = rest % a.seg_count;
+    vec = rest / a.seg_count;
+  }
+  LnLane q;
+  q.r = lane - g * d.NP;
+  q.k = a.k_lo + task;
+  q.base = lane - q.r;
+  q.act = valid && q.r < N;
+  const cplx c0 = ln_shift<FSEL>(a, d, q);
+  LnState<NZ> S;
+  const bool overflow = ln_setup<NZ, FSEL>(a, q, c0, S);
+  if (overflow && a.status) atomicExch(a.status, (int)-5);
+  const int rr = min(q.r, N - 1);
+  cplx y = c_zero();
+  if (q.act) {
+    if (seg_pass == 1) y = c_make(q.r == vec ? 1.0 : 0.0, 0.0);
+    else if (seg_pass == 2) y = a.seg_B[((size_t)seg * K + q.k) * N + q.r];
+    else y = a.state0[(size_t)q.k * N + q.r];
+  }
+  const bool bwd = a.backward != 0;
+  int n_first = bwd ? NT - 1 : 0, n_count = NT;
+  if (seg_pass) {   // time window of this segment, in sweep order
+    if (bwd) {
+      const int w1 = NT - seg * a.seg_len, w0 = max(0, w1 - a.seg_len);
+      n_first = w1 - 1;
+      n_count = w1 - w0;
+    } else {
+      const int w0 = seg * a.seg_len, w1 = min(NT, w0 + a.seg_len);
+      n_first = w0;
+      n_count = w1 - w0;
+    }
+  }
+  const int n_step = bwd ? -1 : 1;
+  if (a.store && q.act && seg == 0 && seg_pass != 1) {
+    const size_t r0 = bwd ? (size_t)NT : 0;
+    kq_store(a, (r0 * K + q.k) * N + q.r, y);
+  }
+  // scalars of the first step
+  double eps[KQ_LN_LMAX];
+#pragma unroll
+  for (int l = 0; l < KQ_LN_LMAX; ++l) eps[l] = (l < L) ? a.pulses[(size_t)l * NT + n_first] : 0.0;
+  double dtn = a.dt[n_first];
+  (void)NN;
+  (void)rr;
+  for (int it = 0, n = n_first; it < n_count; ++it, n += n_step) {
+    // next step's scalars (independent of the chain)
+    const int nn = (it + 1 < n_count) ? n + n_step : n;
+    double eps_next[KQ_LN_LMAX];
+#pragma unroll
+    for (int l = 0; l < KQ_LN_LMAX; ++l) eps_next[l] = (l < L) ? a.pulses[(size_t)l * NT + nn] : 0.0;
+    const double dt_next = a.dt[nn];
+    // exp(c0 dt) of the shift
+    double sn, cs;
+    sincos(c0.y * dtn, &sn, &cs);
+    const double ex = (c0.x != 0.0) ? exp(c0.x * dtn) : 1.0;
+    y = ln_propagate<NZ>(S, y, eps, dtn, c_make(ex * cs, ex * sn), M);
+    if (a.store && q.act && seg_pass != 1) {
+      const size_t r1 = bwd ? (size_t)n : (size_t)n + 1;
+      kq_store(a, (r1 * K + q.k) * N + q.r, y);
+    }
+#pragma unroll
+    for (int l = 0; l < KQ_LN_LMAX; ++l) eps[l] = eps_next[l];
+    dtn = dt_next;
+  }
+  if (seg_pass == 1) {
+    // column `vec` of the segment propagator (column-major)
+    if (q.act) a.seg_P[((size_t)seg * K + q.k) * NN + (size_t)vec * N + q.r] = y;
+  } else if (a.stateT && q.act && (seg_pass == 0 || seg == a.seg_count - 1)) {
+    a.stateT[(size_t)q.k * N + q.r] = y;
   }
 }
