@@ -788,6 +788,92 @@ def test_many_objectives_kernel_vs_oracle(krotov, case):
                        rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize('case', ['lambda_like_K12', 'liouville_two_controls',
+                                  'ladder_n12_complex_drive'])
+def test_entries_in_registers_kernels_vs_oracle(krotov, case):
+    """csrc/kq_lanes.cuh (lane = objective x row, <= 4 non-zeros per row kept
+    in registers, generator shifted by the drift's mid-range diagonal):
+    objectives in several warps, a Liouvillian with a complex shift, complex
+    entries for N > 4 -- against the oracle, and against the generic kernels
+    the family replaces (kq_set_option("lanes", 0))."""
+    from functools import partial
+    from oracle import krotov_oracle as orc
+    from krotov_b200.compiler import initialize_controls
+    from krotov_b200.objectives import liouvillian
+    T, nt = 4.0, 160
+    tlist = np.linspace(0, T, nt)
+    S = partial(krotov.shapes.flattop, t_start=0, t_stop=T, t_rise=0.4,
+                func='sinsq')
+    g1 = lambda t, args: 0.4 * S(t)  # noqa: E731
+    g2 = lambda t, args: 0.15 * S(t) * np.cos(2.0 * t)  # noqa: E731
+    is_super = False
+    if case == 'lambda_like_K12':
+        H0 = np.diag([0.0, 1.3 - 0.1j, 0.4]).astype(complex)
+        Ha = np.zeros((3, 3), complex); Ha[0, 1] = Ha[1, 0] = 0.5
+        Hb = np.zeros((3, 3), complex); Hb[1, 2] = Hb[2, 1] = 0.5
+        psi0 = np.array([[1], [0], [0]], dtype=complex)
+        psi1 = np.array([[0], [0], [1]], dtype=complex)
+        objs = [krotov.Objective(initial_state=psi0, target=psi1,
+                                 H=[H0 * (1 + 0.02 * k), [Ha, g1], [Hb, g2]])
+                for k in range(12)]
+    elif case == 'liouville_two_controls':
+        is_super = True
+        sx = np.array([[0, 1], [1, 0]], dtype=complex)
+        sy = np.array([[0, -1j], [1j, 0]], dtype=complex)
+        H0 = np.diag([-0.6, 0.6]).astype(complex)
+        c_op = np.sqrt(0.08) * np.array([[0, 1], [0, 0]], dtype=complex)
+        L = liouvillian([H0, [sx, g1], [sy, g2]], [c_op])
+        rho0 = np.diag([0.0, 1.0]).astype(complex)
+        rho1 = np.diag([1.0, 0.0]).astype(complex)
+        objs = [krotov.Objective(initial_state=rho0, target=rho1, H=L)]
+    else:
+        n = 12
+        a = np.diag(np.sqrt(np.arange(1, n)), 1).astype(complex)
+        H0 = np.diag(5.0 * np.arange(n) - 0.15 * np.arange(n) * (np.arange(n) - 1))
+        Hx = 0.5 * (a + a.conj().T)
+        Hy = 0.5j * (a - a.conj().T)
+        psi0 = np.zeros((n, 1), complex); psi0[0] = 1
+        psi1 = np.zeros((n, 1), complex); psi1[1] = 1
+        objs = [krotov.Objective(initial_state=psi0, target=psi1,
+                                 H=[H0.astype(complex) * (1 + 0.01 * k),
+                                    [Hx, g1], [Hy, g2]])
+                for k in range(3)]
+    opts = {g1: dict(lambda_a=1.5, update_shape=S),
+            g2: dict(lambda_a=2.5, update_shape=S)}
+    lib = krotov._lib.load()
+    results = []
+    for lanes in (1, 0):
+        assert lib.kq_set_option(b"lanes", lanes) == 0
+        results.append(krotov.optimize_pulses(
+            objs, opts, tlist, propagator=krotov.propagators.expm,
+            chi_constructor=krotov.functionals.chis_re, iter_stop=2,
+            store_all_pulses=True))
+    lib.kq_set_option(b"lanes", 1)
+    (controls, _, pulses, mapping, lam, shp) = initialize_controls(
+        objs, opts, tlist)
+
+    def vec(s):
+        s = np.asarray(s, dtype=complex)
+        return s.reshape(-1, order='F') if (s.ndim == 2 and s.shape[1] > 1) \
+            else s.ravel()
+    terms = []
+    for o in objs:
+        t = [(np.asarray(o.H[0], dtype=complex), -1)]
+        for op, ctrl in o.H[1:]:
+            idx = [i for i, c in enumerate(controls) if c is ctrl][0]
+            t.append((np.asarray(op, dtype=complex), idx))
+        terms.append(t)
+    rec = orc.optimize(
+        terms, [vec(o.initial_state) for o in objs],
+        [vec(o.target) for o in objs], pulses, shp, lam, tlist,
+        orc.chis_re, iter_stop=2, is_super=is_super, operator_norm='fro')
+    for res in results:
+        for it in (1, 2):
+            assert rel(res.all_pulses[it],
+                       rec[it]['optimized_pulses']) < PULSE_RTOL, (case, it)
+    assert rel(results[0].all_pulses[2], results[1].all_pulses[2]) < 1e-11
+
+
 # ---------------------------------------------------------------------------
 # One-launch-per-iteration kernel family (csrc/kq_picard.cuh)
 
