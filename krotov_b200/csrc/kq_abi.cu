@@ -107,6 +107,17 @@ void build_tables(KqTables& T) {
     }
     T.m_of_bin[bin] = m < 1 ? 1 : m;
   }
+  for (int i = 0; i < 4 * KQ_TAYLOR_BINS; ++i) {
+    // xs = 2^-(bin+1) (1 + f), the two leading mantissa bits of f select the quarter
+    const double b = std::min(1.0, std::ldexp(1.0 + (double)(i % 4 + 1) / 4.0, -(i / 4 + 1)));
+    double term = b;
+    int m = 0;
+    while (term > tol && m < KQ_TAYLOR_MAXM) {
+      ++m;
+      term *= b / (double)(m + 1);
+    }
+    T.m_fine[i] = (unsigned char)(m < 1 ? 1 : m);
+  }
   T.inv[0] = 0.0;
   for (int j = 1; j <= KQ_TAYLOR_MAXM; ++j) T.inv[j] = 1.0 / (double)j;
   double f = 1.0;

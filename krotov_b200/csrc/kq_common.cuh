@@ -33,6 +33,8 @@ struct KqTables {
   int m_of_bin[KQ_TAYLOR_BINS];     // Taylor degree for xs in (2^-(i+1), 2^-i]
   double inv[KQ_TAYLOR_MAXM + 1];   // 1/j
   double invfact[KQ_INVFACT_N];     // 1/n!  (closed-form N = 2 step, kq_picard.cuh)
+  // quarter-binade resolution (kq_lanes.cuh): degree for xs <= 2^-(i/4+1) (1 + (i%4 + 1) / 4)
+  unsigned char m_fine[4 * KQ_TAYLOR_BINS];
 };
 
 // Every translation unit has its own copy of the tables, uploaded once per
@@ -110,6 +112,16 @@ __device__ __forceinline__ void taylor_plan(const KqTables& T, double x, int& s,
   int bin = 1022 - e;                           // xs <= 2^-bin
   bin = max(0, min(KQ_TAYLOR_BINS - 1, bin));
   m = T.m_of_bin[bin];
+}
+
+// The same with the degree picked per QUARTER binade (the chain kernels of kq_lanes.cuh pay
+// for every Taylor term with a round of shuffles: 10-15 % fewer terms on average).
+__device__ __forceinline__ void taylor_plan_fine(const KqTables& T, double x, int& s, int& m) {
+  double xs;
+  taylor_plan(T, x, s, m, xs);
+  const int hi = __double2hiint(xs);
+  const int bin = 1022 - ((hi >> 20) & 0x7ff);
+  if (bin >= 0) m = T.m_fine[4 * min(KQ_TAYLOR_BINS - 1, bin) + ((hi >> 18) & 3)];
 }
 
 // ---- low-latency flag+data exchange (two 8-byte halves, each carrying the

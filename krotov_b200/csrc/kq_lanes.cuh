@@ -152,7 +152,9 @@ __device__ __forceinline__ bool ln_setup(const KqSweepArgs& a, const LnLane& q, 
   int cnt = 0;
   bool shifted = false, overflow = false;
   const int kk = min(q.k, K - 1), rr = min(q.r, N - 1);
-  for (int c = 0; c < N; ++c) {
+  // the diagonal first (entry 0 is the lane's own component: no shuffle), then the others
+  for (int cc = 0; cc < N; ++cc) {
+    const int c = (cc == 0) ? rr : (cc <= rr ? cc - 1 : cc);
     cplx t[KQ_MMAX_SMALL];
     bool nz = (c == rr);
 #pragma unroll
@@ -215,8 +217,7 @@ __device__ __forceinline__ cplx ln_propagate(const LnState<NZ>& S, cplx y0,
     x = __hiloint2double(hi, (int)0xffffffff);
   }
   int s, mdeg;
-  double xs;
-  taylor_plan(T, x, s, mdeg, xs);
+  taylor_plan_fine(T, x, s, mdeg);
   const double h = (s == 1) ? dtn : dtn / (double)s;
 #pragma unroll
   for (int z = 0; z < NZ; ++z) A[z] = c_make(h * A[z].x, h * A[z].y);
@@ -229,9 +230,11 @@ __device__ __forceinline__ cplx ln_propagate(const LnState<NZ>& S, cplx y0,
       cplx w0 = c_zero(), w1 = c_zero();
 #pragma unroll
       for (int z = 0; z < NZ; ++z) {
-        cplx yz;
-        yz.x = __shfl_sync(0xffffffffu, y.x, S.src[z]);
-        yz.y = __shfl_sync(0xffffffffu, y.y, S.src[z]);
+        cplx yz = y;   // entry 0: the diagonal
+        if (z > 0) {
+          yz.x = __shfl_sync(0xffffffffu, y.x, S.src[z]);
+          yz.y = __shfl_sync(0xffffffffu, y.y, S.src[z]);
+        }
         if (z & 1) w1 = c_fma(A[z], yz, w1);
         else w0 = c_fma(A[z], yz, w0);
       }
