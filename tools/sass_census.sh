@@ -20,6 +20,8 @@ for line in open(src, errors='replace'):
              'k_dp_sweep' if 'k_dp_sweep' in k else
              'k_dp_build' if 'k_dp_build' in k else
              'k_dp_(plan|segprod|expand|epilogue)' if 'k_dp_' in k else
+             'k_fwupd_sat' if 'k_fwupd_sat' in k else
+             'k_fwupd_rows / k_prop_rows / k_rows_prep' if '_rows' in k and 'k_seg_chain' not in k else
              'k_sweep_csr' if 'k_sweep_csr' in k else
              'k_sweep_warp' if 'k_sweep_warp' in k else
              'k_fwupd_spec' if 'k_fwupd_spec' in k else
