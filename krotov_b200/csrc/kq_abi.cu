@@ -1034,6 +1034,93 @@ int composite_iteration(const kq_problem* p, DpPlan& dp, KqSweepArgs a, int chi_
   return kq_launch_dpoly_epilogue(a, dp.d, 0, st);
 }
 
+
+// sum_j w_j tau_j (chis_sm, functionals.py:225-253), fixed order
+__global__ void k_tau_sum(int K, const cplx* __restrict__ tau, const double* __restrict__ weights,
+                          cplx* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double x = 0.0, y = 0.0;
+  for (int j = 0; j < K; ++j) {
+    const double w = weights ? weights[j] : 1.0;
+    x = fma(w, tau[j].x, x);
+    y = fma(w, tau[j].y, y);
+  }
+  out[0] = c_make(x, y);
+}
+// status words of a composite iteration that cannot decline: {status, 0, 0, 0}
+__global__ void k_diag_ok(const int* status, int* diag_out) {
+  if (threadIdx.x == 0) {
+    diag_out[0] = *reinterpret_cast<const volatile int*>(status);
+    diag_out[1] = 0;
+    diag_out[2] = 0;
+    diag_out[3] = 0;
+  }
+}
+
+// One Krotov iteration as a sequence of launches for the entries-in-registers family
+// (kq_lanes.cuh: few objectives, several controls or sparse rows, first order, one GPU):
+// chi boundary | time-parallel backward sweep | pre-pass | update chain | tau.
+int rows_iteration(const kq_problem* p, KqLanes& ln, KqSweepArgs a, int chi_kind, int K_total,
+                   const cplx* tau_sum_in, const double* guess_pulses, void* workspace, int dev,
+                   cudaStream_t st) {
+  const int K = p->K, N = p->N, NT = p->NT;
+  const size_t xb = ((size_t)(NT + 1) * K * N * sizeof(cplx) + 255) / 256 * 256;
+  const size_t sb = ((size_t)K * N * sizeof(cplx) + 255) / 256 * 256;
+  const size_t nb = ((size_t)K * sizeof(double) + 255) / 256 * 256;
+  void* base = nullptr;
+  int rc = get_scratch(dev, xb + 2 * sb + nb + 256, &base, 1);
+  if (rc) return rc;
+  char* cur = static_cast<char*>(base);
+  cplx* sX = reinterpret_cast<cplx*>(cur);
+  cur += xb;
+  cplx* schi = reinterpret_cast<cplx*>(cur);
+  cur += sb;
+  cplx* sphiT = reinterpret_cast<cplx*>(cur);
+  cur += sb;
+  double* snorms = reinterpret_cast<double*>(cur);
+  cur += nb;
+  cplx* stsum = reinterpret_cast<cplx*>(cur);
+  cplx* X = a.Xout ? a.Xout : sX;
+  const cplx* chi = a.chiT;
+  const double* norms = a.chi_norms;
+  if (chi_kind >= 0) {
+    cplx* chi_w = a.chi_out ? a.chi_out : schi;
+    double* norms_w = a.chi_norms_out ? a.chi_norms_out : snorms;
+    const cplx* tsum = tau_sum_in;
+    if (chi_kind == KQ_CHI_SM && !tsum) {
+      k_tau_sum<<<1, 32, 0, st>>>(K, a.tau_in, a.weights, stsum);
+      KQ_CUDA(cudaGetLastError());
+      tsum = stsum;
+    }
+    const int bt = 128;
+    k_chi_boundary<<<(K + bt - 1) / bt, bt, 0, st>>>(K, N, chi_kind, K_total, a.phiT_in, a.targets,
+                                                     a.tau_in, a.weights, tsum, chi_w, norms_w);
+    KQ_CUDA(cudaGetLastError());
+    chi = chi_w;
+    norms = norms_w;
+  }
+  rc = run_prop(p, true, guess_pulses, reinterpret_cast<const kq_c128*>(chi), nullptr,
+                reinterpret_cast<kq_c128*>(X), st);
+  if (rc) return rc;
+  if (!a.stateT) a.stateT = sphiT;
+  a.X = X;
+  a.chi_norms = norms;
+  a.status = reinterpret_cast<int*>(workspace);
+  a.cond_epoch = 0;
+  rc = launch_lanes_update(p, a, ln, p->is_super ? 2 : 0, st);
+  if (rc) return rc;
+  if (a.tau_out && a.targets) {
+    const int bt = 128;
+    k_overlaps<<<(K + bt - 1) / bt, bt, 0, st>>>(K, N, a.targets, a.stateT, a.tau_out);
+    KQ_CUDA(cudaGetLastError());
+  }
+  if (a.diag_out) {
+    k_diag_ok<<<1, 32, 0, st>>>(a.status, a.diag_out);
+    KQ_CUDA(cudaGetLastError());
+  }
+  return KQ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1393,8 +1480,17 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   const int K_plan = world > 1 ? (K_total + world - 1) / world : p->K;
   DpPlan dp;
   const bool composite = !second && world == 1 && dpoly_preferred(p) && dpoly_plan(p, dp);
-  if (!composite &&
-      (!g_picard || !g_dev[dev].coop || !picard_plan(p, g_dev[dev].sms, pp, K_plan)))
+  const bool fixed_point =
+      !composite && g_picard && g_dev[dev].coop && picard_plan(p, g_dev[dev].sms, pp, K_plan);
+  // what neither takes: few objectives with several controls or sparse rows (kq_lanes.cuh)
+  KqLanes ln;
+  bool rows = false;
+  if (!composite && !fixed_point && !second && world == 1) {
+    KqSweepArgs probe = base_args(p);
+    KqLanes lp;
+    rows = p->ops && p->ops_adj && lanes_plan(p, probe, ln) && prop_lanes_plan(p, lp);
+  }
+  if (!composite && !fixed_point && !rows)
     return fail(KQ_ERR_UNSUPPORTED, "problem is outside the time-parallel kernel family");
   KqSweepArgs a = base_args(p);
   if (world > 1) {
@@ -1433,6 +1529,11 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
     a.status = reinterpret_cast<int*>(workspace);
     return composite_iteration(p, dp, a, chi_kind, workspace, dev,
                                static_cast<cudaStream_t>(stream));
+  }
+  if (rows) {
+    a.epoch = epoch ? epoch : 1u;
+    return rows_iteration(p, ln, a, chi_kind, K_total, reinterpret_cast<const cplx*>(tau_sum),
+                          guess_pulses, workspace, dev, static_cast<cudaStream_t>(stream));
   }
   return launch_picard(p, a, pp, workspace, epoch, second, static_cast<cudaStream_t>(stream));
 }

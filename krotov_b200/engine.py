@@ -295,8 +295,15 @@ class SweepEngine:
         # the library declines (KQ_ERR_UNSUPPORTED) what its kernel families
         # do not cover: N <= 4 runs the time-parallel fixed-point kernel, few
         # objectives with N >= 3 the delta-polynomial sweep (csrc/kq_dpoly.cuh)
-        return (self.gather is None and cp.M == 2 and cp.L == 1
-                and 2 <= cp.N <= 16)
+        if self.gather is None and cp.M == 2 and cp.L == 1 and 2 <= cp.N <= 16:
+            return True
+        # few objectives with several controls or sparse rows: the
+        # entries-in-registers kernels (csrc/kq_lanes.cuh), one call per
+        # iteration as well
+        nnz = getattr(cp, 'row_nnz', 0) or cp.N
+        return (self.gather is None and self.comm is None
+                and cp.ops is not None and 2 <= cp.N <= 32 and 1 <= cp.L <= 4
+                and cp.M <= 5 and nnz <= 4)
 
     def clear_fused_failure(self):
         """Reset the 'first failed epoch' status word."""

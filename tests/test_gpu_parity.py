@@ -305,6 +305,9 @@ def test_lambda_system_four_controls_nonhermitian(krotov, golden, engine_mode):
                        engine_mode=engine_mode)
     assert rec.pulses[0].shape == (4, 499)
     check_against_golden(rec, g, 3)
+    # one ABI call per iteration (kq_krotov_iteration -> csrc/kq_lanes.cuh)
+    # unless the sweep calls were asked for
+    assert res.fused_iterations == (3 if engine_mode is None else 0)
     assert np.allclose(rec.bw, g['backward_states_it1'], rtol=0, atol=1e-12)
     assert rel(res.optimized_controls, g['optimized_controls']) < PULSE_RTOL
     # the imaginary-part pulses start from zero and must have moved

@@ -24,15 +24,19 @@ for name, make in CASES:
         continue
     wl = make()
     chi = getattr(krotov.functionals, 'chis_' + wl.chi)
-    def run(n):
+    def run(n, **kw):
         return krotov.optimize_pulses(
             wl.objectives(krotov.Objective), wl.pulse_options, wl.tlist,
-            propagator=krotov.propagators.expm, chi_constructor=chi, iter_stop=n)
+            propagator=krotov.propagators.expm, chi_constructor=chi, iter_stop=n, **kw)
     run(2)
     torch.cuda.synchronize()
     t0 = time.perf_counter(); r1 = run(5); torch.cuda.synchronize(); t1 = time.perf_counter()
     r2 = run(5 + iters); torch.cuda.synchronize(); t2 = time.perf_counter()
     gpu = iters / ((t2 - t1) - (t1 - t0))
+    # the same with a host hook per iteration (as the reference's notebooks run: print_table)
+    stamps = []
+    run(5 + iters, info_hook=lambda **kw: stamps.append(time.perf_counter()))
+    hooked = iters / (stamps[-1] - stamps[-1 - iters])
     low = wl.lowered()
     chi_o = getattr(orc, 'chis_' + wl.chi)
     with threadpool_limits(1):
@@ -42,6 +46,6 @@ for name, make in CASES:
                      weights=low['weights'])
         cpu = time.perf_counter() - t0
     # iteration 0 (forward propagation) is about a third of the oracle's 1-iteration run
-    print("%-52s GPU %8.1f it/s   CPU port (1 core) %6.2f it/s   fused=%s launches/it=%.1f" % (
-        name, gpu, 1.0 / (cpu * 2.0 / 3.0), getattr(r2, 'fused_iterations', None),
+    print("%-52s GPU %8.1f it/s (with a hook per iteration %8.1f)   CPU port (1 core) %6.2f it/s   fused=%s launches/it=%.1f" % (
+        name, gpu, hooked, 1.0 / (cpu * 2.0 / 3.0), getattr(r2, 'fused_iterations', None),
         (r2.gpu_launches - r1.gpu_launches) / iters), flush=True)
