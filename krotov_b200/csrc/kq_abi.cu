@@ -1162,6 +1162,11 @@ int kq_set_option(const char* name, int value) {
     g_lanes = value ? 1 : 0;
     return KQ_OK;
   }
+  if (name && std::strcmp(name, "sat_min_kpc") == 0) {
+    if (value < 2 || value > 896) return fail(KQ_ERR_ARG, "sat_min_kpc must be in [2, 896]");
+    g_kq_sat_min_kpc = value;
+    return KQ_OK;
+  }
   if (name && std::strcmp(name, "sat") == 0) {
     g_sat = value ? 1 : 0;
     return KQ_OK;

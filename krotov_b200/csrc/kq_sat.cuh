@@ -8,9 +8,9 @@
 //   * one CTA per SM (co-resident grid); warps 2..15 are CONSUMERS with TWO objectives per
 //     thread (14 warps instead of 32 at the CTA barriers of a step, 128 registers per thread
 //     -- the 1024-thread kernel of kq_spec.cuh spills at 64 --, two independent chains per
-//     thread); warp 0 owns no objectives: it reduces the warps' partial sums, publishes the
-//     CTA's sum and gathers the other CTAs' (objectives in the exchange warp would put their
-//     work on the critical path); warp 1 issues the TMA copies (measured: a bulk-copy issue
+//     thread); warp 0 owns no objectives: it reduces the warps' partial sums and publishes the
+//     CTA's sum (objectives in the exchange warp would put their work on the critical path);
+//     warp 1 issues the TMA copies (measured: a bulk-copy issue
 //     holds its warp, and the warp's next shared-memory access, for 500-3000 cycles -- from the
 //     exchange warp that delay lands on every CTA of the grid);
 //   * the backward states of a time step are one contiguous row per CTA (time-major
@@ -18,10 +18,16 @@
 //     ahead of their use; eta = mu^dag chi ||chi|| of the next step is formed while the
 //     reduction of this one is under way;
 //   * CTAs exchange their partial sums through flag-tagged 16-byte slots in L2 (kq_common.cuh):
-//     every CTA PUSHES its sum into a mailbox per CTA, so that a mailbox's lines are polled by
-//     one CTA only; warp 0 polls all slots of its mailbox with the loads in flight together
-//     (one L2 round trip per poll instead of one per slot) and every CTA adds them in the same
-//     order: identical pulses in every CTA, no atomics;
+//     every CTA PUSHES its sum into a mailbox per CTA (two 64-bit max-reductions performed at
+//     L2: {tag, half of the value}; plain stores took 0.6k cycles longer to become visible), so
+//     that a mailbox's lines are polled by one CTA only; FIVE consumer warps -- idle while the
+//     exchange is in flight -- poll 32 slots each with ONE load per lane (a coherent load costs
+//     ~1000 cycles here and the loads of one thread complete one after the other: five slots
+//     per lane in one warp cost 1.6k cycles per poll) and every CTA adds the values in the same
+//     order: identical pulses in every CTA, no floating-point atomics.  Measured and
+//     rejected: several polling loads in flight per lane, polling with atom.or, a delay in
+//     front of the first poll, fewer and fuller CTAs (the hop costs the same for 19 and for
+//     148 participants: it is latency, not contention);
 //   * the step itself is the closed form of exp(iR) for a real 2 x 2 generator (kq_spec.cuh),
 //     its series degree planned from the guess pulse and verified after the update; B200
 //     issues 58 DFMA per clock and SM, so the loop body is kept to about 50 FP64 operations
@@ -33,42 +39,19 @@
 #define KQ_SAT_THREADS (KQ_SAT_BT + 64)
 #define KQ_SAT_OPT 2
 #define KQ_SAT_RING 4
-#define KQ_SAT_NB 5       // slots polled per lane and batch (32 * NB CTAs per batch)
+#define KQ_SAT_NG 5       // consumer warps that gather the mailbox: 32 slots each (grid <= 160)
 
-// All slots of a batch with their loads in flight together; returns the number of polls.
-template <int NB>
-__device__ __forceinline__ int sat_wait_batch(const KqSlot* const (&p)[NB], const bool (&act)[NB],
-                                              uint32_t tag, double (&v)[NB], bool& failed) {
-#pragma unroll
-  for (int u = 0; u < NB; ++u) v[u] = 0.0;
-  if (failed) return 0;
-  for (int spin = 0; spin < (1 << 22); ++spin) {
-    uint32_t lo[NB], t0[NB], hi[NB], t1[NB];
-#pragma unroll
-    for (int u = 0; u < NB; ++u)
-      asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(lo[u]), "=r"(t0[u]), "=r"(hi[u]), "=r"(t1[u])
-                   : "l"(p[u])
-                   : "memory");
-    bool all = true;
-#pragma unroll
-    for (int u = 0; u < NB; ++u) {
-      const bool ok = !act[u] || (t0[u] == tag && t1[u] == tag);
-      all = all && ok;
-      if (act[u]) v[u] = __hiloint2double((int)hi[u], (int)lo[u]);
-    }
-    if (__all_sync(0xffffffffu, all)) return spin + 1;
-  }
-  failed = true;
-  return 0;
-}
+// Publication of a slot as two 64-bit REDUCTIONS (max) performed at L2: {tag, half of the
+// value} with the tag in the high word -- tags only grow, so the maximum is the newest entry.
+// A reduction is carried out where the pollers read; plain stores were measured to take
+// 1.5k+ cycles until a poller on another SM sees them.
 __device__ __forceinline__ void sat_slot_store(KqSlot* p, double v, uint32_t tag) {
-  uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(tag),
-               "r"(hi), "r"(tag)
+  const unsigned long long w0 = ((unsigned long long)tag << 32) | (uint32_t)__double2loint(v);
+  const unsigned long long w1 = ((unsigned long long)tag << 32) | (uint32_t)__double2hiint(v);
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(w0) : "memory");
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(reinterpret_cast<char*>(p) + 8), "l"(w1)
                : "memory");
 }
-
 __device__ __forceinline__ void sat_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -149,7 +132,7 @@ __device__ __forceinline__ void sat_step(SatObj (&o)[KQ_SAT_OPT], double h, doub
 }
 
 // CTA = warp 0 (exchange) + warp 1 (TMA producer) + KQ_SAT_BT consumer threads.
-// shared: red [2][16] | tot [2] (+ pad) | mbar [RING] | empty [RING] | sdt, sg, ssl, sbound [KQ_NTC] |
+// shared: red [2][16] | gpart [2][8] (+ pad) | mbar [RING] | empty [RING] | sdt, sg, ssl, sbound [KQ_NTC] |
 //         splan [KQ_NTC] | ring [RING][kpc][2] | M [kpc][4] (||chi|| mu^T, real)
 __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepArgs a, int kpc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,8 +143,8 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
   const int k0 = blockIdx.x * kpc;
   const int kcta = max(0, min(kpc, K - k0));   // objectives of this CTA (0 for idle CTAs)
   double* red = reinterpret_cast<double*>(smem_raw);            // [2][16]
-  double* tot = red + 32;                                       // [2] (+ pad to 40 doubles)
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 40);       // [RING] row has landed
+  double* gpart = red + 32;                                     // [2][8] gathered sums per polling warp
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(red + 56);       // [RING] row has landed
   uint64_t* empty = mbar + KQ_SAT_RING;                         // [RING] row has been read
   double* sdt = reinterpret_cast<double*>(empty + KQ_SAT_RING);
   double* sg = sdt + KQ_NTC;
@@ -183,6 +166,7 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < 16) gpart[tid] = 0.0;
   // idle CTAs never fill the ring: their (weight-zero) threads must still read finite numbers
   if (kcta == 0)
     for (size_t i = tid; i < (size_t)KQ_SAT_RING * stage; i += KQ_SAT_THREADS) ring[i] = c_zero();
@@ -286,7 +270,7 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
   double ga = 0.0;
   // optional per-phase cycle counts, kq_set_option("picard_timing", 1): thread 0 (exchange
   // warp) and thread 64 (first consumer) of CTA 0
-  const bool timing = a.pic_timing && blockIdx.x == 0 && (tid == 0 || tid == 64);
+  const bool timing = a.pic_timing && (tid == 0 || (tid == 64 && blockIdx.x == 0));
   long long tacc[4] = {0, 0, 0, 0}, tprev = 0, npoll = 0;
 #define KQ_SAT_TICK(i)                  \
   if (timing) {                         \
@@ -312,53 +296,20 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
     sat_bar_a();
     if (timing) tprev = clock64();
     if (warp == 0) {
-      // ---- exchange warp ------------------------------------------------------------
+      // ---- exchange warp: the CTA's sum goes into the mailbox of every CTA (a mailbox's lines
+      // are polled by their owner only -- a slot array read by all CTAs serialises 148 readers
+      // on every line)
       for (int j = 0; j < len; ++j) {
         const int n = base + j, par = n & 1;
         sat_bar_a();   // barrier A: the consumer warps' partial sums are in red[par]
         KQ_SAT_TICK(0)
         double acc = (lane < NCW) ? red[par * 16 + lane] : 0.0;
         acc = warp_allreduce_sum(acc);
-        if (nblk > 1) {
-          const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
-          // push: this CTA's sum goes into the mailbox of every CTA (lines of a mailbox are
-          // polled by their owner only -- a slot array read by all CTAs serialises 148 readers
-          // on every line), then the own mailbox [par][me][writer] is gathered
-          KqSlot* box = a.slots + (size_t)par * nblk * nblk;
-          for (int r = lane; r < nblk; r += 32)
-            sat_slot_store(box + (size_t)r * nblk + blockIdx.x, acc, tag);
-          KQ_SAT_TICK(1)
-          const KqSlot* sl0 = box + (size_t)blockIdx.x * nblk;
-          double g2 = 0.0;
-          for (int q0 = 0; q0 < nblk; q0 += 32 * KQ_SAT_NB) {
-            const KqSlot* p[KQ_SAT_NB];
-            bool act[KQ_SAT_NB];
-            double v[KQ_SAT_NB];
-#pragma unroll
-            for (int u = 0; u < KQ_SAT_NB; ++u) {
-              const int q = q0 + u * 32 + lane;
-              act[u] = q < nblk;
-              p[u] = sl0 + (act[u] ? q : 0);
-            }
-            npoll += sat_wait_batch<KQ_SAT_NB>(p, act, tag, v, failed);
-#pragma unroll
-            for (int u = 0; u < KQ_SAT_NB; ++u) g2 += act[u] ? v[u] : 0.0;
-          }
-          acc = warp_allreduce_sum(g2);
-        }
-        if (lane == 0) tot[par] = acc;
-        // barrier B: release the consumers (this warp does not wait)
-        asm volatile("bar.arrive 1, %0;" ::"n"(KQ_SAT_BT + 32) : "memory");
-        KQ_SAT_TICK(2)
-        if (lane == 0) {
-          if (blockIdx.x == 0) {   // pulse update (optimize.py:471-477)
-            const double sl = ssl[j], d1 = acc;
-            a.opt_pulses[n] = __dadd_rn(sg[j], __dmul_rn(sl, d1));
-            ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), sdt[j]));
-          }
-        }
-        __syncwarp();
-        KQ_SAT_TICK(3)
+        const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
+        KqSlot* box = a.slots + (size_t)par * nblk * nblk;
+        for (int r = lane; r < nblk; r += 32)
+          sat_slot_store(box + (size_t)r * nblk + blockIdx.x, acc, tag);
+        KQ_SAT_TICK(1)
       }
       continue;
     }
@@ -385,9 +336,44 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
       __syncwarp();
       if (lane == 0) sat_mbar_arrive(&empty[(n + 1) % KQ_SAT_RING]);   // row n + 1 is consumed
       KQ_SAT_TICK(1)
-      asm volatile("bar.sync 1, %0;" ::"n"(KQ_SAT_BT + 32) : "memory");   // barrier B
+      // gather: the first KQ_SAT_NG consumer warps poll 32 slots of this CTA's mailbox each,
+      // ONE load per lane (loads of one thread complete one after the other: five slots per
+      // lane in the exchange warp cost 1.6k cycles per poll); by now -- eta took 600-1100
+      // cycles -- the peers' reductions have mostly landed
+      if (warp - 2 < KQ_SAT_NG) {
+        const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
+        const int q = (warp - 2) * 32 + lane;
+        const bool act = q < nblk;
+        const KqSlot* p = a.slots + (size_t)par * nblk * nblk + (size_t)blockIdx.x * nblk + (act ? q : 0);
+        double v = 0.0;
+        if (!failed) {
+          int spin = 0;
+          for (; spin < (1 << 22); ++spin) {
+            uint32_t lo, t0, hi, t1;
+            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1)
+                         : "l"(p)
+                         : "memory");
+            const bool ok = !act || (t0 == tag && t1 == tag);
+            v = act ? __hiloint2double((int)hi, (int)lo) : 0.0;
+            if (__all_sync(0xffffffffu, ok)) break;
+          }
+          npoll += spin + 1;
+          if (spin == (1 << 22)) failed = true;
+        }
+        v = warp_allreduce_sum(failed ? 0.0 : v);
+        if (lane == 0) gpart[par * 8 + warp - 2] = v;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(KQ_SAT_BT) : "memory");   // barrier B (consumers)
       KQ_SAT_TICK(2)
-      const double d1 = tot[par];
+      double d1 = gpart[par * 8];
+#pragma unroll
+      for (int w2 = 1; w2 < KQ_SAT_NG; ++w2) d1 += gpart[par * 8 + w2];
+      if (blockIdx.x == 0 && tid == 64) {   // pulse update (optimize.py:471-477)
+        const double sl = ssl[j];
+        a.opt_pulses[n] = __dadd_rn(sg[j], __dmul_rn(sl, d1));
+        ga = __dadd_rn(ga, __dmul_rn(__dmul_rn(sl, __dmul_rn(d1, d1)), sdt[j]));
+      }
       const double dt_cur = sdt[j];
       const double eps_new = __dadd_rn(sg[j], __dmul_rn(ssl[j], d1));
       // forward step under the updated pulse (series degree planned from the guess pulse,
@@ -416,16 +402,23 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
       KQ_SAT_TICK(3)
     }
   }
-  if (timing) {
+  if (timing && blockIdx.x == 0) {
     long long* out = reinterpret_cast<long long*>(a.status + 16) + (tid == 0 ? 0 : 5);
     for (int i = 0; i < 4; ++i) out[i] = tacc[i];
     out[4] = npoll;
   }
-  if (xwarp) {
-    if (blockIdx.x == 0 && tid == 0) a.g_a[0] = ga;
-    if (failed) atomicExch(a.status, (int)-4);
-    return;
+  if (timing && tid == 0) {
+    // every CTA's exchange-warp counters behind the mailboxes: [cta][4 phases + polls + smid]
+    long long* all = reinterpret_cast<long long*>(a.slots + (size_t)2 * nblk * nblk) + (size_t)blockIdx.x * 6;
+    for (int i = 0; i < 4; ++i) all[i] = tacc[i];
+    all[4] = npoll;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    all[5] = smid;
   }
+  if (failed) atomicExch(a.status, (int)-4);
+  if (xwarp) return;
+  if (blockIdx.x == 0 && tid == 64) a.g_a[0] = ga;
   if (a.stateT) {
 #pragma unroll
     for (int q = 0; q < KQ_SAT_OPT; ++q) {
