@@ -231,17 +231,18 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
   double w[KQ_SAT_OPT];
 #pragma unroll
   for (int q = 0; q < KQ_SAT_OPT; ++q) w[q] = (!xwarp && ctid + q * KQ_SAT_BT < kcta) ? 1.0 : 0.0;
+  auto make_eta_q = [&](int st, int q, cplx (&dst)[KQ_SAT_OPT][2]) {
+    const cplx* row = ring + st * stage + (size_t)kl[q] * 2;
+    const cplx x0 = row[0], x1 = row[1];
+    const double2 m0 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4);
+    const double2 m1 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4 + 2);
+    // eta_c = sum_r M[c][r] chi_r (element (r, c) of mu at c * 2 + r)
+    dst[q][0] = make_double2(w[q] * fma(m0.x, x0.x, m0.y * x1.x), w[q] * fma(m0.x, x0.y, m0.y * x1.y));
+    dst[q][1] = make_double2(w[q] * fma(m1.x, x0.x, m1.y * x1.x), w[q] * fma(m1.x, x0.y, m1.y * x1.y));
+  };
   auto make_eta = [&](int st, cplx (&dst)[KQ_SAT_OPT][2]) {
 #pragma unroll
-    for (int q = 0; q < KQ_SAT_OPT; ++q) {
-      const cplx* row = ring + st * stage + (size_t)kl[q] * 2;
-      const cplx x0 = row[0], x1 = row[1];
-      const double2 m0 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4);
-      const double2 m1 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4 + 2);
-      // eta_c = sum_r M[c][r] chi_r (element (r, c) of mu at c * 2 + r)
-      dst[q][0] = make_double2(w[q] * fma(m0.x, x0.x, m0.y * x1.x), w[q] * fma(m0.x, x0.y, m0.y * x1.y));
-      dst[q][1] = make_double2(w[q] * fma(m1.x, x0.x, m1.y * x1.x), w[q] * fma(m1.x, x0.y, m1.y * x1.y));
-    }
+    for (int q = 0; q < KQ_SAT_OPT; ++q) make_eta_q(st, q, dst);
   };
   if (warp == 1) {
     // ---- producer warp: row r goes into stage r % RING as soon as every consumer warp has
@@ -331,32 +332,40 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
         const int r = n + 1, st = r % KQ_SAT_RING;
         if (kcta > 0) mbar_wait(&mbar[st], (uint32_t)((r / KQ_SAT_RING) & 1));
       }
+      // gather: the first KQ_SAT_NG consumer warps poll 32 slots of this CTA's mailbox each,
+      // ONE load per lane (loads of one thread complete one after the other: five slots per
+      // lane in the exchange warp cost 1.6k cycles per poll).  The first poll is issued between
+      // the two halves of eta: it samples the mailbox about when the peers' reductions land,
+      // and its ~1000 cycles pass under the second half
+      const bool helper = warp - 2 < KQ_SAT_NG;
+      const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
+      const int gq = (warp - 2) * 32 + lane;
+      const bool gact = helper && gq < nblk;
+      const KqSlot* gp = a.slots + (size_t)par * nblk * nblk + (size_t)blockIdx.x * nblk + (gact ? gq : 0);
+      uint32_t lo = 0, t0 = 0, hi = 0, t1 = 0;
       cplx eta_next[KQ_SAT_OPT][2];
-      make_eta((n + 1) % KQ_SAT_RING, eta_next);
+      make_eta_q((n + 1) % KQ_SAT_RING, 0, eta_next);
+      if (helper)
+        asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1)
+                     : "l"(gp)
+                     : "memory");
+      make_eta_q((n + 1) % KQ_SAT_RING, 1, eta_next);
       __syncwarp();
       if (lane == 0) sat_mbar_arrive(&empty[(n + 1) % KQ_SAT_RING]);   // row n + 1 is consumed
       KQ_SAT_TICK(1)
-      // gather: the first KQ_SAT_NG consumer warps poll 32 slots of this CTA's mailbox each,
-      // ONE load per lane (loads of one thread complete one after the other: five slots per
-      // lane in the exchange warp cost 1.6k cycles per poll); by now -- eta took 600-1100
-      // cycles -- the peers' reductions have mostly landed
-      if (warp - 2 < KQ_SAT_NG) {
-        const uint32_t tag = a.tag_base + (uint32_t)n + 1u;
-        const int q = (warp - 2) * 32 + lane;
-        const bool act = q < nblk;
-        const KqSlot* p = a.slots + (size_t)par * nblk * nblk + (size_t)blockIdx.x * nblk + (act ? q : 0);
+      if (helper) {
         double v = 0.0;
         if (!failed) {
           int spin = 0;
           for (; spin < (1 << 22); ++spin) {
-            uint32_t lo, t0, hi, t1;
+            const bool ok = !gact || (t0 == tag && t1 == tag);
+            v = gact ? __hiloint2double((int)hi, (int)lo) : 0.0;
+            if (__all_sync(0xffffffffu, ok)) break;
             asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1)
-                         : "l"(p)
+                         : "l"(gp)
                          : "memory");
-            const bool ok = !act || (t0 == tag && t1 == tag);
-            v = act ? __hiloint2double((int)hi, (int)lo) : 0.0;
-            if (__all_sync(0xffffffffu, ok)) break;
           }
           npoll += spin + 1;
           if (spin == (1 << 22)) failed = true;
