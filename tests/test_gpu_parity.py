@@ -792,7 +792,8 @@ def test_many_objectives_kernel_vs_oracle(krotov, case):
 
 
 @pytest.mark.parametrize('case', ['lambda_like_K12', 'liouville_two_controls',
-                                  'ladder_n12_complex_drive'])
+                                  'ladder_n12_complex_drive',
+                                  'ladder_n6_scaled_steps_ragged_grid'])
 def test_entries_in_registers_kernels_vs_oracle(krotov, case):
     """csrc/kq_lanes.cuh (lane = objective x row, <= 4 non-zeros per row kept
     in registers, generator shifted by the drift's mid-range diagonal):
@@ -829,6 +830,23 @@ def test_entries_in_registers_kernels_vs_oracle(krotov, case):
         rho0 = np.diag([0.0, 1.0]).astype(complex)
         rho1 = np.diag([1.0, 0.0]).astype(complex)
         objs = [krotov.Objective(initial_state=rho0, target=rho1, H=L)]
+    elif case == 'ladder_n6_scaled_steps_ragged_grid':
+        # ||A|| dt > 1 after the shift (repeated scaled Taylor steps), a time grid
+        # with unequal intervals, five objectives in two warps (the second
+        # partially filled)
+        n = 6
+        tlist = np.concatenate([np.linspace(0, 1.0, 40, endpoint=False),
+                                np.linspace(1.0, T, 90)])
+        a = np.diag(np.sqrt(np.arange(1, n)), 1).astype(complex)
+        H0 = np.diag(45.0 * np.arange(n) - 2.0 * np.arange(n) * (np.arange(n) - 1))
+        Hx = 0.5 * (a + a.conj().T)
+        Hy = 0.5j * (a - a.conj().T)
+        psi0 = np.zeros((n, 1), complex); psi0[0] = 1
+        psi1 = np.zeros((n, 1), complex); psi1[1] = 1
+        objs = [krotov.Objective(initial_state=psi0, target=psi1,
+                                 H=[H0.astype(complex) * (1 + 0.01 * k),
+                                    [Hx, g1], [Hy, g2]])
+                for k in range(5)]
     else:
         n = 12
         a = np.diag(np.sqrt(np.arange(1, n)), 1).astype(complex)
