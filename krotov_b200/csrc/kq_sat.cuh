@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
   if (tid == 0) {
     for (int st = 0; st < KQ_SAT_RING; ++st) {
       mbar_init(&mbar[st], 1);
-      mbar_init(&empty[st], (uint32_t)NCW);   // lane 0 of every consumer warp
+      mbar_init(&empty[st], (uint32_t)KQ_SAT_BT);   // every consumer thread releases what it read
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -265,8 +265,7 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
       o[q].eta[0] = e0[q][0];
       o[q].eta[1] = e0[q][1];
     }
-    __syncwarp();
-    if (warp >= 2 && lane == 0) sat_mbar_arrive(&empty[0]);
+    if (warp >= 2) sat_mbar_arrive(&empty[0]);
   }
   double ga = 0.0;
   // optional per-phase cycle counts, kq_set_option("picard_timing", 1): thread 0 (exchange
@@ -351,8 +350,7 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
                      : "l"(gp)
                      : "memory");
       make_eta_q((n + 1) % KQ_SAT_RING, 1, eta_next);
-      __syncwarp();
-      if (lane == 0) sat_mbar_arrive(&empty[(n + 1) % KQ_SAT_RING]);   // row n + 1 is consumed
+      sat_mbar_arrive(&empty[(n + 1) % KQ_SAT_RING]);   // row n + 1 is consumed
       KQ_SAT_TICK(1)
       if (helper) {
         double v = 0.0;
