@@ -205,8 +205,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_csr(const KqSweepArgs a, cons
     for (int m = 0; m < M; ++m) x = fma(fabs(scoef[m]), opn[m], x);
     x *= dtn;
     int sc, mdeg;
-    double xs;
-    taylor_plan(T, x, sc, mdeg, xs);
+    taylor_plan_fine(T, x, sc, mdeg);   // quarter-binade degrees: every term is a pass over the matrix
     const double h = (sc == 1) ? dtn : dtn / (double)sc;
     for (int rep = 0; rep < sc; ++rep) {
       const cplx v = y;

@@ -315,8 +315,7 @@ k_sweep_warp(const KqSweepArgs a, const KqWarpGeom g) {
       x = __hiloint2double(hi, (int)0xffffffff);
     }
     int s, mdeg;
-    double xs;
-    taylor_plan(T, x, s, mdeg, xs);
+    taylor_plan_fine(T, x, s, mdeg);   // quarter-binade degrees
     const double h = (s == 1) ? dtn : dtn / (double)s;
     __syncwarp();
     for (int rep = 0; rep < s; ++rep) {
