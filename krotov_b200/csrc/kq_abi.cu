@@ -1490,7 +1490,10 @@ int kq_krotov_iteration(const kq_problem* p, int chi_kind, int32_t K_total,
   // what neither takes: few objectives with several controls or sparse rows (kq_lanes.cuh)
   KqLanes ln;
   bool rows = false;
-  if (!composite && !fixed_point && !second && world == 1) {
+  // (not the M = 2, L = 1, N <= 4 family: what the one-launch kernel declines there -- long
+  // grids -- is served better by the windowed fixed point of kq_sweep_forward_update)
+  if (!composite && !fixed_point && !second && world == 1 &&
+      !(p->N <= 4 && p->M == 2 && p->L == 1)) {
     KqSweepArgs probe = base_args(p);
     KqLanes lp;
     rows = p->ops && p->ops_adj && lanes_plan(p, probe, ln) && prop_lanes_plan(p, lp);
