@@ -156,6 +156,11 @@ const char* kq_last_error(void);
  * of cudaLaunchCooperativeKernel (co-residency is still checked against the
  * occupancy limit; the kernels wait for the preceding launches before they
  * touch memory).
+ * "lanes" (default 1): the entries-in-registers kernels (csrc/kq_lanes.cuh) for few
+ * objectives with several controls or sparse rows, 0: the generic kernels instead;
+ * "sat" (default 1): the many-objective update sweep (csrc/kq_sat.cuh: N = 2, real
+ * generator, more objectives than one CTA of the sequential kernel holds), 0: the
+ * sequential kernel with its per-step slot exchange.
  * "dpoly" (default 1): the delta-polynomial Krotov iteration (csrc/kq_dpoly.cuh: few
  * objectives, one control, first order; per time step ONE small matrix-vector product
  * with a step propagator that is a polynomial in the deviation of the pulse from an
@@ -271,9 +276,15 @@ int kq_sweep_forward_update(const kq_problem* p, const double* guess_pulses,
  * iteration.  tau_out / phiT_out / X hold this rank's objectives.  For
  * KQ_CHI_SM tau_sum points to sum_j w_j tau_j over ALL ranks (one complex value
  * on the device, e.g. from an NCCL all-reduce on the same stream); NULL otherwise.
- * Returns KQ_ERR_UNSUPPORTED when the problem is outside the
- * family (N in 2..4, state stores fit shared memory): use the four-call
- * sequence then.  If the fixed-point
+ * Two more kernel families stand behind the same call (several launches, one call):
+ * the delta-polynomial iteration ("dpoly" option: few objectives, one control,
+ * N <= 16) and the entries-in-registers chains (csrc/kq_lanes.cuh, "lanes" option:
+ * few objectives, up to four controls and five terms, N <= 32 with at most four
+ * non-zero entries per row -- kq_problem.row_nnz --, first order, one GPU: chi
+ * boundary, time-parallel backward sweep, pre-pass, update chain, tau).
+ * Returns KQ_ERR_UNSUPPORTED when the problem is outside these
+ * families (fixed point: N in 2..4, M = 2, L = 1, state stores fit shared memory):
+ * use the four-call sequence then.  If the fixed-point
  * iteration does not converge ("picard_maxit" option) the outputs are left
  * untouched, workspace status word 1 is set to `epoch` and word 3 to the first
  * such epoch; word 2 holds the number of fixed-point rounds of the last
