@@ -39,12 +39,13 @@ for line in open(src, errors='replace'):
             fam[kern][op] += 0
 interesting = ['DFMA', 'DADD', 'DMUL', 'SHFL', 'LDS', 'STS', 'LDG', 'STG', 'BAR', 'WARPSYNC',
                'UBLKCP', 'SYNCS', 'LDGSTS', 'CREDUX', 'ACQBULK', 'PREEXIT', 'LDL', 'STL',
-               'UTMALDG', 'DMMA', 'HMMA', 'UTCHMMA', 'LDTM', 'MUFU']
+               'UTMALDG', 'DMMA', 'HMMA', 'UTCHMMA', 'LDTM', 'MUFU', 'REDG', 'ATOMG']
 with open(out, 'w') as fh:
     fh.write("SASS census of krotov_b200/csrc/libkrotov_b200.so (cuobjdump -sass, sm_100a), static instruction\n"
              "counts summed over all instantiations of a kernel family.  UBLKCP = cp.async.bulk (TMA bulk copy),\n"
              "SYNCS = mbarrier ops, LDGSTS = cp.async, CREDUX = warp integer reduction (redux.sync), ACQBULK / PREEXIT =\n"
-             "griddepcontrol.wait / launch_dependents, LDL / STL = local-memory (spill) traffic.  There is no\n"
+             "griddepcontrol.wait / launch_dependents, LDL / STL = local-memory (spill) traffic, REDG = reductions performed at L2\n"
+             "(red.global.max.u64: slot publication of k_fwupd_sat).  There is no\n"
              "tensor-core instruction (DMMA / UTC*MMA / LDTM): the arithmetic is complex128 on the FP64 pipe.\n\n")
     fh.write("%-38s %6s " % ("family", "#inst") + " ".join("%8s" % c for c in interesting) + "\n")
     for f in sorted(fam):
