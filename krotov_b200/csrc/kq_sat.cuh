@@ -69,20 +69,44 @@ struct SatObj {
   bool driven;
 };
 
-// rare path, out of line: sin and cos of the trace phase (by value: the objectives must stay
-// in registers)
-static __device__ __noinline__ double2 sat_phase(double t) {
-  double st, ct;
-  sincos(t, &st, &ct);
-  return make_double2(st, ct);
+struct SatPhi {
+  cplx p0, p1;
+};
+// General step, out of line (by value: the objectives must stay in registers): generators
+// with a trace (phase e^{it}), repeated scaled steps, any series degree.
+static __device__ __noinline__ SatPhi sat_step_general(SatPhi v, double dl, double b, double c,
+                                                       double t, int P, int s) {
+  const double z = fma(dl, dl, b * c);
+  double C = c_kq_tables.invfact[2 * (P - 1)], S = c_kq_tables.invfact[2 * (P - 1) + 1];
+  for (int j = P - 2; j >= 0; --j) {
+    C = fma(-z, C, c_kq_tables.invfact[2 * j]);
+    S = fma(-z, S, c_kq_tables.invfact[2 * j + 1]);
+  }
+  const double Sd = S * dl, Sb = S * b, Sc = S * c;
+  double st = 0.0, ct = 1.0;
+  if (t != 0.0) sincos(t, &st, &ct);
+  for (int rep = 0; rep < s; ++rep) {
+    cplx u0 = make_double2(fma(-Sd, v.p0.y, fma(-Sb, v.p1.y, C * v.p0.x)),
+                           fma(Sd, v.p0.x, fma(Sb, v.p1.x, C * v.p0.y)));
+    cplx u1 = make_double2(fma(Sd, v.p1.y, fma(-Sc, v.p0.y, C * v.p1.x)),
+                           fma(-Sd, v.p1.x, fma(Sc, v.p0.x, C * v.p1.y)));
+    if (t != 0.0) {
+      u0 = make_double2(fma(-st, u0.y, ct * u0.x), fma(st, u0.x, ct * u0.y));
+      u1 = make_double2(fma(-st, u1.y, ct * u1.x), fma(st, u1.x, ct * u1.y));
+    }
+    v.p0 = u0;
+    v.p1 = u1;
+  }
+  return v;
 }
 
-// phi <- exp(i R)^s phi for the thread's objectives TOGETHER: straight-line code with the
-// series degree as a template parameter (coefficients are immediates, the independent chains
-// of the objectives interleave); h is the step already divided by s.
+// phi <- exp(i R) phi for the thread's objectives TOGETHER, traceless generators and one
+// unscaled step (the CTA-uniform common case): straight-line code with the series degree as a
+// template parameter (coefficients are immediates, the independent chains of the objectives
+// interleave).
 template <int P>
-__device__ __forceinline__ void sat_step(SatObj (&o)[KQ_SAT_OPT], double h, double heps_new, int s) {
-  double dl[KQ_SAT_OPT], b[KQ_SAT_OPT], c[KQ_SAT_OPT], t[KQ_SAT_OPT], z[KQ_SAT_OPT];
+__device__ __forceinline__ void sat_step_fast(SatObj (&o)[KQ_SAT_OPT], double h, double heps_new) {
+  double dl[KQ_SAT_OPT], b[KQ_SAT_OPT], c[KQ_SAT_OPT], z[KQ_SAT_OPT];
   double C[KQ_SAT_OPT], S[KQ_SAT_OPT];
 #pragma unroll
   for (int q = 0; q < KQ_SAT_OPT; ++q) {
@@ -90,7 +114,6 @@ __device__ __forceinline__ void sat_step(SatObj (&o)[KQ_SAT_OPT], double h, doub
     dl[q] = fma(heps, o[q].d1, h * o[q].d0);
     b[q] = fma(heps, o[q].b1, h * o[q].b0);
     c[q] = fma(heps, o[q].c1, h * o[q].c0);
-    t[q] = fma(heps, o[q].t1, h * o[q].t0);
     z[q] = fma(dl[q], dl[q], b[q] * c[q]);
     C[q] = kq_inv_fact(2 * (P - 1));
     S[q] = kq_inv_fact(2 * (P - 1) + 1);
@@ -106,34 +129,17 @@ __device__ __forceinline__ void sat_step(SatObj (&o)[KQ_SAT_OPT], double h, doub
 #pragma unroll
   for (int q = 0; q < KQ_SAT_OPT; ++q) {
     const double Sd = S[q] * dl[q], Sb = S[q] * b[q], Sc = S[q] * c[q], Cq = C[q];
-    double st = 0.0, ct = 1.0;
-    if (t[q] != 0.0) {   // traceless generators (two-level systems) skip the phase
-      const double2 sc = sat_phase(t[q]);
-      st = sc.x;
-      ct = sc.y;
-    }
-    cplx v0 = o[q].phi[0], v1 = o[q].phi[1];
-#pragma unroll 1
-    for (int rep = 0; rep < s; ++rep) {
-      cplx u0 = make_double2(fma(-Sd, v0.y, fma(-Sb, v1.y, Cq * v0.x)),
-                             fma(Sd, v0.x, fma(Sb, v1.x, Cq * v0.y)));
-      cplx u1 = make_double2(fma(Sd, v1.y, fma(-Sc, v0.y, Cq * v1.x)),
-                             fma(-Sd, v1.x, fma(Sc, v0.x, Cq * v1.y)));
-      if (t[q] != 0.0) {
-        u0 = make_double2(fma(-st, u0.y, ct * u0.x), fma(st, u0.x, ct * u0.y));
-        u1 = make_double2(fma(-st, u1.y, ct * u1.x), fma(st, u1.x, ct * u1.y));
-      }
-      v0 = u0;
-      v1 = u1;
-    }
-    o[q].phi[0] = v0;
-    o[q].phi[1] = v1;
+    const cplx v0 = o[q].phi[0], v1 = o[q].phi[1];
+    o[q].phi[0] = make_double2(fma(-Sd, v0.y, fma(-Sb, v1.y, Cq * v0.x)),
+                               fma(Sd, v0.x, fma(Sb, v1.x, Cq * v0.y)));
+    o[q].phi[1] = make_double2(fma(Sd, v1.y, fma(-Sc, v0.y, Cq * v1.x)),
+                               fma(-Sd, v1.x, fma(Sc, v0.x, Cq * v1.y)));
   }
 }
 
 // CTA = warp 0 (exchange) + warp 1 (TMA producer) + KQ_SAT_BT consumer threads.
 // shared: red [2][16] | gpart [2][8] (+ pad) | mbar [RING] | empty [RING] | sdt, sg, ssl, sbound [KQ_NTC] |
-//         splan [KQ_NTC] | ring [RING][kpc][2] | M [kpc][4] (||chi|| mu^T, real)
+//         splan [KQ_NTC] | ring [RING][kpc][2] | M [kpc + 1][4] (||chi|| mu^T, real; last row zero)
 __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepArgs a, int kpc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   if (a.cond_epoch && *reinterpret_cast<volatile int*>(a.status + 1) != (int)a.cond_epoch) return;
@@ -220,25 +226,29 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
       Oc = fmax(Oc, o[q].driven ? 0.0 : o[q].fixed * a.op_norm[k * 2 + 1]);
     }
   }
-  // weight-zero threads of a CTA with objectives read objective 0's matrix; idle CTAs zeros
-  if (kcta == 0 && tid < 4) sM[tid] = 0.0;
+  // padding threads read the zero matrix behind the last objective: their eta is zero
+  if (tid < 4) sM[(size_t)kpc * 4 + tid] = 0.0;
   O0 = block_max(O0, red);
   O1 = block_max(O1, red);
   Oc = block_max(Oc, red);
+  double trace = 0.0;
+#pragma unroll
+  for (int q = 0; q < KQ_SAT_OPT; ++q) trace = fmax(trace, fabs(o[q].t0) + fabs(o[q].t1));
+  const bool has_trace = block_max(trace, red) > 0.0;
   const double lam = a.lambda_a[0];
   // eta = mu^dag chi ||chi|| of the row in ring stage `st`; padding threads (q-th objective
   // beyond kcta) get zero through `w`
-  double w[KQ_SAT_OPT];
+  int km[KQ_SAT_OPT];
 #pragma unroll
-  for (int q = 0; q < KQ_SAT_OPT; ++q) w[q] = (!xwarp && ctid + q * KQ_SAT_BT < kcta) ? 1.0 : 0.0;
+  for (int q = 0; q < KQ_SAT_OPT; ++q) km[q] = (!xwarp && ctid + q * KQ_SAT_BT < kcta) ? kl[q] : kpc;
   auto make_eta_q = [&](int st, int q, cplx (&dst)[KQ_SAT_OPT][2]) {
     const cplx* row = ring + st * stage + (size_t)kl[q] * 2;
     const cplx x0 = row[0], x1 = row[1];
-    const double2 m0 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4);
-    const double2 m1 = *reinterpret_cast<const double2*>(sM + (size_t)kl[q] * 4 + 2);
+    const double2 m0 = *reinterpret_cast<const double2*>(sM + (size_t)km[q] * 4);
+    const double2 m1 = *reinterpret_cast<const double2*>(sM + (size_t)km[q] * 4 + 2);
     // eta_c = sum_r M[c][r] chi_r (element (r, c) of mu at c * 2 + r)
-    dst[q][0] = make_double2(w[q] * fma(m0.x, x0.x, m0.y * x1.x), w[q] * fma(m0.x, x0.y, m0.y * x1.y));
-    dst[q][1] = make_double2(w[q] * fma(m1.x, x0.x, m1.y * x1.x), w[q] * fma(m1.x, x0.y, m1.y * x1.y));
+    dst[q][0] = make_double2(fma(m0.x, x0.x, m0.y * x1.x), fma(m0.x, x0.y, m0.y * x1.y));
+    dst[q][1] = make_double2(fma(m1.x, x0.x, m1.y * x1.x), fma(m1.x, x0.y, m1.y * x1.y));
   };
   auto make_eta = [&](int st, cplx (&dst)[KQ_SAT_OPT][2]) {
 #pragma unroll
@@ -394,13 +404,27 @@ __global__ void __launch_bounds__(KQ_SAT_THREADS, 1) k_fwupd_sat(const KqSweepAr
       const int P = max(2, (m + 4) >> 1);   // 2P >= m + 3; P > 12 (scaled norm close to 1) runs 18
       const double h = (s == 1) ? dt_cur : dt_cur / (double)s;
       const double heps = h * eps_new;
-      // a few degrees only (more terms than needed cost two DFMA each; every variant is
-      // straight-line code in the loop body, and the loop has to stay in the instruction cache)
-      if (P <= 3) sat_step<3>(o, h, heps, s);
-      else if (P <= 5) sat_step<5>(o, h, heps, s);
-      else if (P <= 8) sat_step<8>(o, h, heps, s);
-      else if (P <= 12) sat_step<12>(o, h, heps, s);
-      else sat_step<18>(o, h, heps, s);
+      if (s == 1 && !has_trace) {
+        // a few degrees only (more terms than needed cost two DFMA each; every variant is
+        // straight-line code in the loop body, and the loop should stay in the instruction cache)
+        if (P <= 3) sat_step_fast<3>(o, h, heps);
+        else if (P <= 5) sat_step_fast<5>(o, h, heps);
+        else if (P <= 8) sat_step_fast<8>(o, h, heps);
+        else if (P <= 12) sat_step_fast<12>(o, h, heps);
+        else sat_step_fast<18>(o, h, heps);
+      } else {
+#pragma unroll
+        for (int q = 0; q < KQ_SAT_OPT; ++q) {
+          const double hq = o[q].driven ? heps : h * o[q].fixed;
+          SatPhi v;
+          v.p0 = o[q].phi[0];
+          v.p1 = o[q].phi[1];
+          v = sat_step_general(v, fma(hq, o[q].d1, h * o[q].d0), fma(hq, o[q].b1, h * o[q].b0),
+                               fma(hq, o[q].c1, h * o[q].c0), fma(hq, o[q].t1, h * o[q].t0), P, s);
+          o[q].phi[0] = v.p0;
+          o[q].phi[1] = v.p1;
+        }
+      }
 #pragma unroll
       for (int q = 0; q < KQ_SAT_OPT; ++q) {
         o[q].eta[0] = eta_next[q][0];

@@ -6,7 +6,7 @@ KQ_DEFINE_TABLES_UPLOAD(kq_tables_upload_sat)
 
 size_t kq_sat_smem(int kpc) {
   return 56 * sizeof(double) + 2 * KQ_SAT_RING * sizeof(uint64_t) + 4 * KQ_NTC * sizeof(double) + KQ_NTC +
-         (size_t)KQ_SAT_RING * kpc * 2 * sizeof(cplx) + (size_t)kpc * 4 * sizeof(double);
+         (size_t)KQ_SAT_RING * kpc * 2 * sizeof(cplx) + (size_t)(kpc + 1) * 4 * sizeof(double);
 }
 
 // objectives per CTA: at most KQ_SAT_BT * KQ_SAT_OPT; 0 if the problem does not fit `sms` CTAs
