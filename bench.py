@@ -648,6 +648,35 @@ def e2e_run(krotov, wl, steps, warmup, parallel_map=None, dist=None,
             "measured_total_d2h_bytes": res.d2h_bytes}, res
 
 
+def notebook_entry(krotov, args, factory, kwargs, flush):
+    """One of the reference's notebook-shaped problems on one B200: device
+    timed iterations (one kq_krotov_iteration call each), the same through
+    optimize_pulses with a host hook, and the numpy port on one core."""
+    w = getattr(krotov.workloads, factory)(**kwargs)
+    d = DeviceRun(krotov, w, engine=args.engine, flush_t=flush)
+    steps = min(args.steps, 10)
+    r = d.run(steps, 3)
+    ee, _ = e2e_run(krotov, w, steps, 3)
+    entry = {
+        "workload": w.name, "K": w.K, "N": d.cp.N, "L": d.cp.L, "nt": w.nt,
+        "value": 1e3 / r['ms_per_step'], "unit": UNIT,
+        "ms_per_step": r['ms_per_step'],
+        "engine": "fused" if r['fused'] else "sweeps",
+        "gpu_launches": r['launches'],
+        "e2e": {k: ee[k] for k in ("value", "unit", "h2d_bytes_per_step",
+                                   "d2h_bytes_per_step", "whole_call_value")},
+    }
+    d.close()
+    if not args.no_cpu:
+        per_iter, ks = time_oracle(w, 1)
+        entry["cpu_baseline"] = {
+            "value": 1.0 / per_iter, "unit": UNIT, "cores": 1, "kind": "port",
+            "host_cpus": os.cpu_count(),
+            "sample": "1 Krotov iteration of the full workload (numpy port, "
+                      "serial, one BLAS thread)"}
+    return entry
+
+
 def saturating_entry(krotov, args, peaks, which, K=131072):
     """One B200, C4's physics with K = 131 072 objectives (backward-state
     store 4.2 GB): whole Krotov iterations through the sweep calls, device
@@ -1000,6 +1029,20 @@ def run_ours(args):
                     entry["cpu_baseline"] = port
                     entry["cpu_baseline_reference"] = ref
                 configs[lab] = entry
+            except Exception as exc:  # pragma: no cover
+                configs[lab] = {"unavailable": repr(exc)}
+        # -- the reference's notebook-shaped problems: several controls per
+        # objective (notebooks 03 / 08) and the 17-level transmon (notebook 05)
+        for lab, factory, kw in (
+                ('nb03_lambda_4controls', 'lambda_system',
+                 dict(nt=500, gamma=0.5)),
+                ('nb08_lambda_ensemble', 'lambda_system',
+                 dict(nt=500, gamma=0.0, lambda_a=0.5,
+                      ensemble_mu=[0.9, 0.95, 1.0, 1.05, 1.1])),
+                ('nb05_transmon_N17', 'transmon_xgate',
+                 dict(nstates=8, nt=1000))):
+            try:
+                configs[lab] = notebook_entry(krotov, args, factory, kw, flush)
             except Exception as exc:  # pragma: no cover
                 configs[lab] = {"unavailable": repr(exc)}
         # -- the same physics with K = 131 072 objectives: the
