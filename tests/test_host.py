@@ -535,3 +535,27 @@ def test_perfect_entangler_functional():
     for l in range(4):
         assert chis[l].shape == (4, 1)
         assert np.allclose(chis[l].ravel(), -(d[:, l] @ bell))
+
+
+def test_row_nnz_of_compiled_problems():
+    """kq_problem.row_nnz (largest number of non-zero columns in a row of an
+    objective's terms taken together, diagonal included) selects the
+    entries-in-registers kernels (csrc/kq_lanes.cuh) for sparse rows."""
+    import krotov_b200 as krotov
+    from krotov_b200.compiler import compile_problem, initialize_controls
+
+    def row_nnz(wl):
+        objs = wl.objectives(krotov.Objective)
+        controls, _, _, mapping, _, _ = initialize_controls(
+            objs, wl.pulse_options, wl.tlist)
+        return compile_problem(objs, controls, mapping, wl.tlist).row_nnz
+
+    W = krotov.workloads
+    # ladder: diagonal drift + tridiagonal drive
+    assert row_nnz(W.transmon_xgate(nstates=8, nt=20)) == 3
+    # Lambda system: 1-2 and 2-3 couplings, diagonal detunings
+    assert row_nnz(W.lambda_system(nt=20, gamma=0.5)) == 3
+    # two-level systems are dense
+    assert row_nnz(W.tls_ensemble(K=3, nt=20)) == 2
+    # the two-qubit gate Hamiltonian of C3 couples every level to three others
+    assert 2 <= row_nnz(W.two_qubit_gate(nt=20)) <= 4
