@@ -332,8 +332,11 @@ int kq_fetch_results(void* dst_host, const void* src_device, size_t nbytes,
 int kq_overlaps(int32_t K, int32_t N, const kq_c128* a, const kq_c128* b,
                 kq_c128* out, void* stream);
 
-/* Introspection for tests / bench: kernel family chosen for a problem
- * (0 = thread-per-objective, 1 = lane-per-row) and its launch geometry. */
+/* Introspection for tests / bench: kernel family the sequential update sweep of
+ * kq_sweep_forward_update uses for a problem on a 148-SM device (0 = thread per
+ * objective, 1 = lane per row, 2 = row per thread on CSR matrices, 3 = entries in
+ * registers -- csrc/kq_lanes.cuh --, 4 = many-objective sweep -- csrc/kq_sat.cuh)
+ * and its launch geometry. */
 int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid,
             int32_t* block, int32_t* smem_bytes);
 

@@ -1262,6 +1262,25 @@ int kq_plan(const kq_problem* p, int32_t* family, int32_t* grid, int32_t* block,
   Plan pl;
   rc = make_plan(p, true, false, 148, pl);
   if (rc) return rc;
+  {
+    // the families that stand in front of the generic kernels (launch_sequential_update)
+    KqSweepArgs probe = base_args(p);
+    KqLanes ln;
+    const bool generic = pl.family == 1 || (pl.family == 0 && !pl.spec);
+    if (generic && (pl.family == 0 || p->row_nnz > 0) && lanes_plan(p, probe, ln)) {
+      pl.family = 3;
+      pl.grid = 1;
+      pl.block = ln.W * 32;
+      pl.smem = 2 * KQ_LN_LMAX * 8 * sizeof(double);
+    } else if (pl.family == 0 && pl.spec && g_sat && p->real_ops && !p->is_super && p->N == 2 &&
+               pl.grid > 1 && kq_sat_kpc(p->K, 148)) {
+      const int kpc = kq_sat_kpc(p->K, 148);
+      pl.family = 4;
+      pl.grid = (p->K + kpc - 1) / kpc;
+      pl.block = 512;
+      pl.smem = kq_sat_smem(kpc);
+    }
+  }
   if (family) *family = pl.family;
   if (grid) *grid = pl.grid;
   if (block) *block = pl.block;

@@ -184,6 +184,7 @@ int kq_launch_prop_lanes(const KqSweepArgs& a, const KqLanes& d, int fsel, int n
 // update sweep for many two-level objectives with a real generator (kq_sat.cuh)
 extern int g_kq_sat_min_kpc;   // kq_set_option("sat_min_kpc", v)
 int kq_sat_kpc(int K, int sms);
+size_t kq_sat_smem(int kpc);
 int kq_launch_sat(const KqSweepArgs& a, int sms, cudaStream_t st);
 // delta-polynomial update sweep (kq_dpoly.cuh)
 struct KqDpoly;

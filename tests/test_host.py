@@ -559,3 +559,28 @@ def test_row_nnz_of_compiled_problems():
     assert row_nnz(W.tls_ensemble(K=3, nt=20)) == 2
     # the two-qubit gate Hamiltonian of C3 couples every level to three others
     assert 2 <= row_nnz(W.two_qubit_gate(nt=20)) <= 4
+
+
+def test_kq_plan_reports_the_kernel_families():
+    """kq_plan is host-only introspection: which family the update sweep of a
+    problem runs on (include/krotov_b200.h)."""
+    import ctypes
+    from krotov_b200 import _lib
+    lib = _lib.load()
+
+    def family(K, N, NT, L, M, real=0, nnz=0):
+        p = _lib.KqProblem(K=K, N=N, NT=NT, L=L, M=M, is_super=0, ops=1,
+                           ops_adj=1, mu=1, term2pulse=1, op_norm=1, dt=1,
+                           shape=1, lambda_a=1, real_ops=real, reserved=0,
+                           update_sweep=0, row_nnz=nnz, sparse=None)
+        v = [ctypes.c_int32() for _ in range(4)]
+        assert lib.kq_plan(ctypes.byref(p),
+                           *[ctypes.byref(x) for x in v]) == 0
+        return v[0].value, v[1].value, v[2].value
+
+    assert family(128, 2, 999, 1, 2, real=1)[0] == 0          # C4
+    assert family(131072, 2, 999, 1, 2, real=1) == (4, 148, 512)   # kq_sat
+    assert family(5, 3, 499, 4, 5, nnz=3) == (3, 1, 32)       # Lambda ensemble
+    assert family(2, 17, 999, 1, 2, real=1, nnz=3) == (3, 1, 64)   # transmon
+    assert family(2, 17, 999, 1, 2, real=1, nnz=0)[0] == 1    # dense rows
+    assert family(300, 3, 499, 4, 5, nnz=3)[0] == 0           # too many lanes
